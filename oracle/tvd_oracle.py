@@ -1,0 +1,461 @@
+"""NumPy restatement of DarSIA's split-Bregman TV denoising hot path.
+
+TEST INFRASTRUCTURE ONLY (see ``oracle/__init__.py``): the checker for the CUDA
+path and the timed CPU arm of ``bench.py``.  Never imported by ``darsia_b200``.
+
+Every function cites the reference lines it restates (paths relative to
+``/root/reference/src/darsia/``).  The arithmetic follows SURVEY.md Appendix A;
+the *order* of floating-point operations follows the reference so that the
+restatement agrees with the verbatim reference to round-off (pinned by
+``tests/golden``; see ``tests/test_oracle_golden.py``).
+
+Deliberate, documented differences from the reference:
+
+* Q2  a fresh solver state per call (the reference caches ``const_diag`` in a
+      shared default ``Jacobi()`` instance and never invalidates it);
+* Q3  the isotropic shrinkage follows the loop body / docstring of the Numba
+      kernel (``restoration/split_bregman_tvd.py:107-126``) but for any spatial
+      dimension, dtype and per-voxel ``mu/ell``;
+* Q4  ``CG.tol`` is SciPy's relative tolerance (``rtol``; ``tol=`` was removed
+      in SciPy 1.14) and the CG recurrence of ``scipy.sparse.linalg.cg``
+      (third party, version unpinned by the reference; restated from SciPy
+      1.18.1 ``_isolve/iterative.py``) is written out here;
+* Q5/Q6 trailing (non-spatial) axes are independent problems, solved slice by
+      slice exactly as ``restoration/h1_regularization.py:54-67`` does.
+"""
+
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple, Union
+
+import numpy as np
+
+Coeff = Union[float, int, np.ndarray]
+
+
+# --------------------------------------------------------------------------- #
+# Finite differences (utils/derivatives.py)
+# --------------------------------------------------------------------------- #
+def _axis_slice(ndim: int, axis: int, start, stop) -> tuple:
+    """Index tuple selecting ``start:stop`` along ``axis`` (utils/array_slice.py:14-35)."""
+    idx = [slice(None)] * ndim
+    idx[axis] = slice(start, stop)
+    return tuple(idx)
+
+
+def backward_diff(x: np.ndarray, axis: int, dim: int = 2) -> np.ndarray:
+    """``G_a x[k] = x[k+1] - x[k]`` and 0 in the last slice.
+
+    Restates utils/derivatives.py:16-37 (``np.diff`` with the last slice appended).
+    """
+    assert axis < dim, "axis must be smaller than dimension"
+    out = np.zeros_like(x)
+    n = x.shape[axis]
+    if n > 1:
+        out[_axis_slice(x.ndim, axis, 0, n - 1)] = (
+            x[_axis_slice(x.ndim, axis, 1, n)] - x[_axis_slice(x.ndim, axis, 0, n - 1)]
+        )
+    return out
+
+
+def forward_diff(x: np.ndarray, axis: int, dim: int = 2) -> np.ndarray:
+    """``H_a x[k] = x[k] - x[k-1]`` and 0 in the first slice.
+
+    Restates utils/derivatives.py:40-59 (``np.diff`` with the first slice prepended).
+    """
+    assert axis < dim, "axis must be smaller than dimension"
+    out = np.zeros_like(x)
+    n = x.shape[axis]
+    if n > 1:
+        out[_axis_slice(x.ndim, axis, 1, n)] = (
+            x[_axis_slice(x.ndim, axis, 1, n)] - x[_axis_slice(x.ndim, axis, 0, n - 1)]
+        )
+    return out
+
+
+def laplace(x: np.ndarray, dim: int = 2, diffusion_coeff: Coeff = 1) -> np.ndarray:
+    """``L x = sum_a 1/2 [ G_a(l * H_a x) + H_a(l * G_a x) ]`` with ``h = None``.
+
+    Restates utils/derivatives.py:62-104 (the ``axis is None`` branch used by
+    ``CG``).  Boundary rows get half weight.
+    """
+    if isinstance(diffusion_coeff, np.ndarray):
+        assert diffusion_coeff.shape == x.shape
+    lap = np.zeros_like(x)
+    for ax in range(dim):
+        lap += 0.5 * (
+            backward_diff(diffusion_coeff * forward_diff(x, ax, dim), ax, dim)
+            + forward_diff(diffusion_coeff * backward_diff(x, ax, dim), ax, dim)
+        )
+    return lap
+
+
+# --------------------------------------------------------------------------- #
+# Jacobi (utils/linear_solvers/jacobi.py)
+# --------------------------------------------------------------------------- #
+def neighbor_accumulation(x: np.ndarray) -> np.ndarray:
+    """Sum of the 2*ndim edge-replicated neighbours (jacobi.py:25-55).
+
+    The order of the additions per entry is the reference's: for each axis the
+    lower neighbour (or the entry itself in the first slice) is added before the
+    upper neighbour (or the entry itself in the last slice).
+    """
+    acc = np.zeros_like(x)
+    nd = x.ndim
+    for ax in range(nd):
+        n = x.shape[ax]
+        acc[_axis_slice(nd, ax, 0, 1)] += x[_axis_slice(nd, ax, 0, 1)]
+        acc[_axis_slice(nd, ax, 1, n)] += x[_axis_slice(nd, ax, 0, n - 1)]
+        acc[_axis_slice(nd, ax, 0, n - 1)] += x[_axis_slice(nd, ax, 1, n)]
+        acc[_axis_slice(nd, ax, n - 1, n)] += x[_axis_slice(nd, ax, n - 1, n)]
+    return acc
+
+
+def jacobi_sweep(
+    x: np.ndarray, rhs: np.ndarray, omega: Coeff, ell: Coeff, dim: int
+) -> np.ndarray:
+    """One sweep ``x <- rhs/diag + N(x)/(diag/ell)``, ``diag = omega + 2*dim*ell``.
+
+    Restates jacobi.py:57-72 (diag, ``h = 1``) and :101-114 (sweep).
+    """
+    diag = omega + ell * 2 * dim / 1.0**2
+    diag_scaled = np.divide(diag, ell / 1.0**2)
+    return np.divide(rhs, diag) + np.divide(neighbor_accumulation(x), diag_scaled)
+
+
+class Solver:
+    """Parameter carrier (utils/linear_solvers/solver.py:12-72)."""
+
+    def __init__(
+        self,
+        maxiter: int = 1,
+        tol: Optional[float] = None,
+        dim: int = 2,
+        mass_coeff: Optional[Coeff] = None,
+        diffusion_coeff: Optional[Coeff] = None,
+        verbose: bool = False,
+    ) -> None:
+        self.dim = dim
+        self.maxiter = maxiter
+        self.tol = tol
+        self.mass_coeff = mass_coeff
+        self.diffusion_coeff = diffusion_coeff
+        self.verbose = verbose
+
+    def update_params(self, dim=None, mass_coeff=None, diffusion_coeff=None) -> None:
+        """solver.py:40-58."""
+        self.dim = dim if dim is not None else self.dim
+        self.mass_coeff = mass_coeff if mass_coeff is not None else self.mass_coeff
+        self.diffusion_coeff = (
+            diffusion_coeff if diffusion_coeff is not None else self.diffusion_coeff
+        )
+
+    def reset(self) -> None:
+        """Forget per-call cached state (fresh-solver-per-call semantics)."""
+
+    def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:  # pragma: no cover
+        raise NotImplementedError
+
+
+class Jacobi(Solver):
+    """Matrix-free Jacobi for ``omega x - ell Lap x = rhs`` (jacobi.py:74-133).
+
+    ``diag`` and ``diag/ell`` are cached on the first sweep after ``reset()`` and
+    NOT refreshed by ``update_params`` -- this is the reference's behaviour within
+    one ``split_bregman_tvd`` call (jacobi.py:101-106; it is why ``adaptive`` never
+    changes Jacobi's diagonal).  ``split_bregman_tvd`` calls ``reset()`` first, so
+    nothing leaks between calls.
+    """
+
+    def reset(self) -> None:
+        self._diag = None
+        self._diag_scaled = None
+
+    def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+        omega, ell, dim = self.mass_coeff, self.diffusion_coeff, self.dim
+        if getattr(self, "_diag", None) is None:
+            self._diag = omega + ell * 2 * dim / 1.0**2
+            self._diag_scaled = np.divide(self._diag, ell / 1.0**2)
+        diag, diag_scaled = self._diag, self._diag_scaled
+        rhs_scaled = np.divide(rhs, diag)
+        x = x0
+        if self.tol is None:
+            for _ in range(self.maxiter):
+                x = rhs_scaled + np.divide(neighbor_accumulation(x), diag_scaled)
+        else:
+            # jacobi.py:118-131: on convergence the PREVIOUS iterate is returned and
+            # the error is normalised by ||x0||.
+            for _ in range(self.maxiter):
+                x_new = rhs_scaled + np.divide(neighbor_accumulation(x), diag_scaled)
+                err = np.linalg.norm(x_new - x) / np.linalg.norm(x0)
+                if err < self.tol:
+                    break
+                x = x_new
+        return x
+
+
+# --------------------------------------------------------------------------- #
+# CG (utils/linear_solvers/cg.py + scipy.sparse.linalg.cg)
+# --------------------------------------------------------------------------- #
+def cg_matvec(x: np.ndarray, omega: Coeff, ell: Coeff, dim: int) -> np.ndarray:
+    """``A x = omega*x - laplace(x, dim, h=None, diffusion_coeff=ell)`` (cg.py:37-44)."""
+    return omega * x - laplace(x, dim=dim, diffusion_coeff=ell)
+
+
+class CG(Solver):
+    """CG for ``(omega - L_ell) x = rhs`` with SciPy's recurrence written out.
+
+    Restates utils/linear_solvers/cg.py:16-59 and ``scipy.sparse.linalg.cg``
+    (SciPy 1.18.1, ``_isolve/iterative.py``): ``atol = max(0, rtol*||b||)``; return
+    ``b`` if ``||b|| == 0``; ``r = b - A x`` (``b.copy()`` if ``x`` is all zero);
+    per iteration: stop if ``||r|| < atol``; ``rho = r.r``; ``p = r`` (first) or
+    ``p = (rho/rho_prev) p + r``; ``q = A p``; ``alpha = rho/(p.q)``;
+    ``x += alpha p``; ``r -= alpha q``.
+    """
+
+    def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+        assert x0.shape == rhs.shape
+        if self.tol is None:
+            raise TypeError("CG requires a numeric tol (SciPy rejects rtol=None); use tol=0.0 for a fixed count")
+        omega, ell, dim = self.mass_coeff, self.diffusion_coeff, self.dim
+        shape = x0.shape
+
+        def matvec(v: np.ndarray) -> np.ndarray:
+            return cg_matvec(v.reshape(shape), omega, ell, dim).ravel()
+
+        b = rhs.ravel()
+        x = x0.ravel().copy()
+        bnrm2 = np.linalg.norm(b)
+        atol = max(0.0, float(self.tol) * float(bnrm2))
+        if bnrm2 == 0:
+            return b.reshape(shape).copy()
+        r = b - matvec(x) if x.any() else b.copy()
+        rho_prev, p = None, None
+        for iteration in range(self.maxiter):
+            if np.linalg.norm(r) < atol:
+                break
+            rho_cur = np.dot(r, r)
+            if iteration > 0:
+                beta = rho_cur / rho_prev
+                p *= beta
+                p += r
+            else:
+                p = r.copy()
+            q = matvec(p)
+            alpha = rho_cur / np.dot(p, q)
+            x += alpha * p
+            r -= alpha * q
+            rho_prev = rho_cur
+        return x.reshape(shape)
+
+
+# --------------------------------------------------------------------------- #
+# Shrinkage (restoration/split_bregman_tvd.py:80-81, 107-126)
+# --------------------------------------------------------------------------- #
+def shrink_anisotropic(t: np.ndarray, kappa: Coeff) -> np.ndarray:
+    """``sign(t) * max(|t| - kappa, 0)`` (split_bregman_tvd.py:80-81)."""
+    return np.maximum(np.abs(t) - kappa, 0) * np.sign(t)
+
+
+def shrink_isotropic(t: np.ndarray, kappa: Coeff) -> Tuple[np.ndarray, np.ndarray]:
+    """Vector shrinkage of ``t`` (component axis last) -> ``(d, b)``.
+
+    ``s = sqrt(sum_a t_a^2); phi = max(s - kappa, 0)/(s + 1e-18); d = t*phi;
+    b = t*(1 - phi)`` -- the loop body of the reference's Numba kernel
+    (split_bregman_tvd.py:116-126) for any dimension / dtype / per-voxel kappa.
+    """
+    s = np.zeros(t.shape[:-1], dtype=t.dtype)
+    for k in range(t.shape[-1]):
+        s = s + t[..., k] ** 2
+    s = s**0.5
+    phi = np.maximum(s - kappa, 0) / (s + 1e-18)
+    phi = np.asarray(phi, dtype=t.dtype)
+    d = t * phi[..., None]
+    b = t * (1 - phi)[..., None]
+    return d, b
+
+
+# --------------------------------------------------------------------------- #
+# Outer loop (restoration/split_bregman_tvd.py:14-177)
+# --------------------------------------------------------------------------- #
+def _split_bregman_single(
+    img: np.ndarray,
+    mu: Coeff,
+    omega: Coeff,
+    ell: Coeff,
+    dim: int,
+    max_num_iter: int,
+    eps: Optional[float],
+    x0,
+    isotropic: bool,
+    solver: Solver,
+    adaptive: Optional[Callable[[int], bool]],
+    history: Optional[list],
+) -> np.ndarray:
+    """One independent ``dim``-dimensional problem (``img.ndim == dim``)."""
+    assert img.ndim == dim
+    img_nrm = np.linalg.norm(img)  # :58
+    solver.reset()
+    solver.update_params(mass_coeff=omega, diffusion_coeff=ell, dim=dim)  # :64-68
+
+    def rhs_function(d, b, ell_t):  # :84-89
+        result = np.multiply(omega, img)
+        for i in range(dim):
+            result = result + forward_diff(ell_t * (b[..., i] - d[..., i]), i, dim)
+        return result
+
+    if x0 is not None:  # :93-97
+        u, d, b = x0
+        u = np.array(u, dtype=img.dtype, copy=True)
+        d = np.array(d, dtype=img.dtype, copy=True)
+        b = np.array(b, dtype=img.dtype, copy=True)
+    else:  # :99-101
+        u = img.copy()
+        d = np.zeros((*img.shape, dim), dtype=img.dtype)
+        b = np.zeros((*img.shape, dim), dtype=img.dtype)
+
+    for it in range(max_num_iter):  # :129
+        u_new = solver(x0=u, rhs=rhs_function(d, b, ell))  # :133
+        kappa = mu / ell
+        if isotropic:  # :136-140
+            t = b.copy()
+            for j in range(dim):
+                t[..., j] += backward_diff(u_new, j, dim)
+            d, b = shrink_isotropic(t, kappa)
+        else:  # :142-146
+            for j in range(dim):
+                t = backward_diff(u_new, j, dim) + b[..., j]
+                d[..., j] = shrink_anisotropic(t, kappa)
+                b[..., j] = t - d[..., j]
+        if adaptive is not None and adaptive(it):  # :149-158
+            grad1 = np.zeros(img.shape, dtype=img.dtype)
+            for j in range(dim):
+                grad1 = grad1 + np.abs(backward_diff(u_new, j, dim))
+            ell = 1.0 / np.maximum(grad1, 1e-12)
+            solver.update_params(mass_coeff=omega, diffusion_coeff=ell, dim=dim)
+        inc = np.linalg.norm(u_new - u) / img_nrm  # :161
+        if history is not None:
+            history.append(float(inc))
+        u = u_new.copy()  # :170
+        if eps is not None and inc < eps:  # :173-175
+            break
+    return u.astype(img.dtype, copy=False)  # :177 (float -> same float)
+
+
+def _coeff_slice(c: Coeff, idx: tuple, spatial_shape: tuple, full_shape: tuple) -> Coeff:
+    """Pick the coefficient for one trailing-axis slice (batching rule Q5/Q6)."""
+    if not isinstance(c, np.ndarray) or c.ndim == 0:
+        return c
+    if c.shape == spatial_shape:
+        return c
+    if c.shape == full_shape:
+        return c[(slice(None),) * len(spatial_shape) + idx]
+    raise AssertionError(f"coefficient shape {c.shape} matches neither {spatial_shape} nor {full_shape}")
+
+
+def split_bregman_tvd(
+    img: np.ndarray,
+    mu: Coeff = 1.0,
+    omega: Coeff = 1.0,
+    ell: Optional[Coeff] = None,
+    dim: int = 2,
+    max_num_iter: int = 100,
+    eps: Optional[float] = None,
+    x0=None,
+    isotropic: bool = False,
+    verbose: Union[bool, int] = False,
+    solver: Optional[Solver] = None,
+    adaptive=None,
+    history: Optional[list] = None,
+) -> np.ndarray:
+    """Restatement of ``darsia.split_bregman_tvd`` (split_bregman_tvd.py:14-177).
+
+    Trailing axes beyond ``dim`` are independent problems (Q5/Q6).  ``history``
+    (additive, test-only) collects the relative increments of every problem.
+    """
+    if not np.issubdtype(img.dtype, np.floating):
+        raise TypeError("float images only (SURVEY Q10)")
+    if solver is None:
+        solver = Jacobi()
+    if ell is None:  # :62-63
+        ell = 2 * mu
+    if img.ndim == dim:
+        return _split_bregman_single(
+            img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic, solver, adaptive, history
+        )
+    spatial = img.shape[:dim]
+    out = np.empty_like(img)
+    for idx in np.ndindex(img.shape[dim:]):
+        sel = (slice(None),) * dim + idx
+        x0_s = None
+        if x0 is not None:
+            u0, d0, b0 = x0
+            # d0, b0 are (*img.shape, dim): component axis last, batch axes before it
+            x0_s = (u0[sel], d0[sel + (slice(None),)], b0[sel + (slice(None),)])
+        hist = [] if history is not None else None
+        out[sel] = _split_bregman_single(
+            np.ascontiguousarray(img[sel]),
+            _coeff_slice(mu, idx, spatial, img.shape),
+            _coeff_slice(omega, idx, spatial, img.shape),
+            _coeff_slice(ell, idx, spatial, img.shape),
+            dim,
+            max_num_iter,
+            eps,
+            x0_s,
+            isotropic,
+            solver,
+            adaptive,
+            hist,
+        )
+        if history is not None:
+            history.append(hist)
+    return out
+
+
+# --------------------------------------------------------------------------- #
+# Entry point (restoration/tvd.py)
+# --------------------------------------------------------------------------- #
+class TVD:
+    """Restatement of ``darsia.TVD`` for ``method="heterogeneous bregman"``.
+
+    tvd.py:23-43 (argument plumbing incl. the key prefix, Q15), :45-63 (dispatch),
+    :103-112 (call), :117-129 (Image in/out).  ``regularization`` is popped (Q1).
+    """
+
+    def __init__(self, key: str = "", **kwargs) -> None:
+        self.method = kwargs.pop(key + "method", "chambolle").lower()
+        if self.method == "heterogeneous bregman":
+            self.omega = kwargs.pop("omega", 1)
+            self.regularization = kwargs.pop("regularization", 1.0)
+        self.weight = kwargs.pop(key + "weight", 0.1)
+        self.max_num_iter = kwargs.pop(key + "max_num_iter", 200)
+        self.eps = kwargs.pop(key + "eps", 2e-4)
+        self.kwargs = kwargs
+
+    def __call__(self, img):
+        if isinstance(img, np.ndarray):
+            return self._tvd_array(img)
+        if hasattr(img, "img") and hasattr(img, "copy"):
+            out = img.copy()
+            out.img = self._tvd_array(img.img)
+            return out
+        raise TypeError(f"Input type {type(img)} not supported.")
+
+    def _tvd_array(self, img: np.ndarray) -> np.ndarray:
+        if self.method != "heterogeneous bregman":
+            raise ValueError(f"Method {self.method} not supported by the oracle.")
+        return split_bregman_tvd(
+            img,
+            mu=self.weight,
+            omega=self.omega,
+            ell=self.regularization,
+            max_num_iter=self.max_num_iter,
+            eps=self.eps,
+            **self.kwargs,
+        )
+
+
+def tvd(img, method: str = "chambolle", weight: Coeff = 1.0, max_num_iter: int = 200,
+        eps: float = 2e-4, **kwargs):
+    """Restatement of ``darsia.tvd`` (tvd.py:132-163)."""
+    return TVD(method=method, weight=weight, max_num_iter=max_num_iter, eps=eps, **kwargs)(img)

@@ -1,0 +1,82 @@
+"""The NumPy oracle against golden vectors produced by the verbatim DarSIA reference.
+
+This is what pins the oracle (tests/golden/generate_golden.py ran the reference's own
+hot-path files; the reference has no golden vectors of its own for this path).
+CPU only.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for, GOLDEN_DIR
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_oracle_matches_reference(name):
+    arrays, params = load_golden(name)
+    out = run_case_with(oracle, arrays, params)
+    ref = arrays["out"]
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    err = rel_l2(out, ref)
+    # tolerance of north_star; the restatement actually agrees to round-off
+    assert err <= tolerance_for(ref.dtype), f"{name}: rel L2 {err:.3e}"
+    if ref.dtype == np.float64:
+        assert err <= 1e-13, f"{name}: restatement drifted from the reference ({err:.3e})"
+
+
+@pytest.fixture(scope="module")
+def ops():
+    with np.load(f"{GOLDEN_DIR}/operators.npz") as z:
+        return {k: z[k] for k in z.files}
+
+
+@pytest.mark.parametrize("tag,dim", [("2d", 2), ("3d", 3), ("thin", 2)])
+def test_operator_level(ops, tag, dim):
+    x, ell, rhs = ops[f"{tag}_x"], ops[f"{tag}_ell"], ops[f"{tag}_rhs"]
+    for ax in range(dim):
+        np.testing.assert_array_equal(oracle.backward_diff(x, ax, dim), ops[f"{tag}_bdiff{ax}"])
+        np.testing.assert_array_equal(oracle.forward_diff(x, ax, dim), ops[f"{tag}_fdiff{ax}"])
+    np.testing.assert_allclose(oracle.laplace(x, dim, 0.7), ops[f"{tag}_lap_scalar"], rtol=0, atol=1e-15)
+    np.testing.assert_allclose(oracle.laplace(x, dim, ell), ops[f"{tag}_lap_array"], rtol=0, atol=1e-15)
+    np.testing.assert_array_equal(oracle.neighbor_accumulation(x), ops[f"{tag}_nacc"])
+    np.testing.assert_allclose(oracle.jacobi_sweep(x, rhs, 1.3, 0.7, dim), ops[f"{tag}_sweep"], rtol=0, atol=1e-15)
+    cg = oracle.CG(maxiter=4, tol=0.0, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
+    assert rel_l2(cg(x0=x, rhs=rhs), ops[f"{tag}_cg4"]) < 1e-13
+    cgh = oracle.CG(maxiter=4, tol=0.0, dim=dim, mass_coeff=1.3, diffusion_coeff=ell)
+    assert rel_l2(cgh(x0=x, rhs=rhs), ops[f"{tag}_cg4_hetero"]) < 1e-13
+
+
+def test_oracle_cg_is_scipy_recurrence():
+    """The written-out recurrence == scipy.sparse.linalg.cg (third party on this path)."""
+    import scipy.sparse.linalg as spla
+
+    rng = np.random.default_rng(3)
+    shape = (19, 23)
+    x0 = rng.standard_normal(shape)
+    rhs = rng.standard_normal(shape)
+    for tol, maxiter in ((0.0, 6), (1e-4, 200)):
+        A = spla.LinearOperator(
+            (x0.size, x0.size),
+            matvec=lambda v: oracle.cg_matvec(v.reshape(shape), 1.1, 0.9, 2).ravel(),
+        )
+        xs, _ = spla.cg(A, rhs.ravel(), x0.ravel().copy(), rtol=tol, atol=0.0, maxiter=maxiter)
+        xo = oracle.CG(maxiter=maxiter, tol=tol, dim=2, mass_coeff=1.1, diffusion_coeff=0.9)(x0, rhs)
+        assert rel_l2(xo.ravel(), xs) < 1e-14
+
+
+def test_oracle_properties():
+    """Constant image is a fixed point; batching = per-slice solves (Q5/Q6)."""
+    const = np.full((12, 9), 0.37)
+    out = oracle.split_bregman_tvd(const, mu=0.1, omega=1.0, ell=1.0, max_num_iter=5)
+    assert rel_l2(out, const) < 1e-15
+    rng = np.random.default_rng(0)
+    img = rng.random((14, 11, 3))
+    out = oracle.split_bregman_tvd(img, mu=0.1, ell=1.0, max_num_iter=4, isotropic=True,
+                                   solver=oracle.CG(maxiter=3, tol=0.0))
+    for c in range(3):
+        one = oracle.split_bregman_tvd(np.ascontiguousarray(img[..., c]), mu=0.1, ell=1.0, max_num_iter=4,
+                                       isotropic=True, solver=oracle.CG(maxiter=3, tol=0.0))
+        np.testing.assert_array_equal(out[..., c], one)
+    with pytest.raises(TypeError):
+        oracle.split_bregman_tvd((img * 255).astype(np.uint8))
