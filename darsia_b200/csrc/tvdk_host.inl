@@ -1,0 +1,961 @@
+// tvdk_host.inl -- host side of libtvdk: argument checking, launch geometry, the outer
+// split-Bregman loop, and the extern "C" entry points declared in include/tvdk.h.
+//
+// Included by exactly one translation unit per backend, after the backend has defined
+//   namespace tvdk::backend {
+//     template <class K> int launch(const typename K::Args&, int gx, int gy, int gz, int ntx,
+//                                   int nty, size_t smem, void* stream, double* partials,
+//                                   unsigned* counters);
+//     int memset_async(void* p, int value, size_t bytes, void* stream);
+//     int poll_begin(int slot, const int* dev_flag, void* stream);   // async read of a device int
+//     int poll_end(int slot, int* value);                            // wait for it
+//     int device_ok(char* msg, size_t n);
+//   }
+// The sm_100a backend is tvdk.cu; tests/emu/tvdk_emu.cpp is a CPU thread-stepper used only by
+// the CPU test-suite.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+
+namespace tvdk {
+
+static thread_local std::string g_last_error;
+
+static int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_last_error = buf;
+  return code;
+}
+#define TVDK_TRY(expr)            \
+  do {                            \
+    int rc_ = (expr);             \
+    if (rc_ != 0) return rc_;     \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------
+// geometry / coefficient conversion
+// ---------------------------------------------------------------------------------------
+static int check_geom(const tvdk_geom_t* g) {
+  if (!g) return fail(TVDK_ERR_INVALID, "geom is NULL");
+  if (g->dim != 2 && g->dim != 3) return fail(TVDK_ERR_INVALID, "dim must be 2 or 3, got %d", g->dim);
+  if (g->dtype != TVDK_F64 && g->dtype != TVDK_F32) return fail(TVDK_ERR_INVALID, "bad dtype %d", g->dtype);
+  for (int a = 0; a < g->dim; ++a)
+    if (g->n[a] < 1) return fail(TVDK_ERR_INVALID, "extent n[%d] = %d must be >= 1", a, g->n[a]);
+  const int vec = g->dtype == TVDK_F64 ? 2 : 4;
+  const int nlast = g->n[g->dim - 1];
+  if (g->pitch < nlast || g->pitch % vec != 0)
+    return fail(TVDK_ERR_INVALID, "pitch %d must be >= %d and a multiple of %d", g->pitch, nlast, vec);
+  if (g->nb < 1 || g->nb > 65535) return fail(TVDK_ERR_INVALID, "nb = %d out of range [1, 65535]", g->nb);
+  if (g->z_begin < 0 || g->z_end > g->n[0] || g->z_begin >= g->z_end)
+    return fail(TVDK_ERR_INVALID, "bad owned plane range [%d, %d) of %d", g->z_begin, g->z_end, g->n[0]);
+  if (g->g0_off < 0 || g->g0_off + g->z_end > g->g0_n)
+    return fail(TVDK_ERR_INVALID, "slab [%d + %d) exceeds global extent %d", g->g0_off, g->z_end, g->g0_n);
+  return 0;
+}
+
+static Geom make_geom(const tvdk_geom_t& g) {
+  Geom r;
+  r.n0 = g.n[0];
+  r.ny = g.dim == 3 ? g.n[1] : 1;
+  r.nx = g.n[g.dim - 1];
+  r.pitch = g.pitch;
+  r.s0 = (long long)r.ny * r.pitch;
+  r.sb = (long long)r.n0 * r.s0;
+  r.nb = g.nb;
+  r.g0_off = g.g0_off;
+  r.g0_n = g.g0_n;
+  r.z_begin = g.z_begin;
+  r.z_end = g.z_end;
+  r.zchunk = g.z_end - g.z_begin;
+  r.xtiles = r.ytiles = 1;
+  return r;
+}
+
+template <typename T>
+static Coef<T> make_coef(const tvdk_coef_t& c) {
+  Coef<T> r;
+  r.p = reinterpret_cast<const T*>(c.device_ptr);
+  r.val = (T)c.value;
+  r.sb = c.batch_stride;
+  return r;
+}
+
+// Scalars as the reference computes them with Python floats (jacobi.py:57-72,101-106;
+// split_bregman_tvd.py:140,145), cast to T afterwards.
+template <typename T>
+static Coefs<T> make_coefs(const tvdk_coef_t* mu, const tvdk_coef_t* om, const tvdk_coef_t* el, int dim) {
+  static const tvdk_coef_t one = {nullptr, 1.0, 0};
+  if (!mu) mu = &one;
+  if (!om) om = &one;
+  if (!el) el = &one;
+  Coefs<T> k;
+  k.mu = make_coef<T>(*mu);
+  k.omega = make_coef<T>(*om);
+  k.ell = make_coef<T>(*el);
+  Scalars<T>& s = k.sc;
+  s.mu = (T)mu->value;
+  s.omega = (T)om->value;
+  s.ell = (T)el->value;
+  s.kappa = (T)(mu->value / el->value);
+  const double diag = om->value + el->value * 2 * dim / 1.0;
+  s.inv_diag = (T)(1.0 / diag);
+  s.c_nb = (T)(1.0 / (diag / el->value));
+  s.dim_t = (T)dim;
+  s.hetero = (mu->device_ptr || om->device_ptr || el->device_ptr) ? 1 : 0;
+  return k;
+}
+
+// ---------------------------------------------------------------------------------------
+// launch geometry
+// ---------------------------------------------------------------------------------------
+struct Tune {
+  int tile_x, tile_y, zchunk;  // 0 = default
+};
+
+struct LaunchCfg {
+  int ntx, nty, gx, gy, gz;
+  size_t smem;
+  Geom g;
+};
+
+static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+
+template <class K, typename T, int D>
+static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
+  typedef typename K::C C;
+  constexpr int V = Vec<T>::N;
+  LaunchCfg L;
+  const int halo_x = K::LH + C::RHX;
+  const int need_x = (g.nx + V - 1) / V + halo_x;  // vectors to cover one row incl. halo
+  if (D == 2) {
+    int ntx = tune.tile_x > 0 ? tune.tile_x : 128;
+    ntx = std::min(ntx, round_up(need_x, 32));
+    ntx = std::max(ntx, 32);
+    L.ntx = ntx;
+    L.nty = 1;
+  } else {
+    int ntx = tune.tile_x > 0 ? tune.tile_x : 32;
+    ntx = std::min(ntx, round_up(need_x, 8));
+    ntx = std::max(ntx, 8);
+    int nty = tune.tile_y > 0 ? tune.tile_y : (big_tile ? 16 : 8);
+    const int halo_y = K::LH + K::RH;
+    nty = std::min(nty, round_up(g.ny + halo_y, 4));
+    nty = std::max(nty, halo_y + 1);
+    while ((ntx * nty) % 32 != 0) ++nty;
+    while (ntx * nty > 512 && nty > halo_y + 1) --nty;
+    while ((ntx * nty) % 32 != 0 && nty > halo_y + 1) --nty;
+    L.ntx = ntx;
+    L.nty = nty;
+  }
+  const int iw = C::iw(L.ntx), ih = C::ih(L.nty);
+  g.xtiles = (g.nx + iw - 1) / iw;
+  g.ytiles = D == 3 ? (g.ny + ih - 1) / ih : 1;
+  const int nz = g.z_end - g.z_begin;
+  int zc = tune.zchunk;
+  if (zc <= 0) {
+    const long long tiles = (long long)g.xtiles * g.ytiles * g.nb;
+    const long long target = 148LL * 8;
+    const long long want = std::max(1LL, (target + tiles - 1) / tiles);
+    zc = (int)((nz + want - 1) / want);
+    zc = std::max(zc, 16);
+  }
+  zc = std::min(zc, nz);
+  g.zchunk = zc;
+  L.gx = g.xtiles * g.ytiles;
+  L.gy = (nz + zc - 1) / zc;
+  L.gz = g.nb;
+  L.smem = (size_t)K::NROWS * C::row_elems(L.ntx, L.nty) * sizeof(T);
+  L.g = g;
+  return L;
+}
+
+// device scratch carved from the caller's workspace
+struct Scratch {
+  double* partials;
+  unsigned* counters;
+  int* ndone;
+  unsigned char* fields;  // start of the field area
+  size_t partial_cap;     // doubles
+};
+
+static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// upper bound of (blocks per launch) * NRED over every kernel configuration we use
+template <typename T, int D>
+static size_t partial_capacity(const Geom& g, const Tune& tune) {
+  // the fused kernel has the widest halo (fewest interior columns per block) => most blocks
+  LaunchCfg a = plan_launch<KFusedJ1<T, D, false>, T, D>(g, tune, true);
+  LaunchCfg b = plan_launch<KSweep<T, D>, T, D>(g, tune, false);
+  LaunchCfg c = plan_launch<KShrink<T, D, false>, T, D>(g, tune, false);
+  LaunchCfg d = plan_launch<KDot<T, D, 0>, T, D>(g, tune, false);
+  size_t m = 0;
+  for (const LaunchCfg* L : {&a, &b, &c, &d}) m = std::max(m, (size_t)L->gx * L->gy * L->gz);
+  return m * 2 + 64;
+}
+
+static size_t scratch_bytes(size_t partial_cap, int nb) {
+  return align_up(partial_cap * sizeof(double), 256) + align_up((size_t)nb * sizeof(unsigned), 256) + 256;
+}
+
+static Scratch carve_scratch(void* ws, size_t partial_cap, int nb) {
+  Scratch s;
+  unsigned char* p = reinterpret_cast<unsigned char*>(ws);
+  s.partials = reinterpret_cast<double*>(p);
+  p += align_up(partial_cap * sizeof(double), 256);
+  s.counters = reinterpret_cast<unsigned*>(p);
+  p += align_up((size_t)nb * sizeof(unsigned), 256);
+  s.ndone = reinterpret_cast<int*>(p);
+  p += 256;
+  s.fields = p;
+  s.partial_cap = partial_cap;
+  return s;
+}
+
+template <class K, typename T, int D>
+static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_tile, const Scratch& sc,
+               void* stream) {
+  LaunchCfg L = plan_launch<K, T, D>(g, tune, big_tile);
+  a.g = L.g;
+  if ((size_t)L.gx * L.gy * L.gz * (K::NRED > 0 ? K::NRED : 1) > sc.partial_cap)
+    return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
+  return backend::launch<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
+}
+
+static Fin no_fin() {
+  Fin f;
+  memset(&f, 0, sizeof f);
+  f.kind = FIN_NONE;
+  f.eps = -1.0;
+  return f;
+}
+
+// ---------------------------------------------------------------------------------------
+// the outer loop
+// ---------------------------------------------------------------------------------------
+struct FieldPlan {
+  // number of extra fields taken from the workspace
+  bool fusedj1, cg, jac, expl;
+  int n_fields;
+};
+
+static FieldPlan field_plan(const tvdk_problem_t* p) {
+  FieldPlan fp;
+  fp.expl = p->x0_b != nullptr || p->x0_d != nullptr;
+  fp.cg = p->solver_kind == TVDK_SOLVER_CG;
+  fp.fusedj1 = p->fused && !fp.cg && p->solver_maxiter == 1 && p->solver_tol < 0.0;
+  fp.jac = !fp.cg;
+  const int D = p->geom.dim;
+  int n = 0;
+  if (fp.fusedj1) {
+    n += 1 + D;           // U2, T2
+    if (fp.expl) n += 2;  // rhs + xa for the explicit first iteration
+  } else if (fp.cg) {
+    n += 4;  // X, R, P0, P1
+  } else {
+    n += (p->solver_maxiter >= 2) ? 3 : 2;  // rhs, XA, (XB)
+  }
+  fp.n_fields = n;
+  return fp;
+}
+
+template <typename T, int D>
+static size_t workspace_bytes_impl(const tvdk_problem_t* p) {
+  Geom g = make_geom(p->geom);
+  Tune tune = {p->tile_x, p->tile_y, p->zchunk};
+  const size_t cap = partial_capacity<T, D>(g, tune);
+  const FieldPlan fp = field_plan(p);
+  const size_t field_bytes = align_up((size_t)g.sb * g.nb * sizeof(T), 256);
+  return scratch_bytes(cap, g.nb) + fp.n_fields * field_bytes + 256;
+}
+
+template <typename T, int D>
+static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched) {
+  const Geom g = make_geom(p->geom);
+  const Tune tune = {p->tile_x, p->tile_y, p->zchunk};
+  const bool iso = p->isotropic != 0;
+  const FieldPlan fp = field_plan(p);
+  const size_t need = workspace_bytes_impl<T, D>(p);
+  if (!p->workspace || p->workspace_bytes < need)
+    return fail(TVDK_ERR_WORKSPACE, "workspace of %zu bytes needed, %zu given", need, p->workspace_bytes);
+  if (!p->f || !p->u || !p->t || !p->stats) return fail(TVDK_ERR_INVALID, "f, u, t and stats must be non-NULL");
+  if (fp.expl && (!p->x0_b || !p->x0_d)) return fail(TVDK_ERR_INVALID, "warm start needs both x0_d and x0_b");
+  if (p->solver_maxiter < 1) return fail(TVDK_ERR_INVALID, "solver maxiter must be >= 1");
+  if (fp.cg && p->solver_tol < 0.0)
+    return fail(TVDK_ERR_INVALID, "CG needs a numeric tol (SciPy rejects rtol=None); use 0.0 for a fixed count");
+  if (p->geom.z_begin != 0 || p->geom.z_end != p->geom.n[0] || p->geom.g0_off != 0 || p->geom.g0_n != p->geom.n[0])
+    return fail(TVDK_ERR_INVALID, "tvdk_solve works on whole volumes; slabs use the building-block entry points");
+
+  const size_t cap = partial_capacity<T, D>(g, tune);
+  const Scratch sc = carve_scratch(p->workspace, cap, g.nb);
+  const size_t fe = align_up((size_t)g.sb * g.nb * sizeof(T), 256) / sizeof(T);  // elements per field slot
+  T* wsf = reinterpret_cast<T*>(sc.fields);
+  int next_field = 0;
+  auto take = [&](int n) {
+    T* r = wsf + (size_t)next_field * fe;
+    next_field += n;
+    return r;
+  };
+
+  const Coefs<T> k = make_coefs<T>(&p->mu, &p->omega, &p->ell, D);
+  const T* f = reinterpret_cast<const T*>(p->f);
+  T* ubuf[2] = {reinterpret_cast<T*>(p->u), nullptr};
+  T* tbuf[2] = {reinterpret_cast<T*>(p->t), nullptr};
+  long long tcs[2] = {p->t_comp_stride, (long long)fe};
+  T *RB = nullptr, *XA = nullptr, *XB = nullptr, *X = nullptr, *P[2] = {nullptr, nullptr};
+  if (fp.fusedj1) {
+    ubuf[1] = take(1);
+    tbuf[1] = take(D);
+    if (fp.expl) {
+      RB = take(1);
+      XA = take(1);
+    }
+  } else if (fp.cg) {
+    X = take(1);
+    RB = take(1);
+    P[0] = take(1);
+    P[1] = take(1);
+  } else {
+    RB = take(1);
+    XA = take(1);
+    if (p->solver_maxiter >= 2) XB = take(1);
+  }
+
+  tvdk_stat_t* st = p->stats;
+  TVDK_TRY(backend::memset_async(st, 0, sizeof(tvdk_stat_t) * (size_t)g.nb, stream));
+  TVDK_TRY(backend::memset_async(sc.counters, 0, sizeof(unsigned) * (size_t)g.nb, stream));
+  TVDK_TRY(backend::memset_async(sc.ndone, 0, sizeof(int), stream));
+
+  {  // ||img|| (split_bregman_tvd.py:58)
+    typename KDot<T, D, 0>::Args a;
+    memset(&a, 0, sizeof a);
+    a.x = f;
+    a.y = f;
+    a.fin = no_fin();
+    a.fin.kind = FIN_NRMF;
+    a.fin.stats = st;
+    TVDK_TRY((run<KDot<T, D, 0>, T, D>(a, g, tune, false, sc, stream)));
+  }
+
+  auto outer_fin = [&](int it, int buf_id) {
+    Fin fn = no_fin();
+    fn.kind = FIN_OUTER;
+    fn.stats = st;
+    fn.eps = p->eps;
+    fn.history = p->history;
+    fn.iter = it;
+    fn.nb = g.nb;
+    fn.ndone = sc.ndone;
+    fn.buf_id = buf_id;
+    return fn;
+  };
+
+  // shrink + Bregman update + in-place u update, shared by the unfused routes
+  auto launch_shrink = [&](int it, int cur, const T* u0, const T* u1, const T* u2, int use_sel, bool expl_now) {
+    Fin fn = outer_fin(it, cur);
+    if (iso) {
+      typename KShrink<T, D, true>::Args a;
+      memset(&a, 0, sizeof a);
+      a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
+      a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
+      a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
+      a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;
+      a.skip = st; a.fin = fn;
+      return run<KShrink<T, D, true>, T, D>(a, g, tune, false, sc, stream);
+    } else {
+      typename KShrink<T, D, false>::Args a;
+      memset(&a, 0, sizeof a);
+      a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
+      a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
+      a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
+      a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;
+      a.skip = st; a.fin = fn;
+      return run<KShrink<T, D, false>, T, D>(a, g, tune, false, sc, stream);
+    }
+  };
+
+#define TVDK_RHS_ARGS(a, cur, expl_now)                                   \
+  memset(&a, 0, sizeof a);                                                \
+  a.k = k; a.f = f;                                                       \
+  a.t = (expl_now) ? nullptr : tbuf[cur]; a.tcs = tcs[cur];               \
+  a.xd = reinterpret_cast<const T*>(p->x0_d);                             \
+  a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;  \
+  a.u = ubuf[cur]; a.skip = st; a.fin = no_fin();
+
+  auto launch_rhs_sweep = [&](int cur, bool expl_now, T* rhs, T* x, const Fin& fn) {
+    if (iso) {
+      typename KRhs<T, D, true, RHS_SWEEP>::Args a;
+      TVDK_RHS_ARGS(a, cur, expl_now)
+      a.rhs = rhs; a.x = x; a.fin = fn;
+      return run<KRhs<T, D, true, RHS_SWEEP>, T, D>(a, g, tune, false, sc, stream);
+    } else {
+      typename KRhs<T, D, false, RHS_SWEEP>::Args a;
+      TVDK_RHS_ARGS(a, cur, expl_now)
+      a.rhs = rhs; a.x = x; a.fin = fn;
+      return run<KRhs<T, D, false, RHS_SWEEP>, T, D>(a, g, tune, false, sc, stream);
+    }
+  };
+  auto launch_rhs_cginit = [&](int cur, bool expl_now, T* x, T* r, const Fin& fn) {
+    if (iso) {
+      typename KRhs<T, D, true, RHS_CGINIT>::Args a;
+      TVDK_RHS_ARGS(a, cur, expl_now)
+      a.x = x; a.r = r; a.fin = fn;
+      return run<KRhs<T, D, true, RHS_CGINIT>, T, D>(a, g, tune, false, sc, stream);
+    } else {
+      typename KRhs<T, D, false, RHS_CGINIT>::Args a;
+      TVDK_RHS_ARGS(a, cur, expl_now)
+      a.x = x; a.r = r; a.fin = fn;
+      return run<KRhs<T, D, false, RHS_CGINIT>, T, D>(a, g, tune, false, sc, stream);
+    }
+  };
+
+  const bool tolmode = !fp.cg && p->solver_tol >= 0.0;
+  const int check_every = p->check_every > 0 ? p->check_every : 8;
+  int cur = 0, launched = 0, slot = 0;
+  bool pending[2] = {false, false};
+  bool all_done = false;
+
+  for (int it = 0; it < p->max_num_iter && !all_done; ++it) {
+    const bool expl_now = fp.expl && it == 0;
+    if (p->verbose_every > 0 && it % p->verbose_every == 0 && p->energy_history) {
+      // energy of the current iterate (split_bregman_tvd.py:162-167 prints _functional(img_iter))
+      typename KEnergy<T, D>::Args a;
+      memset(&a, 0, sizeof a);
+      a.k = k; a.x = ubuf[cur]; a.f = f; a.skip = st;
+      a.fin = no_fin();
+      a.fin.kind = FIN_ENERGY; a.fin.stats = st; a.fin.history = p->energy_history; a.fin.iter = it; a.fin.nb = g.nb;
+      TVDK_TRY((run<KEnergy<T, D>, T, D>(a, g, tune, false, sc, stream)));
+    }
+    if (fp.fusedj1 && !expl_now) {
+      const Fin fn = outer_fin(it, 1 - cur);
+      if (iso) {
+        typename KFusedJ1<T, D, true>::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.f = f; a.u_in = ubuf[cur]; a.u_out = ubuf[1 - cur];
+        a.t_in = tbuf[cur]; a.t_out = tbuf[1 - cur]; a.tcs_in = tcs[cur]; a.tcs_out = tcs[1 - cur];
+        a.skip = st; a.fin = fn;
+        TVDK_TRY((run<KFusedJ1<T, D, true>, T, D>(a, g, tune, true, sc, stream)));
+      } else {
+        typename KFusedJ1<T, D, false>::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.f = f; a.u_in = ubuf[cur]; a.u_out = ubuf[1 - cur];
+        a.t_in = tbuf[cur]; a.t_out = tbuf[1 - cur]; a.tcs_in = tcs[cur]; a.tcs_out = tcs[1 - cur];
+        a.skip = st; a.fin = fn;
+        TVDK_TRY((run<KFusedJ1<T, D, false>, T, D>(a, g, tune, true, sc, stream)));
+      }
+      cur = 1 - cur;
+    } else if (fp.cg) {
+      Fin fn = no_fin();
+      fn.kind = FIN_CGINIT; fn.stats = st; fn.tol = p->solver_tol;
+      TVDK_TRY(launch_rhs_cginit(cur, expl_now, X, RB, fn));
+      for (int i = 0; i < p->solver_maxiter; ++i) {
+        typename KCg<T, D, CG_PQ>::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.p_in = P[(i & 1) ^ 1]; a.r_in = RB; a.p_out = P[i & 1];
+        a.coef.p = &st[0].beta; a.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
+        a.first.p = &st[0].cg_first; a.first.stride = (int)(sizeof(tvdk_stat_t) / sizeof(int));
+        a.skip = st; a.fin = no_fin(); a.fin.kind = FIN_CGPQ; a.fin.stats = st;
+        TVDK_TRY((run<KCg<T, D, CG_PQ>, T, D>(a, g, tune, false, sc, stream)));
+        typename KCg<T, D, CG_UPDATE>::Args b;
+        memset(&b, 0, sizeof b);
+        b.k = k; b.p_in = P[i & 1]; b.x = X; b.r = RB;
+        b.coef.p = &st[0].alpha; b.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
+        b.skip = st; b.fin = no_fin(); b.fin.kind = FIN_CGRR; b.fin.stats = st;
+        TVDK_TRY((run<KCg<T, D, CG_UPDATE>, T, D>(b, g, tune, false, sc, stream)));
+      }
+      TVDK_TRY(launch_shrink(it, cur, X, nullptr, nullptr, 0, expl_now));
+    } else {
+      // Jacobi: sweep 1 fused with the rhs, then ping-pong XA/XB (jacobi.py:109-131)
+      Fin fn = no_fin();
+      if (tolmode) {
+        fn.kind = FIN_JTOL; fn.stats = st; fn.tol = p->solver_tol; fn.buf_id = 1; fn.first_sweep = 1;
+      }
+      TVDK_TRY(launch_rhs_sweep(cur, expl_now, RB, XA, fn));
+      T* xin = XA;
+      T* xout = XB;
+      int out_id = 2;
+      for (int s = 2; s <= p->solver_maxiter; ++s) {
+        typename KSweep<T, D>::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
+        if (tolmode) {
+          a.fin.kind = FIN_JTOL; a.fin.stats = st; a.fin.tol = p->solver_tol; a.fin.buf_id = out_id;
+        }
+        TVDK_TRY((run<KSweep<T, D>, T, D>(a, g, tune, false, sc, stream)));
+        std::swap(xin, xout);
+        out_id = 3 - out_id;
+      }
+      if (tolmode)
+        TVDK_TRY(launch_shrink(it, cur, ubuf[cur], XA, XB ? XB : XA, 1, expl_now));
+      else
+        TVDK_TRY(launch_shrink(it, cur, xin, nullptr, nullptr, 0, expl_now));
+    }
+    ++launched;
+    // convergence polling (split_bregman_tvd.py:173-175) without stalling the queue: the flag
+    // read after chunk k is inspected before chunk k+2 is enqueued
+    if (p->eps >= 0.0 && (launched % check_every) == 0 && it + 1 < p->max_num_iter) {
+      const int other = slot ^ 1;
+      TVDK_TRY(backend::poll_begin(slot, sc.ndone, stream));
+      pending[slot] = true;
+      if (pending[other]) {
+        int v = 0;
+        TVDK_TRY(backend::poll_end(other, &v));
+        pending[other] = false;
+        if (v >= g.nb) all_done = true;
+      }
+      slot = other;
+    }
+  }
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (pending[s2]) {
+      int v = 0;
+      TVDK_TRY(backend::poll_end(s2, &v));
+    }
+  if (fp.fusedj1) {  // bring every problem's iterate back into p->u
+    typename KSelectCopy<T, D>::Args a;
+    memset(&a, 0, sizeof a);
+    a.src = ubuf[1]; a.dst = ubuf[0]; a.stats = st; a.want = 1; a.fin = no_fin();
+    TVDK_TRY((run<KSelectCopy<T, D>, T, D>(a, g, tune, false, sc, stream)));
+    for (int d = 0; d < D; ++d) {
+      typename KSelectCopy<T, D>::Args b;
+      memset(&b, 0, sizeof b);
+      b.src = tbuf[1] + d * tcs[1]; b.dst = tbuf[0] + d * tcs[0]; b.stats = st; b.want = 1; b.fin = no_fin();
+      TVDK_TRY((run<KSelectCopy<T, D>, T, D>(b, g, tune, false, sc, stream)));
+    }
+  }
+  if (iters_launched) *iters_launched = launched;
+  return 0;
+}
+
+// dispatch helpers ---------------------------------------------------------------------
+#define TVDK_DISPATCH(geom, CALL)                                   \
+  do {                                                              \
+    if ((geom).dtype == TVDK_F64) {                                 \
+      if ((geom).dim == 2) { typedef double T; constexpr int D = 2; CALL; } \
+      else { typedef double T; constexpr int D = 3; CALL; }         \
+    } else {                                                        \
+      if ((geom).dim == 2) { typedef float T; constexpr int D = 2; CALL; }  \
+      else { typedef float T; constexpr int D = 3; CALL; }          \
+    }                                                               \
+  } while (0)
+
+template <typename T, int D>
+static size_t op_ws_impl(const tvdk_geom_t* gg) {
+  Geom g = make_geom(*gg);
+  Tune tune = {0, 0, 0};
+  return scratch_bytes(partial_capacity<T, D>(g, tune), g.nb) + 256;
+}
+
+template <typename T, int D>
+static int op_scratch(const tvdk_geom_t* gg, void* ws, size_t ws_bytes, Scratch* sc, void* stream) {
+  Geom g = make_geom(*gg);
+  Tune tune = {0, 0, 0};
+  const size_t cap = partial_capacity<T, D>(g, tune);
+  if (!ws || ws_bytes < scratch_bytes(cap, g.nb))
+    return fail(TVDK_ERR_WORKSPACE, "operator workspace of %zu bytes needed, %zu given", scratch_bytes(cap, g.nb), ws_bytes);
+  *sc = carve_scratch(ws, cap, g.nb);
+  return backend::memset_async(sc->counters, 0, sizeof(unsigned) * (size_t)g.nb, stream);
+}
+
+static Fin sum_fin(double* out) {
+  Fin f = no_fin();
+  f.sum_out = out;
+  return f;
+}
+
+}  // namespace tvdk
+
+// ---------------------------------------------------------------------------------------
+// extern "C"
+// ---------------------------------------------------------------------------------------
+using namespace tvdk;
+
+// (definitions pick up C linkage from the declarations in include/tvdk.h)
+
+int tvdk_version(void) { return TVDK_VERSION; }
+const char* tvdk_last_error(void) { return g_last_error.c_str(); }
+
+int tvdk_device_ok(void) {
+  char msg[256] = {0};
+  const int ok = backend::device_ok(msg, sizeof msg);
+  if (!ok) g_last_error = msg;
+  return ok;
+}
+
+int tvdk_pitch(int dtype, int n_last) {
+  const int a = dtype == TVDK_F64 ? 16 : 32;  // 128 bytes
+  return (n_last + a - 1) / a * a;
+}
+
+int64_t tvdk_field_elems(const tvdk_geom_t* g) {
+  if (check_geom(g)) return -1;
+  return make_geom(*g).sb;
+}
+
+size_t tvdk_workspace_bytes(const tvdk_problem_t* p) {
+  if (!p || check_geom(&p->geom)) return 0;
+  size_t r = 0;
+  TVDK_DISPATCH(p->geom, r = (workspace_bytes_impl<T, D>(p)));
+  return r;
+}
+
+size_t tvdk_op_workspace_bytes(const tvdk_geom_t* g) {
+  if (check_geom(g)) return 0;
+  size_t r = 0;
+  TVDK_DISPATCH(*g, r = (op_ws_impl<T, D>(g)));
+  return r;
+}
+
+int tvdk_solve(const tvdk_problem_t* p, void* stream, int* iters_launched) {
+  if (!p) return fail(TVDK_ERR_INVALID, "problem is NULL");
+  TVDK_TRY(check_geom(&p->geom));
+  if (p->max_num_iter < 0) return fail(TVDK_ERR_INVALID, "max_num_iter must be >= 0");
+  if (p->solver_kind != TVDK_SOLVER_JACOBI && p->solver_kind != TVDK_SOLVER_CG)
+    return fail(TVDK_ERR_UNSUPPORTED, "unknown solver kind %d (Jacobi and CG only)", p->solver_kind);
+  int rc = 0;
+  TVDK_DISPATCH(p->geom, rc = (solve_impl<T, D>(p, stream, iters_launched)));
+  return rc;
+}
+
+int tvdk_pack(const tvdk_geom_t* gg, int src_dtype, const void* src, void* dst, void* stream) {
+  TVDK_TRY(check_geom(gg));
+  if (!src || !dst) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  Geom g = make_geom(*gg);
+  const long long per_row = (long long)g.nx * g.nb;
+  const int ntx = 256;
+  const int gy = (int)std::min<long long>((per_row + ntx - 1) / ntx, 64);
+  const long long rows = (long long)g.n0 * g.ny;
+#define TVDK_PACK_CALL(TI, TF)                                                          \
+  {                                                                                     \
+    typename KPack<TI, TF, 1>::Args a;                                                  \
+    memset(&a, 0, sizeof a);                                                            \
+    a.g = g; a.src = src; a.dst = dst; a.fin = no_fin();                                \
+    return backend::launch<KPack<TI, TF, 1>>(a, (int)rows, gy, 1, ntx, 1, 0, stream, nullptr, nullptr); \
+  }
+  if (src_dtype == TVDK_F64 && gg->dtype == TVDK_F64) TVDK_PACK_CALL(double, double)
+  if (src_dtype == TVDK_F64 && gg->dtype == TVDK_F32) TVDK_PACK_CALL(double, float)
+  if (src_dtype == TVDK_F32 && gg->dtype == TVDK_F64) TVDK_PACK_CALL(float, double)
+  if (src_dtype == TVDK_F32 && gg->dtype == TVDK_F32) TVDK_PACK_CALL(float, float)
+#undef TVDK_PACK_CALL
+  return fail(TVDK_ERR_INVALID, "bad dtype");
+}
+
+int tvdk_unpack(const tvdk_geom_t* gg, int dst_dtype, const void* src, void* dst, void* stream) {
+  TVDK_TRY(check_geom(gg));
+  if (!src || !dst) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  Geom g = make_geom(*gg);
+  const long long per_row = (long long)g.nx * g.nb;
+  const int ntx = 256;
+  const int gy = (int)std::min<long long>((per_row + ntx - 1) / ntx, 64);
+  const long long rows = (long long)g.n0 * g.ny;
+#define TVDK_UNPACK_CALL(TI, TF)                                                        \
+  {                                                                                     \
+    typename KPack<TI, TF, 0>::Args a;                                                  \
+    memset(&a, 0, sizeof a);                                                            \
+    a.g = g; a.src = src; a.dst = dst; a.fin = no_fin();                                \
+    return backend::launch<KPack<TI, TF, 0>>(a, (int)rows, gy, 1, ntx, 1, 0, stream, nullptr, nullptr); \
+  }
+  if (dst_dtype == TVDK_F64 && gg->dtype == TVDK_F64) TVDK_UNPACK_CALL(double, double)
+  if (dst_dtype == TVDK_F64 && gg->dtype == TVDK_F32) TVDK_UNPACK_CALL(double, float)
+  if (dst_dtype == TVDK_F32 && gg->dtype == TVDK_F64) TVDK_UNPACK_CALL(float, double)
+  if (dst_dtype == TVDK_F32 && gg->dtype == TVDK_F32) TVDK_UNPACK_CALL(float, float)
+#undef TVDK_UNPACK_CALL
+  return fail(TVDK_ERR_INVALID, "bad dtype");
+}
+
+// ---- operators ---------------------------------------------------------------------------
+#define TVDK_OP_PROLOGUE(gg)                                  \
+  TVDK_TRY(check_geom(gg));                                   \
+  Scratch sc;                                                 \
+  const Geom g = make_geom(*gg);                              \
+  const Tune tune = {0, 0, 0};                                \
+  (void)tune;
+
+#define TVDK_ISO_CALL(iso, KT, FILL, BIG)                                   \
+  if (iso) {                                                                \
+    typedef KT(true) K_;                                                    \
+    typename K_::Args a; memset(&a, 0, sizeof a); FILL;                     \
+    rc = run<K_, T, D>(a, g, tune, BIG, sc, stream);                        \
+  } else {                                                                  \
+    typedef KT(false) K_;                                                   \
+    typename K_::Args a; memset(&a, 0, sizeof a); FILL;                     \
+    rc = run<K_, T, D>(a, g, tune, BIG, sc, stream);                        \
+  }
+
+template <typename T, int D>
+static int rhs_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
+                    const tvdk_coef_t* el, const void* f, const void* t, int64_t tcs, void* rhs, void* ws,
+                    size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  int rc = 0;
+#define KT(I) KRhs<T, D, I, RHS_ONLY>
+  TVDK_ISO_CALL(iso, KT,
+                (a.k = make_coefs<T>(mu, om, el, D), a.f = (const T*)f, a.t = (const T*)t, a.tcs = tcs,
+                 a.rhs = (T*)rhs, a.fin = no_fin()),
+                false)
+#undef KT
+  return rc;
+}
+
+int tvdk_rhs(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+             const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, void* rhs,
+             void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (rhs_impl<T, D>(g, isotropic, mu, omega, ell, f, t, t_comp_stride, rhs, workspace,
+                                         workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int sweep_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* x_in,
+                      const void* rhs, void* x_out, void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  typename KSweep<T, D>::Args a;
+  memset(&a, 0, sizeof a);
+  a.k = make_coefs<T>(nullptr, om, el, D);
+  a.x_in = (const T*)x_in; a.rhs = (const T*)rhs; a.x_out = (T*)x_out; a.fin = no_fin();
+  return run<KSweep<T, D>, T, D>(a, g, tune, false, sc, stream);
+}
+
+int tvdk_jacobi_sweep(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x_in,
+                      const void* rhs, void* x_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (sweep_impl<T, D>(g, omega, ell, x_in, rhs, x_out, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int matvec_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* x, void* y,
+                       void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  typename KCg<T, D, CG_MATVEC>::Args a;
+  memset(&a, 0, sizeof a);
+  a.k = make_coefs<T>(nullptr, om, el, D);
+  a.p_in = (const T*)x; a.p_out = (T*)y; a.fin = no_fin();
+  return run<KCg<T, D, CG_MATVEC>, T, D>(a, g, tune, false, sc, stream);
+}
+
+int tvdk_cg_matvec(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x, void* y,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (matvec_impl<T, D>(g, omega, ell, x, y, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int shrink_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* el,
+                       const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t tcs,
+                       double* sum_out, void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  int rc = 0;
+#define KT(I) KShrink<T, D, I>
+  TVDK_ISO_CALL(iso, KT,
+                (a.k = make_coefs<T>(mu, nullptr, el, D), a.unew[0] = (const T*)u_new, a.u_old = (const T*)u_old,
+                 a.u_out = nullptr, a.t_in = (const T*)t_in, a.t_out = (T*)t_out, a.tcs = tcs,
+                 a.fin = sum_fin(sum_out)),
+                false)
+#undef KT
+  return rc;
+}
+
+int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t t_comp_stride,
+                double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, t_in, t_out, t_comp_stride,
+                                            sum_out, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int expand_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* el, const void* t,
+                       int64_t tcs, void* d, void* b, int64_t ocs, void* stream) {
+  TVDK_TRY(check_geom(gg));
+  const Geom g = make_geom(*gg);
+  const Tune tune = {0, 0, 0};
+  Scratch sc;
+  memset(&sc, 0, sizeof sc);
+  sc.partial_cap = (size_t)-1;
+  int rc = 0;
+#define KT(I) KExpand<T, D, I>
+  TVDK_ISO_CALL(iso, KT,
+                (a.k = make_coefs<T>(mu, nullptr, el, D), a.t = (const T*)t, a.tcs = tcs, a.d = (T*)d,
+                 a.b = (T*)b, a.ocs = ocs, a.fin = no_fin()),
+                false)
+#undef KT
+  return rc;
+}
+
+int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                      const void* t, int64_t t_comp_stride, void* d, void* b, int64_t db_comp_stride,
+                      void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (expand_impl<T, D>(g, isotropic, mu, ell, t, t_comp_stride, d, b, db_comp_stride, stream)));
+  return rc;
+}
+
+template <typename T, int D, int MODE>
+static int dot_impl(const tvdk_geom_t* gg, const void* x, const void* y, double* out, void* ws, size_t wsb,
+                    void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  typename KDot<T, D, MODE>::Args a;
+  memset(&a, 0, sizeof a);
+  a.x = (const T*)x; a.y = (const T*)y; a.fin = sum_fin(out);
+  return run<KDot<T, D, MODE>, T, D>(a, g, tune, false, sc, stream);
+}
+
+int tvdk_dot(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
+             size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (dot_impl<T, D, 0>(g, x, y, out, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+int tvdk_norm_diff2(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (dot_impl<T, D, 1>(g, x, y, out, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int energy_impl(const tvdk_geom_t* gg, const tvdk_coef_t* mu, const tvdk_coef_t* om, const void* x,
+                       const void* f, double* out, void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  typename KEnergy<T, D>::Args a;
+  memset(&a, 0, sizeof a);
+  a.k = make_coefs<T>(mu, om, nullptr, D);
+  a.x = (const T*)x; a.f = (const T*)f; a.fin = sum_fin(out);
+  return run<KEnergy<T, D>, T, D>(a, g, tune, false, sc, stream);
+}
+
+int tvdk_energy(const tvdk_geom_t* g, const tvdk_coef_t* mu, const tvdk_coef_t* omega, const void* x,
+                const void* f, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (energy_impl<T, D>(g, mu, omega, x, f, out, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int fj1_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
+                    const tvdk_coef_t* el, const void* f, const void* u_in, void* u_out, const void* t_in,
+                    void* t_out, int64_t tcs, double* sum_out, void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  int rc = 0;
+#define KT(I) KFusedJ1<T, D, I>
+  TVDK_ISO_CALL(iso, KT,
+                (a.k = make_coefs<T>(mu, om, el, D), a.f = (const T*)f, a.u_in = (const T*)u_in,
+                 a.u_out = (T*)u_out, a.t_in = (const T*)t_in, a.t_out = (T*)t_out, a.tcs_in = tcs,
+                 a.tcs_out = tcs, a.fin = sum_fin(sum_out)),
+                true)
+#undef KT
+  return rc;
+}
+
+int tvdk_fused_jacobi1(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+                       const tvdk_coef_t* ell, const void* f, const void* u_in, void* u_out, const void* t_in,
+                       void* t_out, int64_t t_comp_stride, double* sum_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  if (u_in == u_out || t_in == t_out) return fail(TVDK_ERR_INVALID, "fused kernel is out-of-place");
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (fj1_impl<T, D>(g, isotropic, mu, omega, ell, f, u_in, u_out, t_in, t_out,
+                                         t_comp_stride, sum_out, workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int cginit_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
+                       const tvdk_coef_t* el, const void* f, const void* t, int64_t tcs, const void* u, void* x,
+                       void* r, double* sum_out, void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  int rc = 0;
+#define KT(I) KRhs<T, D, I, RHS_CGINIT>
+  TVDK_ISO_CALL(iso, KT,
+                (a.k = make_coefs<T>(mu, om, el, D), a.f = (const T*)f, a.t = (const T*)t, a.tcs = tcs,
+                 a.u = (const T*)u, a.x = (T*)x, a.r = (T*)r, a.fin = sum_fin(sum_out)),
+                false)
+#undef KT
+  return rc;
+}
+
+int tvdk_cg_init(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+                 const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, const void* u, void* x,
+                 void* r, double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (cginit_impl<T, D>(g, isotropic, mu, omega, ell, f, t, t_comp_stride, u, x, r, sum_out,
+                                            workspace, workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int cgpq_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* p_in,
+                     const void* r, void* p_out, const double* beta, int first, double* sum_out, void* ws,
+                     size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  typename KCg<T, D, CG_PQ>::Args a;
+  memset(&a, 0, sizeof a);
+  a.k = make_coefs<T>(nullptr, om, el, D);
+  a.p_in = (const T*)p_in; a.r_in = (const T*)r; a.p_out = (T*)p_out;
+  a.coef.p = beta; a.coef.stride = 1; a.first_all = first; a.fin = sum_fin(sum_out);
+  return run<KCg<T, D, CG_PQ>, T, D>(a, g, tune, false, sc, stream);
+}
+
+int tvdk_cg_pq(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* p_in,
+               const void* r, void* p_out, const double* beta, int first, double* sum_out, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  TVDK_TRY(check_geom(g));
+  if (p_in == p_out) return fail(TVDK_ERR_INVALID, "cg_pq is out-of-place in p");
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (cgpq_impl<T, D>(g, omega, ell, p_in, r, p_out, beta, first, sum_out, workspace,
+                                          workspace_bytes, stream)));
+  return rc;
+}
+
+template <typename T, int D>
+static int cgupd_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* pp, void* x,
+                      void* r, const double* alpha, double* sum_out, void* ws, size_t wsb, void* stream) {
+  TVDK_OP_PROLOGUE(gg)
+  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  typename KCg<T, D, CG_UPDATE>::Args a;
+  memset(&a, 0, sizeof a);
+  a.k = make_coefs<T>(nullptr, om, el, D);
+  a.p_in = (const T*)pp; a.x = (T*)x; a.r = (T*)r;
+  a.coef.p = alpha; a.coef.stride = 1; a.fin = sum_fin(sum_out);
+  return run<KCg<T, D, CG_UPDATE>, T, D>(a, g, tune, false, sc, stream);
+}
+
+int tvdk_cg_update(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* p, void* x,
+                   void* r, const double* alpha, double* sum_out, void* workspace, size_t workspace_bytes,
+                   void* stream) {
+  TVDK_TRY(check_geom(g));
+  int rc = 0;
+  TVDK_DISPATCH(*g, rc = (cgupd_impl<T, D>(g, omega, ell, p, x, r, alpha, sum_out, workspace, workspace_bytes,
+                                           stream)));
+  return rc;
+}
+

@@ -1,0 +1,261 @@
+"""Device-resident engine behind ``split_bregman_tvd``: geometry, field allocation, layout
+conversion and the call into ``tvdk_solve``.
+
+``Engine`` owns every device buffer (as torch tensors) and hands raw pointers to the C ABI.
+It is also what ``bench.py`` times: ``upload`` -> ``solve`` -> ``download``.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import torch
+
+from . import _cabi
+from ._runtime import device_guard, resolve_device, stream_ptr
+
+_TORCH_DTYPE = {_cabi.TVDK_F64: torch.float64, _cabi.TVDK_F32: torch.float32}
+_NP_CODE = {np.dtype(np.float64): _cabi.TVDK_F64, np.dtype(np.float32): _cabi.TVDK_F32}
+
+
+@dataclass
+class SolverSpec:
+    """What the kernels need to know about a ``darsia.Solver`` descriptor."""
+
+    kind: int  # _cabi.TVDK_SOLVER_*
+    maxiter: int
+    tol: Optional[float]
+
+
+@dataclass
+class SolveInfo:
+    """Per-problem outcome of one ``Engine.solve``."""
+
+    iters: np.ndarray  # outer iterations performed per problem
+    inc: np.ndarray  # last relative increment per problem
+    done: np.ndarray  # eps criterion fired
+    history: Optional[np.ndarray]  # (max_num_iter, nb) relative increments (NaN where not run)
+    energy: Optional[np.ndarray]  # (max_num_iter, nb) energies when verbose
+    launched: int  # outer iterations enqueued by the host
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One batch of ``nb`` independent ``dim``-dimensional problems of the same spatial shape."""
+
+    def __init__(
+        self,
+        spatial_shape: Sequence[int],
+        nb: int = 1,
+        dtype=np.float64,
+        device=None,
+        tile: Tuple[int, int, int] = (0, 0, 0),
+    ) -> None:
+        self.lib = _cabi.get_library()
+        self.device = resolve_device(device)
+        self.spatial = tuple(int(n) for n in spatial_shape)
+        self.dim = len(self.spatial)
+        if self.dim not in (2, 3):
+            raise ValueError(f"dim must be 2 or 3, got {self.dim}")
+        self.nb = int(nb)
+        self.np_dtype = np.dtype(dtype)
+        if self.np_dtype not in _NP_CODE:
+            raise TypeError(f"compute dtype must be float32 or float64, got {self.np_dtype}")
+        self.code = _NP_CODE[self.np_dtype]
+        self.tdtype = _TORCH_DTYPE[self.code]
+        self.tile = tuple(int(x) for x in tile)
+        g = _cabi.Geom()
+        g.dim = self.dim
+        g.dtype = self.code
+        for a in range(3):
+            g.n[a] = self.spatial[a] if a < self.dim else 1
+        g.pitch = self.lib.pitch(self.code, self.spatial[-1])
+        g.nb = self.nb
+        g.g0_off, g.g0_n, g.z_begin, g.z_end = 0, self.spatial[0], 0, self.spatial[0]
+        self.geom = g
+        self.field_elems = int(self.lib.field_elems(C.byref(g)))  # one problem
+        if self.field_elems <= 0:
+            raise ValueError(self.lib.last_error().decode())
+        self.batch_elems = self.field_elems * self.nb  # one field over all problems
+        self.nvox = int(np.prod(self.spatial))
+        self._op_ws: Optional[torch.Tensor] = None
+
+    # ------------------------------------------------------------------ allocation / layout
+    def stream(self) -> int:
+        return stream_ptr(self.lib, self.device)
+
+    def empty_fields(self, n: int = 1) -> torch.Tensor:
+        """``n`` fields (each over all problems), uninitialised."""
+        return torch.empty(n * self.batch_elems, dtype=self.tdtype, device=self.device)
+
+    def zero_fields(self, n: int = 1) -> torch.Tensor:
+        return torch.zeros(n * self.batch_elems, dtype=self.tdtype, device=self.device)
+
+    def _geom_nb(self, nb: int) -> _cabi.Geom:
+        g = _cabi.Geom.from_buffer_copy(self.geom)
+        g.nb = nb
+        return g
+
+    def to_device(self, arr: np.ndarray) -> torch.Tensor:
+        """Host array -> flat device tensor in host order (a plain H2D copy)."""
+        t = torch.from_numpy(np.ascontiguousarray(arr).reshape(-1))
+        return t.to(self.device, non_blocking=True)
+
+    def pack(self, inter: torch.Tensor, nb: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Host-order device tensor ``(voxels, nb)`` -> planar padded field(s) (``tvdk_pack``)."""
+        nb = self.nb if nb is None else nb
+        if inter.numel() != self.nvox * nb:
+            raise AssertionError(f"expected {self.nvox * nb} elements, got {inter.numel()}")
+        src_code = {torch.float64: _cabi.TVDK_F64, torch.float32: _cabi.TVDK_F32}[inter.dtype]
+        if out is None:
+            # zero-filled so that the pad columns hold finite values
+            out = torch.zeros(self.field_elems * nb, dtype=self.tdtype, device=self.device)
+        g = self._geom_nb(nb)
+        with device_guard(self.device):
+            rc = self.lib.pack(C.byref(g), src_code, inter.data_ptr(), out.data_ptr(), self.stream())
+        self.lib.check(rc, "tvdk_pack")
+        return out
+
+    def unpack(self, field: torch.Tensor, dst_dtype=None, nb: Optional[int] = None) -> torch.Tensor:
+        """Planar field(s) -> host-order device tensor ``(voxels, nb)`` (``tvdk_unpack``)."""
+        nb = self.nb if nb is None else nb
+        dst_dtype = self.np_dtype if dst_dtype is None else np.dtype(dst_dtype)
+        code = _NP_CODE[dst_dtype]
+        out = torch.empty(self.nvox * nb, dtype=_TORCH_DTYPE[code], device=self.device)
+        g = self._geom_nb(nb)
+        with device_guard(self.device):
+            rc = self.lib.unpack(C.byref(g), code, field.data_ptr(), out.data_ptr(), self.stream())
+        self.lib.check(rc, "tvdk_unpack")
+        return out
+
+    def upload(self, img: np.ndarray) -> torch.Tensor:
+        """Host image ``(*spatial, *batch)`` -> field (H2D copy + layout kernel)."""
+        return self.pack(self.to_device(img))
+
+    def download(self, field: torch.Tensor, out_dtype=None, shape=None) -> np.ndarray:
+        """Field -> host array ``(*spatial, *batch)``."""
+        inter = self.unpack(field, out_dtype)
+        host = inter.cpu().numpy()
+        return host.reshape(shape if shape is not None else (*self.spatial, self.nb))
+
+    def coef(self, value, full_shape: Optional[tuple] = None, name: str = "coefficient"):
+        """Scalar or per-voxel coefficient -> (``tvdk_coef_t``, keep-alive tensor)."""
+        c = _cabi.Coef()
+        if isinstance(value, torch.Tensor) and value.device == self.device and value.dim() == 1:
+            # already a packed field (shared map or per problem)
+            if value.numel() not in (self.field_elems, self.batch_elems):
+                raise AssertionError(f"{name}: packed field has the wrong size")
+            c.device_ptr = value.data_ptr()
+            c.value = 0.0
+            c.batch_stride = self.field_elems if (self.nb > 1 and value.numel() == self.batch_elems) else 0
+            return c, value
+        arr = np.asarray(value)
+        if arr.ndim == 0:
+            c.device_ptr = None
+            c.value = float(arr)
+            c.batch_stride = 0
+            return c, None
+        if arr.shape == self.spatial:
+            nbc = 1
+        elif full_shape is not None and arr.shape == tuple(full_shape):
+            nbc = self.nb
+        else:
+            raise AssertionError(
+                f"{name} of shape {arr.shape} matches neither the spatial shape {self.spatial} nor the image shape"
+            )
+        field = self.pack(self.to_device(arr.astype(self.np_dtype, copy=False)), nb=nbc)
+        c.device_ptr = field.data_ptr()
+        c.value = 0.0
+        c.batch_stride = self.field_elems if nbc > 1 else 0
+        return c, field
+
+    def op_workspace(self) -> torch.Tensor:
+        if self._op_ws is None:
+            n = int(self.lib.op_workspace_bytes(C.byref(self.geom)))
+            self._op_ws = torch.empty(n, dtype=torch.uint8, device=self.device)
+        return self._op_ws
+
+    # ------------------------------------------------------------------ the outer loop
+    def solve(
+        self,
+        f: torch.Tensor,
+        u: torch.Tensor,
+        t: torch.Tensor,
+        mu,
+        omega,
+        ell,
+        isotropic: bool,
+        solver: SolverSpec,
+        max_num_iter: int,
+        eps: Optional[float],
+        x0_db: Optional[Tuple[torch.Tensor, torch.Tensor]] = None,
+        verbose_every: int = 0,
+        record_history: bool = False,
+        fused: bool = True,
+        check_every: int = 8,
+        full_shape: Optional[tuple] = None,
+        sync: bool = True,
+    ) -> Optional[SolveInfo]:
+        """Run ``tvdk_solve`` on resident fields: ``u`` (in: initial iterate, out: result) and the
+        compressed state ``t`` are updated in place.  With ``sync=False`` nothing is read back
+        (``None`` is returned) and the call only enqueues work.
+        """
+        lib = self.lib
+        p = _cabi.Problem()
+        p.geom = self.geom
+        p.isotropic = 1 if isotropic else 0
+        p.solver_kind = solver.kind
+        p.solver_maxiter = int(solver.maxiter)
+        p.solver_tol = -1.0 if solver.tol is None else float(solver.tol)
+        p.max_num_iter = int(max_num_iter)
+        p.eps = -1.0 if eps is None else float(eps)
+        keep = []
+        for name, val in (("mu", mu), ("omega", omega), ("ell", ell)):
+            c, k = self.coef(val, full_shape, name)
+            setattr(p, name, c)
+            keep.append(k)
+        p.f, p.u, p.t = f.data_ptr(), u.data_ptr(), t.data_ptr()
+        p.t_comp_stride = self.batch_elems
+        if x0_db is not None:
+            p.x0_d, p.x0_b = x0_db[0].data_ptr(), x0_db[1].data_ptr()
+            p.x0_comp_stride = self.batch_elems
+        p.verbose_every = int(verbose_every)
+        p.check_every = int(check_every)
+        p.fused = 1 if fused else 0
+        p.tile_x, p.tile_y, p.zchunk = self.tile
+        nbytes = int(lib.workspace_bytes(C.byref(p)))
+        if nbytes == 0:
+            raise ValueError(lib.last_error().decode())
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        stats = torch.zeros(self.nb * C.sizeof(_cabi.Stat), dtype=torch.uint8, device=self.device)
+        hist = ehist = None
+        if record_history or verbose_every > 0:
+            hist = torch.full((max(max_num_iter, 1) * self.nb,), float("nan"), dtype=torch.float64, device=self.device)
+        if verbose_every > 0:
+            ehist = torch.full((max(max_num_iter, 1) * self.nb,), float("nan"), dtype=torch.float64, device=self.device)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+        p.stats = stats.data_ptr()
+        p.history, p.energy_history = _ptr(hist), _ptr(ehist)
+        launched = C.c_int(0)
+        with device_guard(self.device):
+            rc = lib.solve(C.byref(p), self.stream(), C.byref(launched))
+        lib.check(rc, "tvdk_solve")
+        self._last = (ws, stats, hist, ehist, keep)  # keep alive until the stream has consumed them
+        if not sync:
+            return None
+        raw = stats.cpu().numpy().tobytes()  # synchronises the stream
+        recs = (_cabi.Stat * self.nb).from_buffer_copy(raw)
+        return SolveInfo(
+            iters=np.array([r.iters for r in recs]),
+            inc=np.array([r.inc for r in recs]),
+            done=np.array([bool(r.done) for r in recs]),
+            history=None if hist is None else hist.cpu().numpy().reshape(-1, self.nb),
+            energy=None if ehist is None else ehist.cpu().numpy().reshape(-1, self.nb),
+            launched=int(launched.value),
+        )

@@ -1,0 +1,2 @@
+from .split_bregman_tvd import split_bregman_tvd  # noqa: F401
+from .tvd import TVD, tvd  # noqa: F401

@@ -1,0 +1,168 @@
+"""``darsia.split_bregman_tvd`` on B200: same signature, device-resident outer loop.
+
+Reference: ``restoration/split_bregman_tvd.py:14-177``.  The host code below only validates
+arguments, moves the image to the GPU, calls ``tvdk_solve`` (one C-ABI call for the whole
+outer loop) and brings the result back; there is no CPU fallback.
+
+Policy on the reference's quirks:
+  Q2  a fresh solver state per call;  Q3  isotropic works for any dim / dtype / per-voxel mu;
+  Q5/Q6  axes beyond ``dim`` are independent problems;  Q10  integer images raise TypeError;
+  Q11 ``verbose=0`` is silent;  Q12  non-positive ``ell`` raises ValueError.
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Union
+
+import numpy as np
+
+from .. import _cabi
+from ..engine import Engine, SolveInfo, SolverSpec
+from ..utils.linear_solvers import CG, Jacobi, Solver
+
+Coeff = Union[float, int, np.ndarray]
+
+
+def _solver_spec(solver: Optional[Solver]) -> SolverSpec:
+    if solver is None:
+        solver = Jacobi()
+    kind = getattr(solver, "kind", None)
+    if kind not in (_cabi.TVDK_SOLVER_JACOBI, _cabi.TVDK_SOLVER_CG):
+        raise NotImplementedError(
+            f"inner solver {type(solver).__name__} is not implemented on the GPU (Jacobi and CG are); "
+            "darsia_b200 has no CPU fallback"
+        )
+    maxiter = int(solver.maxiter)
+    if maxiter < 1:
+        raise ValueError("solver.maxiter must be >= 1")
+    tol = solver.tol
+    if kind == _cabi.TVDK_SOLVER_CG and tol is None:
+        raise TypeError("CG needs a numeric tol (SciPy rejects rtol=None); use tol=0.0 for a fixed iteration count")
+    return SolverSpec(kind=kind, maxiter=maxiter, tol=None if tol is None else float(tol))
+
+
+def _check_positive(name: str, c: Coeff) -> None:
+    a = np.asarray(c)
+    if not np.all(a > 0):
+        raise ValueError(f"{name} must be positive everywhere (the reference divides by it; SURVEY Q12)")
+
+
+def split_bregman_tvd(
+    img: np.ndarray,
+    mu: Coeff = 1.0,
+    omega: Coeff = 1.0,
+    ell: Optional[Coeff] = None,
+    dim: int = 2,
+    max_num_iter: int = 100,
+    eps: Optional[float] = None,
+    x0: Optional[tuple] = None,
+    isotropic: bool = False,
+    verbose: Union[bool, int] = False,
+    solver: Optional[Solver] = None,
+    adaptive=None,
+    *,
+    precision: Optional[str] = None,
+    device=None,
+    return_info: bool = False,
+    fused: bool = True,
+    tile=(0, 0, 0),
+):
+    """Split Bregman algorithm for TV denoising (drop-in for ``darsia.split_bregman_tvd``).
+
+    Args (as the reference, ``split_bregman_tvd.py:28-49``):
+        img: float image, spatial axes first; axes beyond ``dim`` are independent problems.
+        mu, omega, ell: scalar, an array of the spatial shape (shared by all problems) or of
+            the full image shape.  ``ell=None`` means ``2 * mu``.
+        dim, max_num_iter, eps, x0, isotropic, verbose, solver: as the reference.
+        adaptive: not implemented on the GPU (``NotImplementedError`` when not ``None``).
+    Additive keyword-only arguments:
+        precision: ``"fp64"`` / ``"fp32"`` compute precision (default: the image's dtype).
+        device: CUDA device (default: the current one).
+        return_info: also return a ``SolveInfo`` (iterations, increments, history).
+        fused: allow the fused one-kernel-per-iteration path (default True).
+        tile: (block_x, block_y, planes_per_block) launch-shape override, 0 = default (tuning/tests).
+    """
+    if not isinstance(img, np.ndarray):
+        raise TypeError(f"Input type {type(img)} not supported.")
+    if not np.issubdtype(img.dtype, np.floating) or img.dtype not in (np.float32, np.float64):
+        raise TypeError(
+            f"float32/float64 images only, got {img.dtype} (the reference mixes rescaled and raw integers, SURVEY Q10)"
+        )
+    if adaptive is not None:
+        raise NotImplementedError("the adaptive ell schedule is not implemented on the GPU path")
+    if dim not in (2, 3):
+        raise ValueError(f"dim must be 2 or 3, got {dim}")
+    if img.ndim < dim:
+        raise AssertionError("image has fewer axes than dim")
+    spec = _solver_spec(solver)
+    if ell is None:  # split_bregman_tvd.py:62-63
+        ell = 2 * mu
+    _check_positive("ell", ell)
+
+    if precision is None:
+        cdtype = img.dtype
+    elif precision in ("fp64", "float64"):
+        cdtype = np.dtype(np.float64)
+    elif precision in ("fp32", "float32"):
+        cdtype = np.dtype(np.float32)
+    else:
+        raise ValueError(f"precision must be 'fp64' or 'fp32', got {precision!r}")
+
+    spatial = img.shape[:dim]
+    nb = int(np.prod(img.shape[dim:], dtype=np.int64))
+    if img.size == 0:
+        return (img.copy(), None) if return_info else img.copy()
+    eng = Engine(spatial, nb=nb, dtype=cdtype, device=device, tile=tile)
+
+    f = eng.upload(img)
+    x0_db = None
+    if x0 is not None:  # split_bregman_tvd.py:93-97
+        u0, d0, b0 = x0
+        u0, d0, b0 = np.asarray(u0), np.asarray(d0), np.asarray(b0)
+        assert u0.shape == img.shape and d0.shape == (*img.shape, dim) and b0.shape == (*img.shape, dim)
+        u = eng.upload(u0.astype(img.dtype, copy=False))
+        # component axis last in the reference; planar components on the device
+        d_pl = eng.empty_fields(dim)
+        b_pl = eng.empty_fields(dim)
+        for a in range(dim):
+            sl = slice(a * eng.batch_elems, (a + 1) * eng.batch_elems)
+            d_pl[sl] = eng.upload(np.ascontiguousarray(d0[..., a]).astype(img.dtype, copy=False))
+            b_pl[sl] = eng.upload(np.ascontiguousarray(b0[..., a]).astype(img.dtype, copy=False))
+        x0_db = (d_pl, b_pl)
+    else:  # split_bregman_tvd.py:99-101
+        u = f.clone()
+    t = eng.zero_fields(dim)
+
+    if isinstance(verbose, bool):
+        verbose_every = 1 if verbose else 0
+    else:
+        verbose_every = int(verbose) if verbose and verbose > 0 else 0  # Q11: 0 is silent
+
+    info: SolveInfo = eng.solve(
+        f, u, t, mu, omega, ell, isotropic, spec, max_num_iter, eps,
+        x0_db=x0_db, verbose_every=verbose_every, record_history=return_info, fused=fused,
+        full_shape=img.shape,
+    )
+    if verbose_every:
+        _print_verbose(info, verbose_every)
+    out = eng.download(u, img.dtype, img.shape)  # convert_dtype, split_bregman_tvd.py:177
+    return (out, info) if return_info else out
+
+
+def _print_verbose(info: SolveInfo, every: int) -> None:
+    """The reference's progress lines (split_bregman_tvd.py:103-104, 162-167), printed after
+    the device-resident loop has finished (one line per problem when batched)."""
+    hist, en = info.history, info.energy
+    if hist is None or en is None:
+        return
+    nb = hist.shape[1]
+    for b in range(nb):
+        tag = f"[problem {b}] " if nb > 1 else ""
+        if info.iters[b] > 0 or hist.shape[0] > 0:
+            print(f"{tag}The energy functional starts at {en[0, b]}")
+        for it in range(int(info.iters[b])):
+            if it % every == 0:
+                print(
+                    f"{tag}Split Bregman iteration {it} - relative increment: {hist[it, b]}, "
+                    f"energy functional: {en[it, b]}"
+                )

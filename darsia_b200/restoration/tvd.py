@@ -1,0 +1,81 @@
+"""``darsia.TVD`` / ``darsia.tvd`` with the heterogeneous split-Bregman method on the GPU.
+
+Reference: ``restoration/tvd.py:15-163``.  Only ``method="heterogeneous bregman"`` is
+implemented here (the path BASELINE.json names); the skimage-backed methods ("chambolle",
+"anisotropic bregman", "isotropic bregman", ``tvd.py:77-101``) are a different algorithm and
+stay with DarSIA/scikit-image -- asking for them raises ``NotImplementedError`` rather than
+silently running something else.
+"""
+
+from __future__ import annotations
+
+from typing import Union
+
+import numpy as np
+
+from ..image import is_image_like
+from .split_bregman_tvd import split_bregman_tvd
+
+
+class TVD:
+    """Total variation denoising interface (``restoration/tvd.py:15-129``)."""
+
+    def __init__(self, key: str = "", **kwargs) -> None:
+        # tvd.py:31-43 -- method/weight/max_num_iter/eps honour the key prefix, omega and
+        # regularization do not; regularization is popped (Q1: the reference
+        # leaves it in kwargs and then crashes, so through this class ell is 1.0 unless given).
+        self.method = kwargs.pop(key + "method", "chambolle").lower()
+        if self.method == "heterogeneous bregman":
+            self.omega = kwargs.pop("omega", 1)
+            self.regularization = kwargs.pop("regularization", 1.0)
+        self.weight = kwargs.pop(key + "weight", 0.1)
+        self.max_num_iter = kwargs.pop(key + "max_num_iter", 200)
+        self.eps = kwargs.pop(key + "eps", 2e-4)
+        self.kwargs = kwargs
+
+    # NOTE: exactly two positional parameters -- CombinedModel inspects
+    # model.__call__.__code__.co_argcount == 2 (signals/models/combinedmodel.py:47-48, Q16)
+    def __call__(self, img):
+        if isinstance(img, np.ndarray):
+            return self._tvd_array(img)
+        elif is_image_like(img):
+            return self._tvd_image(img)
+        else:
+            raise TypeError(f"Input type {type(img)} not supported.")
+
+    def _tvd_array(self, img: np.ndarray) -> np.ndarray:
+        if self.method == "heterogeneous bregman":  # tvd.py:103-112
+            return split_bregman_tvd(
+                img,
+                mu=self.weight,
+                omega=self.omega,
+                ell=self.regularization,
+                max_num_iter=self.max_num_iter,
+                eps=self.eps,
+                **self.kwargs,
+            )
+        elif self.method in ("chambolle", "anisotropic bregman", "isotropic bregman"):
+            raise NotImplementedError(
+                f"method {self.method!r} is scikit-image's algorithm (tvd.py:77-101) and is not part of the "
+                "B200 path; use method='heterogeneous bregman'"
+            )
+        else:
+            raise ValueError(f"Method {self.method} not supported.")
+
+    def _tvd_image(self, img):
+        img_copy = img.copy()  # tvd.py:127-129
+        img_copy.img = self._tvd_array(img.img)
+        return img_copy
+
+
+def tvd(
+    img,
+    method: str = "chambolle",
+    weight: Union[float, np.ndarray] = 1.0,
+    max_num_iter: int = 200,
+    eps: float = 2e-4,
+    **kwargs,
+):
+    """Inline application of TVD (``restoration/tvd.py:132-163``)."""
+    op = TVD(method=method, weight=weight, max_num_iter=max_num_iter, eps=eps, **kwargs)
+    return op(img)

@@ -1,0 +1,217 @@
+/*
+ * tvdk.h -- C ABI of libtvdk, the B200-native (sm_100a) split-Bregman TV denoising kernels.
+ *
+ * This is the drop-in boundary of the hot path.  The DarSIA reference is pure Python and has
+ * no FFI layer; the "interface" each entry point replaces is the Python callable cited beside
+ * it (paths relative to /root/reference/src/darsia/).  The binding a maintainer would add on
+ * the reference side (ctypes) is shown in INTEGRATION.md; darsia_b200/_cabi.py is that binding.
+ *
+ * Conventions
+ *   - every pointer named "device" is a raw CUDA device pointer owned by the caller (PyTorch);
+ *     the library allocates nothing persistent on the device and frees nothing it did not
+ *     allocate; the workspace is caller-provided (size from tvdk_workspace_bytes);
+ *   - every function returns 0 on success, a negative tvdk error code, or a positive
+ *     cudaError_t; tvdk_last_error() returns a thread-local message;
+ *   - "stream" is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - no global mutable state besides the thread-local error string: safe to drive 8 GPUs
+ *     from 8 threads or 8 processes.
+ *
+ * Device data layout ("field"): batch-major planar, last axis contiguous and padded to
+ * `pitch` elements (a multiple of 16 bytes so every row start is 128-bit aligned):
+ *     2-D: field[b][i0][pitch]            3-D: field[b][i0][i1][pitch]
+ * The split-Bregman state is kept COMPRESSED: instead of the reference's d and b arrays
+ * (split_bregman_tvd.py:100-101) the library stores t_a = grad_a(u) + b_a (one field per
+ * spatial axis), from which d_a = shrink(t)_a and b_a = t_a - d_a are recomputed with the
+ * reference's own arithmetic (split_bregman_tvd.py:117-126, 142-146) wherever they are
+ * needed.  Component a of t lives at t + a * comp_stride elements.
+ */
+#ifndef TVDK_H
+#define TVDK_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TVDK_VERSION 100 /* 0.1.0 */
+
+/* error codes (negative) */
+#define TVDK_OK 0
+#define TVDK_ERR_INVALID (-1)   /* bad argument */
+#define TVDK_ERR_UNSUPPORTED (-2) /* valid in DarSIA, not implemented here */
+#define TVDK_ERR_WORKSPACE (-3) /* workspace too small */
+#define TVDK_ERR_NODEVICE (-4)  /* no CUDA device / wrong architecture */
+
+/* dtype codes */
+#define TVDK_F64 0
+#define TVDK_F32 1
+
+/* solver kinds: darsia.Jacobi (utils/linear_solvers/jacobi.py:14), darsia.CG (cg.py:10) */
+#define TVDK_SOLVER_JACOBI 0
+#define TVDK_SOLVER_CG 1
+
+/* Geometry of one batch of independent dim-dimensional problems. */
+typedef struct tvdk_geom {
+  int32_t dim;      /* 2 or 3 (split_bregman_tvd.py:19 `dim`) */
+  int32_t dtype;    /* TVDK_F64 / TVDK_F32 */
+  int32_t n[3];     /* local extents, slowest first; n[2] unused for dim == 2 */
+  int32_t pitch;    /* elements per row of the last axis, multiple of 16 bytes */
+  int32_t nb;       /* number of independent problems (channels / frames), >= 1 */
+  /* Slab decomposition along axis 0 (multi-GPU, one volume): the local array holds planes
+   * [0, n[0]) of which [z_begin, z_end) are owned/computed; local plane 0 is global plane
+   * g0_off of g0_n.  Single GPU: g0_off = 0, g0_n = n[0], z_begin = 0, z_end = n[0]. */
+  int32_t g0_off;
+  int32_t g0_n;
+  int32_t z_begin;
+  int32_t z_end;
+} tvdk_geom_t;
+
+/* A coefficient (mu / omega / ell of split_bregman_tvd.py:16-18): scalar, or a per-voxel
+ * field with the geometry's layout; batch_stride = 0 shares one map between all problems. */
+typedef struct tvdk_coef {
+  const void* device_ptr; /* NULL -> scalar `value` */
+  double value;
+  int64_t batch_stride;   /* elements; 0 or the field size */
+} tvdk_coef_t;
+
+/* Per-problem result record written by tvdk_solve (device memory, nb entries). */
+typedef struct tvdk_stat {
+  double nrm_f;     /* ||img||_2                       (split_bregman_tvd.py:58)  */
+  double inc;       /* last relative increment          (split_bregman_tvd.py:161) */
+  double energy;    /* last energy functional if asked  (split_bregman_tvd.py:71-77) */
+  double bnrm, atol, rho, rho_prev, pq, alpha, beta; /* CG scalars (scipy cg recurrence) */
+  double jac_x0nrm2, jac_err;                        /* Jacobi tol branch (jacobi.py:118-131) */
+  int32_t iters;    /* outer iterations performed */
+  int32_t done;     /* 1 once inc < eps fired       (split_bregman_tvd.py:173-175) */
+  int32_t cg_stop, cg_first, cg_iters;
+  int32_t jac_stop, jac_sel;
+  int32_t cur_buf;  /* internal: which buffer holds the iterate */
+} tvdk_stat_t;
+
+/* One call of darsia.split_bregman_tvd (restoration/split_bregman_tvd.py:14-27). */
+typedef struct tvdk_problem {
+  tvdk_geom_t geom;
+  int32_t isotropic;       /* split_bregman_tvd.py:23 */
+  int32_t solver_kind;     /* TVDK_SOLVER_* */
+  int32_t solver_maxiter;  /* Solver.maxiter (solver.py:20) */
+  int32_t max_num_iter;    /* split_bregman_tvd.py:20 */
+  double solver_tol;       /* Solver.tol; < 0 means None (Jacobi only) */
+  double eps;              /* < 0 means None (split_bregman_tvd.py:21) */
+  tvdk_coef_t mu, omega, ell;
+  const void* f;           /* device: image field (read only) */
+  void* u;                 /* device: in = initial iterate (copy of f, or x0[0]); out = result */
+  void* t;                 /* device: dim fields, compressed state; in = zeros unless warm start */
+  int64_t t_comp_stride;   /* elements between components of t */
+  /* Warm start x0 = (u0, d0, b0) (split_bregman_tvd.py:93-97): d0/b0 as planar fields; the
+   * first outer iteration reads them explicitly, afterwards the state is compressed. */
+  const void* x0_d;        /* device or NULL */
+  const void* x0_b;        /* device or NULL */
+  int64_t x0_comp_stride;
+  void* workspace;         /* device, tvdk_workspace_bytes() bytes, 256-byte aligned */
+  size_t workspace_bytes;
+  tvdk_stat_t* stats;      /* device, nb entries */
+  double* history;         /* device or NULL: max_num_iter * nb relative increments */
+  double* energy_history;  /* device or NULL: energies (verbose), max_num_iter * nb */
+  int32_t verbose_every;   /* 0 = never compute the energy functional */
+  int32_t check_every;     /* host polls the device "all done" flag every N outer iterations */
+  int32_t fused;           /* 1 = allow the fused per-iteration kernels (default), 0 = building blocks only */
+  int32_t tile_x, tile_y, zchunk; /* 0 = library default; thread-block shape / planes per CTA */
+} tvdk_problem_t;
+
+int tvdk_version(void);
+const char* tvdk_last_error(void);
+/* 1 if a CUDA device of compute capability 10.x is current, else 0 (and sets last_error). */
+int tvdk_device_ok(void);
+
+/* Recommended pitch (elements) for a last-axis extent. */
+int tvdk_pitch(int dtype, int n_last);
+/* Elements of one field (n0*[n1*]pitch) and of one batch of fields. */
+int64_t tvdk_field_elems(const tvdk_geom_t* g);
+
+/* Workspace needed by tvdk_solve for this problem (device pointers are ignored). */
+size_t tvdk_workspace_bytes(const tvdk_problem_t* p);
+
+/* The whole outer loop of darsia.split_bregman_tvd (split_bregman_tvd.py:129-175), device
+ * resident; returns after enqueueing (and polling for convergence when eps >= 0).
+ * `iters_launched` (host, may be NULL) receives the number of outer iterations enqueued. */
+int tvdk_solve(const tvdk_problem_t* p, void* stream, int* iters_launched);
+
+/* Layout conversion between the host-order array (spatial axes..., batch axes flattened last,
+ * C-contiguous: element (i, b) at i*nb + b) and the planar padded device layout, with dtype
+ * cast.  src/dst are device pointers.  (replaces img.copy()/img_as_float, :99, and the final
+ * convert_dtype, split_bregman_tvd.py:177) */
+int tvdk_pack(const tvdk_geom_t* g, int src_dtype, const void* src_interleaved, void* dst_field, void* stream);
+int tvdk_unpack(const tvdk_geom_t* g, int dst_dtype, const void* src_field, void* dst_interleaved, void* stream);
+
+/* ---- test-granularity operators (each one is one kernel launch) -------------------------- */
+
+/* rhs = omega*f + sum_a H_a(ell*(b_a - d_a)) from the compressed state t
+ * (split_bregman_tvd.py:84-89 `_rhs_function`). */
+int tvdk_rhs(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+             const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, void* rhs,
+             void* workspace, size_t workspace_bytes, void* stream);
+
+/* One Jacobi sweep x_out = rhs/diag + N(x_in)/(diag/ell) (jacobi.py:101-114). */
+int tvdk_jacobi_sweep(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell,
+                      const void* x_in, const void* rhs, void* x_out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* y = omega*x - laplace(x, diffusion_coeff=ell) (cg.py:37-44, derivatives.py:88-104). */
+int tvdk_cg_matvec(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell,
+                   const void* x, void* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Shrinkage + Bregman update on the compressed state: t_out = grad(u_new) + b(t_in)
+ * (split_bregman_tvd.py:136-146); sum_out[b] (device, doubles) = ||u_new - u_old||^2. */
+int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                const void* u_new, const void* u_old, const void* t_in, void* t_out,
+                int64_t t_comp_stride, double* sum_out, void* workspace, size_t workspace_bytes,
+                void* stream);
+
+/* Expand the compressed state into the reference's d and b (planar fields, dim each). */
+int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu,
+                      const tvdk_coef_t* ell, const void* t, int64_t t_comp_stride, void* d, void* b,
+                      int64_t db_comp_stride, void* stream);
+
+/* Deterministic reductions over the valid voxels of each problem: out[b] (device doubles). */
+int tvdk_dot(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
+             size_t workspace_bytes, void* stream);
+int tvdk_norm_diff2(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
+                    size_t workspace_bytes, void* stream);
+
+/* Energy functional 1/2||omega(x-f)||^2 + sum_a sum |mu G_a x| (split_bregman_tvd.py:71-77). */
+int tvdk_energy(const tvdk_geom_t* g, const tvdk_coef_t* mu, const tvdk_coef_t* omega, const void* x,
+                const void* f, double* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Workspace needed by the single-operator entry points above. */
+size_t tvdk_op_workspace_bytes(const tvdk_geom_t* g);
+
+/* One fused outer iteration with Jacobi(maxiter=1): (u_in, t_in) -> (u_out, t_out), and
+ * sum_out[b] = ||u_out - u_in||^2 (the K1 kernel; used by the slab-decomposed driver). */
+int tvdk_fused_jacobi1(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu,
+                       const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* f,
+                       const void* u_in, void* u_out, const void* t_in, void* t_out,
+                       int64_t t_comp_stride, double* sum_out, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
+/* CG building blocks for the slab-decomposed driver (scalars supplied by the caller after the
+ * cross-rank reduction; each returns per-problem partial sums in sum_out, device doubles).
+ *   cg_init:   r = rhs(t,f) - A u ; x = u ; sum_out[2b] = ||rhs||^2, sum_out[2b+1] = r.r
+ *   cg_pq:     p_out = first ? r : beta[b]*p_in + r ; sum_out[b] = p_out . (A p_out)
+ *   cg_update: x += alpha[b]*p ; r -= alpha[b]*(A p) ; sum_out[b] = r.r                      */
+int tvdk_cg_init(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+                 const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride,
+                 const void* u, void* x, void* r, double* sum_out, void* workspace,
+                 size_t workspace_bytes, void* stream);
+int tvdk_cg_pq(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell,
+               const void* p_in, const void* r, void* p_out, const double* beta, int first,
+               double* sum_out, void* workspace, size_t workspace_bytes, void* stream);
+int tvdk_cg_update(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell,
+                   const void* p, void* x, void* r, const double* alpha, double* sum_out,
+                   void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TVDK_H */

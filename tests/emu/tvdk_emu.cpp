@@ -1,0 +1,84 @@
+// tvdk_emu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// A CPU "thread stepper" for the kernel functors of darsia_b200/csrc/tvdk_core.h: the very same
+// kernel source is compiled with g++ and every thread of a block is advanced phase by phase
+// (init | pre | barrier | post ...), blocks one after another.  It exposes the same C ABI as
+// libtvdk.so with host pointers in place of device pointers, so the CPU test-suite can check
+// the kernels' index/halo/boundary logic, the host driver and the multi-rank (gloo) paths
+// against the oracle without a GPU.  The product (darsia_b200) never loads this library: its
+// loader only accepts darsia_b200/csrc/libtvdk.so and a CUDA device.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../darsia_b200/csrc/tvdk_core.h"
+
+namespace tvdk {
+namespace backend {
+
+template <class K>
+int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem_bytes, void*,
+           double*, unsigned*) {
+  const int nthreads = ntx * nty;
+  std::vector<K> th(nthreads);
+  std::vector<unsigned char> smem_store(smem_bytes + 64, 0);
+  // 16-byte aligned base, like the device's dynamic shared memory
+  unsigned char* smem = smem_store.data();
+  smem += (16 - (reinterpret_cast<uintptr_t>(smem) & 15)) & 15;
+  constexpr int NR = K::NRED > 0 ? K::NRED : 1;
+  for (int bz = 0; bz < gz; ++bz) {
+    double tot[NR];
+    for (int r = 0; r < NR; ++r) tot[r] = 0.0;
+    bool any = false;
+    for (int by = 0; by < gy; ++by)
+      for (int bx = 0; bx < gx; ++bx) {
+        int alive = 0;
+        for (int t = 0; t < nthreads; ++t) {
+          LaunchCtx lc;
+          lc.tx = t % ntx; lc.ty = t / ntx; lc.ntx = ntx; lc.nty = nty;
+          lc.bx = bx; lc.by = by; lc.bz = bz; lc.nbx = gx; lc.nby = gy;
+          alive += th[t].init(a, lc, smem) ? 1 : 0;
+        }
+        if (alive == 0) continue;
+        if (alive != nthreads) abort();  // early exit must be block-uniform
+        any = true;
+        while (th[0].more()) {
+          for (int t = 0; t < nthreads; ++t) th[t].pre(a, smem);
+          for (int t = 0; t < nthreads; ++t) th[t].post(a, smem);
+        }
+        if (K::NRED > 0) {
+          double blk[NR];
+          for (int r = 0; r < NR; ++r) blk[r] = 0.0;
+          for (int t = 0; t < nthreads; ++t)
+            for (int r = 0; r < K::NRED; ++r) blk[r] += th[t].red[r];
+          for (int r = 0; r < NR; ++r) tot[r] += blk[r];
+        }
+      }
+    if (K::NRED > 0 && any) K::finalize(a, bz, tot);
+  }
+  return 0;
+}
+
+static int memset_async(void* p, int value, size_t bytes, void*) {
+  memset(p, value, bytes);
+  return 0;
+}
+static int g_poll_val[2];
+static int poll_begin(int slot, const int* flag, void*) {
+  g_poll_val[slot] = *flag;
+  return 0;
+}
+static int poll_end(int slot, int* value) {
+  *value = g_poll_val[slot];
+  return 0;
+}
+static int device_ok(char*, size_t) { return 1; }
+
+}  // namespace backend
+}  // namespace tvdk
+
+#include "../../darsia_b200/csrc/tvdk_host.inl"
+
+extern "C" int tvdk_is_emulator(void) { return 1; }
