@@ -1,0 +1,446 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the split-Bregman TVD hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+Metric (BASELINE.json): TVD Mvoxel*iter/s -- voxels (all channels/frames) x OUTER Bregman
+iterations per second.  One "step" is one whole solve (``tvd()`` with a fixed number of outer
+iterations) of one synthetic image batch.
+
+Workload at N = 1 is BASELINE.json configs[1]: a 2-D 4000x7000 3-channel fp64 image, isotropic
+TVD, CG(maxiter=10, tol=0) inner solver, 100 outer iterations.  At N > 1 every rank solves its
+own image of that shape (frames of a series sharded over ranks: no data-path collective, weak
+scaling), the value is the whole-job aggregate over the max-over-ranks time.
+
+Printed JSON (one line, rank 0): see the driver contract; additionally
+  roofline     dominant kernel (the CG update kernel), achieved algorithmic GB/s vs measured peak
+  cpu_baseline the NumPy oracle (a port of the reference's algorithm) on the host cores
+  e2e          same metric through darsia_b200.tvd() with HOST buffers, copies inside the timing
+"""
+
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: spatial shape, channels, dtype, isotropic, solver (kind, maxiter, tol), outer iterations, hetero
+    "cfg2_2d_iso_cg10": dict(shape=(4000, 7000), nb=3, dtype="float64", iso=True, solver=("cg", 10, 0.0),
+                             outer=100, hetero=False),
+    "cfg1_2d_aniso_j1": dict(shape=(1788, 3180), nb=1, dtype="float64", iso=False, solver=("jacobi", 1, None),
+                             outer=100, hetero=False),
+    "cfg3_2d_hetero_j1": dict(shape=(4000, 7000), nb=8, dtype="float64", iso=False, solver=("jacobi", 1, None),
+                              outer=100, hetero=True),
+    "cfg5_3d_aniso_j1_f32": dict(shape=(512, 512, 512), nb=1, dtype="float32", iso=False,
+                                 solver=("jacobi", 1, None), outer=50, hetero=False),
+    "small": dict(shape=(512, 768), nb=3, dtype="float64", iso=True, solver=("cg", 10, 0.0), outer=10, hetero=False),
+}
+DEFAULT_WORKLOAD = "cfg2_2d_iso_cg10"
+MU, OMEGA, ELL = 0.1, 1.0, 1.0
+
+
+def algo_words_per_voxel_iter(dim: int, solver, hetero_arrays: int = 0) -> float:
+    """Algorithmic words per voxel and outer iteration of the IMPLEMENTED formulation
+    (compressed state t, q = A p recomputed)."""
+    kind, m, _ = solver
+    D = dim
+    if kind == "jacobi" and m == 1:
+        return 3 + 2 * D + hetero_arrays  # read u f t(D), write u t(D)
+    if kind == "jacobi":
+        # rhs+sweep1: read f t(D) u, write rhs x ; middle sweeps: 3 each ; shrink: read u+ u t(D), write u t(D)
+        return (2 + D + 2) + 3 * (m - 1) + (2 + D + 1 + D)
+    # CG: init: read f t(D) u, write x r ; per iteration: pq 3 (read p r, write p) + update 5 (read p x r, write x r)
+    return (2 + D + 2) + 8 * m + (2 + D + 1 + D)
+
+
+def phantom_np(shape, seed, dtype):
+    """Seeded synthetic image: piecewise-constant blocks + noise, clipped to [0, 1]."""
+    rng = np.random.default_rng(seed)
+    spatial = shape
+    idx = np.indices(spatial, sparse=True)
+    cells = [max(2, n // 8) for n in spatial]
+    checker = sum((idx[a] // cells[a]) for a in range(len(spatial))) % 3
+    base = np.choose(checker, [0.2, 0.5, 0.8])
+    img = base + 0.1 * rng.standard_normal(spatial, dtype=np.float32)
+    return np.clip(img, 0.0, 1.0).astype(dtype)
+
+
+def make_host_image(w, seed):
+    chans = [phantom_np(w["shape"], seed + c, w["dtype"]) for c in range(w["nb"])]
+    return np.stack(chans, axis=-1) if w["nb"] > 1 else chans[0]
+
+
+def hetero_maps(w, seed):
+    rng = np.random.default_rng(seed + 1000)
+    shape = w["shape"]
+    mu = (0.1 * (0.5 + 0.5 * rng.random(shape, dtype=np.float32))).astype(w["dtype"])
+    mu[rng.random(shape, dtype=np.float32) < 0.1] = 0.0  # 10 % zero mask (workflow-style weight*mask)
+    om = (0.5 + 1.5 * rng.random(shape, dtype=np.float32)).astype(w["dtype"])
+    return mu, om
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampler (nvidia-smi while the timed region runs)
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int) -> None:
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the NumPy oracle (port of the reference's algorithm) on a bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_sample(w, budget_voxels=7_000_000):
+    """A crop of one channel of the workload such that ~3 outer iterations take 10-30 s."""
+    shape = list(w["shape"])
+    while np.prod(shape) > budget_voxels:
+        a = int(np.argmax(shape))
+        shape[a] = max(8, shape[a] // 2)
+    return tuple(shape)
+
+
+_ORACLE_WARM = False
+
+
+def cpu_time_oracle(w, seed, n1=1, n2=3):
+    """Seconds per outer iteration of the oracle on the bounded sample: marginal cost
+    (t(n2) - t(n1)) / (n2 - n1) (falls back to t(n2)/n2 if noise makes it non-positive)."""
+    global _ORACLE_WARM
+    import oracle
+
+    shape = cpu_sample(w)
+    img = phantom_np(shape, seed, w["dtype"])
+    kind, m, tol = w["solver"]
+    mk = (lambda: oracle.Jacobi(maxiter=m, tol=tol)) if kind == "jacobi" else (lambda: oracle.CG(maxiter=m, tol=tol))
+    kw = dict(mu=MU, omega=OMEGA, ell=ELL, dim=len(shape), isotropic=w["iso"])
+    if w["hetero"]:
+        mu, om = hetero_maps(dict(w, shape=shape), seed)
+        kw.update(mu=mu, omega=om)
+    if not _ORACLE_WARM:  # one-time costs (imports, BLAS thread pool) paid on a tiny problem
+        tiny = phantom_np(tuple(16 for _ in shape), 0, w["dtype"])
+        oracle.split_bregman_tvd(tiny, max_num_iter=1, solver=mk(), mu=MU, omega=OMEGA, ell=ELL, dim=len(shape),
+                                 isotropic=w["iso"])
+        _ORACLE_WARM = True
+    ts = []
+    for n in (n1, n2):
+        t0 = time.perf_counter()
+        oracle.split_bregman_tvd(img, max_num_iter=n, solver=mk(), **kw)
+        ts.append(time.perf_counter() - t0)
+    per_iter = (ts[1] - ts[0]) / (n2 - n1)
+    if per_iter <= 0:
+        per_iter = ts[1] / n2
+    return shape, per_iter, ts
+
+
+def blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+
+        return max([p.get("num_threads", 1) for p in threadpool_info()] or [1])
+    except Exception:
+        return None
+
+
+def run_reference_arm(args, w, wname):
+    """--impl reference: the reference's CPU algorithm (oracle port; the Python reference itself
+    cannot travel to the GPU box) on the host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    vals = []
+    shape = cpu_sample(w)
+    nvox = int(np.prod(shape))
+    for s in range(args.warmup + args.steps):
+        _, per_iter, _ = cpu_time_oracle(w, seed=2 + s, n1=1, n2=2)
+        if s >= args.warmup:
+            vals.append(nvox / per_iter / 1e6)
+    v = float(np.mean(vals))
+    sample = (f"oracle (NumPy port of the reference algorithm) on one channel cropped to {shape}, marginal cost of "
+              f"outer iteration 2 vs 1; element-wise NumPy is single-threaded, BLAS threads={blas_threads()}")
+    line = {
+        "impl": "reference", "metric": "tvd_mvoxel_iter_per_s", "value": v, "unit": "Mvoxel*iter/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * nvox / (v * 1e6), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64" if w["dtype"] == "float64" else "f32", "data": "synthetic",
+        "config": {"workload": wname, **{k: (list(x) if isinstance(x, tuple) else x) for k, x in w.items()}},
+        "cpu_baseline": {"value": v, "unit": "Mvoxel*iter/s", "cores": 1, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": "Mvoxel*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def measured_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as fh:
+            return float(json.load(fh)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args, w, wname):
+    import torch
+    import torch.distributed as dist
+
+    import darsia_b200 as da
+    from darsia_b200 import _cabi
+    from darsia_b200.engine import Engine, SolverSpec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    lib = _cabi.get_library()
+    dim = len(w["shape"])
+    kind, m, tol = w["solver"]
+    spec = SolverSpec(kind=_cabi.TVDK_SOLVER_CG if kind == "cg" else _cabi.TVDK_SOLVER_JACOBI, maxiter=m, tol=tol)
+    np_dtype = np.dtype(w["dtype"])
+    nvox_step = int(np.prod(w["shape"])) * w["nb"]  # per rank
+    outer = w["outer"]
+
+    # ---- synthetic inputs: one host image per rank (seeded), resident copy on the device ----
+    host_img = make_host_image(w, seed=2 + 100 * rank)
+    pinned_in = torch.from_numpy(host_img).pin_memory()
+    pinned_np = pinned_in.numpy()
+    eng = Engine(w["shape"], nb=w["nb"], dtype=np_dtype, device=dev)
+    mu, om = MU, OMEGA
+    n_het = 0
+    if w["hetero"]:
+        mu_h, om_h = hetero_maps(w, seed=2)
+        mu, _k1 = eng.coef(mu_h)[1], None
+        om = eng.coef(om_h)[1]
+        n_het = 2
+        mu_host, om_host = mu_h, om_h
+    f = eng.upload(pinned_np)
+    u = eng.empty_fields(1)
+    t = eng.empty_fields(dim)
+
+    def device_step():
+        u.copy_(f)  # d2d reset of the iterate (plumbing, outside the algorithmic bytes; < 1 % of a step)
+        t.zero_()
+        eng.solve(f, u, t, mu, om, ELL, w["iso"], spec, outer, None, sync=False)
+
+    # ---- warm-up, then K timed steps with CUDA events on the launching stream ----
+    for _ in range(args.warmup):
+        device_step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    lib.launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        device_step()
+    ev1.record()
+    barrier()
+    launches = int(lib.launch_count(1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms = ev0.elapsed_time(ev1)
+    tm = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_total = float(tm.item())
+    ms_per_step = ms_total / args.steps
+    value = world * nvox_step * outer / (ms_per_step * 1e-3) / 1e6
+
+    # ---- parity spot-check of what was just timed (cheap, not timed): determinism + finite ----
+    res = eng.unpack(u)
+    assert bool(torch.isfinite(res).all()), "non-finite result"
+
+    # ---- dominant kernel alone: average launch duration with CUDA events ----
+    W = np_dtype.itemsize
+    g = eng.geom
+    ws = eng.op_workspace()
+    sums = torch.zeros(w["nb"], dtype=torch.float64, device=dev)
+    coef = torch.full((w["nb"],), 1e-3, dtype=torch.float64, device=dev)
+    omc, _ = eng.coef(om)
+    elc, _ = eng.coef(ELL)
+    muc, _ = eng.coef(mu)
+    if kind == "cg":
+        dom_name, dom_words = "cg_update (x += a p; r -= a A p; r.r)", 5
+        p_, x_, r_ = eng.upload(pinned_np), eng.zero_fields(1), eng.zero_fields(1)
+
+        def dom():
+            return lib.cg_update(C.byref(g), C.byref(omc), C.byref(elc), p_.data_ptr(), x_.data_ptr(), r_.data_ptr(),
+                                 coef.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream())
+    else:
+        dom_name, dom_words = "fused_jacobi1 (rhs+sweep+shrink+update)", 3 + 2 * dim + n_het
+        u2, t2 = eng.empty_fields(1), eng.empty_fields(dim)
+        t.zero_()
+
+        def dom():
+            return lib.fused_jacobi1(C.byref(g), 1 if w["iso"] else 0, C.byref(muc), C.byref(omc), C.byref(elc),
+                                     f.data_ptr(), u.data_ptr(), u2.data_ptr(), t.data_ptr(), t2.data_ptr(),
+                                     eng.batch_elems, sums.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream())
+    for _ in range(3):
+        lib.check(dom(), "dominant kernel")
+    torch.cuda.synchronize(dev)
+    reps = 20
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(reps):
+        dom()
+    k1.record()
+    torch.cuda.synchronize(dev)
+    dom_ms = k0.elapsed_time(k1) / reps
+    peak, peak_src = measured_peak()
+    dom_bytes = dom_words * W * nvox_step
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    words_iter = algo_words_per_voxel_iter(dim, w["solver"], n_het)
+    step_bytes = words_iter * W * nvox_step * outer
+    step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
+    survey_words = {"cg": 8 + 5 * dim + 10 * m, "jacobi": (3 + 4 * dim) if m == 1 else (3 * m + 2 + 5 * dim)}[kind] + n_het
+    roofline = {
+        "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "algo_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
+        "whole_step": {"algo_words_per_voxel_iter": words_iter, "achieved": step_gbs, "frac": step_gbs / peak,
+                       "survey_words_per_voxel_iter": survey_words,
+                       "frac_vs_survey_bytes": survey_words * W * nvox_step * outer / (ms_per_step * 1e-3) / 1e9 / peak},
+    }
+
+    # ---- e2e: public API, host buffers in, host array out, copies inside the timed region ----
+    solver_obj = (da.CG(maxiter=m, tol=tol) if kind == "cg" else da.Jacobi(maxiter=m, tol=tol))
+    kw = dict(method="heterogeneous bregman", weight=(mu_host if w["hetero"] else MU),
+              omega=(om_host if w["hetero"] else OMEGA), regularization=ELL, dim=dim, isotropic=w["iso"],
+              max_num_iter=outer, eps=None, solver=solver_obj)
+    e2e_steps = max(1, min(args.steps, 2))
+    out = da.tvd(pinned_np, **kw)  # warm-up (allocator, pinned staging)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        out = da.tvd(pinned_np, **kw)
+    torch.cuda.synchronize(dev)
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_val = world * nvox_step * outer / float(te.item()) / 1e6
+    h2d = host_img.nbytes + (mu_host.nbytes + om_host.nbytes if w["hetero"] else 0)
+    d2h = out.nbytes + w["nb"] * C.sizeof(_cabi.Stat)
+    # the e2e result must be the device-timed result (same inputs, deterministic kernels)
+    same = bool(np.array_equal(out.reshape(-1), res.cpu().numpy().reshape(-1)))
+
+    # ---- CPU baseline on rank 0 (N = 1 only) ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        shape_s, per_iter, ts = cpu_time_oracle(w, seed=2)
+        cpu = {
+            "value": float(np.prod(shape_s)) / per_iter / 1e6, "unit": "Mvoxel*iter/s", "cores": 1, "kind": "port",
+            "sample": (f"NumPy oracle (port of the reference algorithm; the Python reference cannot travel to the GPU "
+                       f"box) on one channel cropped to {tuple(shape_s)}: marginal cost (t(3 its)-t(1 it))/2 = "
+                       f"{per_iter:.3f} s per outer iteration; raw {ts[1] / 3:.3f} s/iter; element-wise NumPy is "
+                       f"single-threaded, host has {os.cpu_count()} cpus, BLAS threads={blas_threads()}"),
+        }
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "tvd_mvoxel_iter_per_s", "value": value, "unit": "Mvoxel*iter/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if np_dtype == np.float64 else "f32",
+        "data": "synthetic (seeded block phantom + noise; random-free weights: scalar mu/omega/ell)",
+        "config": {"workload": wname, "shape": list(w["shape"]), "channels_per_rank": w["nb"], "isotropic": w["iso"],
+                   "solver": list(w["solver"]), "outer_iterations": outer, "hetero": w["hetero"],
+                   "l2_policy": "inputs larger than L2 (each field is %.0f MB, L2 is 126 MB)" % (eng.batch_elems * W / 1e6),
+                   "sharding": "one image per rank, no collective"},
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "e2e": {"value": e2e_val, "unit": "Mvoxel*iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "s_per_step": float(te.item()), "matches_device_timed_result": same},
+        "gpu_launches": launches,
+        "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, w, args.workload)
+    else:
+        run_ours(args, w, args.workload)
+
+
+if __name__ == "__main__":
+    main()

@@ -23,6 +23,7 @@
 namespace tvdk {
 
 static thread_local std::string g_last_error;
+static thread_local long long g_launches = 0;
 
 static int fail(int code, const char* fmt, ...) {
   char buf[512];
@@ -225,6 +226,7 @@ static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_ti
   a.g = L.g;
   if ((size_t)L.gx * L.gy * L.gz * (K::NRED > 0 ? K::NRED : 1) > sc.partial_cap)
     return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
+  ++g_launches;
   return backend::launch<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
 }
 
@@ -588,6 +590,12 @@ int tvdk_device_ok(void) {
   return ok;
 }
 
+int64_t tvdk_launch_count(int reset) {
+  const long long n = g_launches;
+  if (reset) g_launches = 0;
+  return n;
+}
+
 int tvdk_pitch(int dtype, int n_last) {
   const int a = dtype == TVDK_F64 ? 16 : 32;  // 128 bytes
   return (n_last + a - 1) / a * a;
@@ -636,6 +644,7 @@ int tvdk_pack(const tvdk_geom_t* gg, int src_dtype, const void* src, void* dst, 
     typename KPack<TI, TF, 1>::Args a;                                                  \
     memset(&a, 0, sizeof a);                                                            \
     a.g = g; a.src = src; a.dst = dst; a.fin = no_fin();                                \
+    ++g_launches;                                                                       \
     return backend::launch<KPack<TI, TF, 1>>(a, (int)rows, gy, 1, ntx, 1, 0, stream, nullptr, nullptr); \
   }
   if (src_dtype == TVDK_F64 && gg->dtype == TVDK_F64) TVDK_PACK_CALL(double, double)
@@ -659,6 +668,7 @@ int tvdk_unpack(const tvdk_geom_t* gg, int dst_dtype, const void* src, void* dst
     typename KPack<TI, TF, 0>::Args a;                                                  \
     memset(&a, 0, sizeof a);                                                            \
     a.g = g; a.src = src; a.dst = dst; a.fin = no_fin();                                \
+    ++g_launches;                                                                       \
     return backend::launch<KPack<TI, TF, 0>>(a, (int)rows, gy, 1, ntx, 1, 0, stream, nullptr, nullptr); \
   }
   if (dst_dtype == TVDK_F64 && gg->dtype == TVDK_F64) TVDK_UNPACK_CALL(double, double)

@@ -141,7 +141,14 @@ class Engine:
     def download(self, field: torch.Tensor, out_dtype=None, shape=None) -> np.ndarray:
         """Field -> host array ``(*spatial, *batch)``."""
         inter = self.unpack(field, out_dtype)
-        host = inter.cpu().numpy()
+        if self.device.type == "cuda":
+            # D2H into pinned memory (torch's caching host allocator reuses the block)
+            host_t = torch.empty(inter.shape, dtype=inter.dtype, pin_memory=True)
+            host_t.copy_(inter, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+            host = host_t.numpy()
+        else:
+            host = inter.numpy()
         return host.reshape(shape if shape is not None else (*self.spatial, self.nb))
 
     def coef(self, value, full_shape: Optional[tuple] = None, name: str = "coefficient"):

@@ -124,6 +124,8 @@ int tvdk_version(void);
 const char* tvdk_last_error(void);
 /* 1 if a CUDA device of compute capability 10.x is current, else 0 (and sets last_error). */
 int tvdk_device_ok(void);
+/* Number of kernels this thread has launched through the library since the last reset. */
+int64_t tvdk_launch_count(int reset);
 
 /* Recommended pitch (elements) for a last-axis extent. */
 int tvdk_pitch(int dtype, int n_last);

@@ -176,8 +176,10 @@ case("aniso2d_j1_f32", (37, 52), 29, dtype="float32", mu=0.1, omega=1.0, ell=1.0
 case("aniso3d_j1_f32", (13, 17, 11), 30, dtype="float32", mu=0.1, omega=1.0, ell=1.0, dim=3,
      max_num_iter=25, isotropic=False, solver=J1)
 # --- convergence / warm start / tol branches ------------------------------------------
-case("aniso2d_j1_eps", (37, 52), 31, mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=200,
-     eps=2e-3, isotropic=False, solver=J1)
+case("aniso2d_j1_eps", (37, 52), 31, mu=0.1, omega=1.0, dim=2, max_num_iter=200,
+     eps=2e-3, isotropic=False, solver=J1)  # ell = 2*mu: converges after a few iterations
+case("iso2d_cg3_eps", (37, 52), 39, mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=200,
+     eps=2e-3, isotropic=True, solver={"kind": "cg", "maxiter": 3, "tol": 0.0})
 case("aniso2d_jtol", (37, 52), 32, mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=10,
      isotropic=False, solver={"kind": "jacobi", "maxiter": 30, "tol": 1e-3})
 case("aniso2d_j1_x0", (24, 31), 33, x0=True, mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=10,

@@ -1,0 +1,62 @@
+"""CPU: the kernel SOURCE (darsia_b200/csrc/tvdk_core.h) stepped thread by thread on the host
+(tests/emu) against the golden vectors of the reference and against the oracle.
+
+This checks the index / halo / boundary logic of every kernel, the host driver and the Python
+boundary without a GPU.  It says nothing about the sm_100a build -- the ``-m gpu`` modules do.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
+from emu.harness import emulated
+from parity_cases import run_pair, small_grid
+
+import darsia_b200 as da
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _emu():
+    with emulated() as lib:
+        assert lib.is_emulator
+        yield lib
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_golden(name):
+    arrays, params = load_golden(name)
+    out = run_case_with(da, arrays, params)
+    ref = arrays["out"]
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    assert rel_l2(out, ref) <= tolerance_for(ref.dtype)
+
+
+@pytest.mark.parametrize("shape,dim,tile,iso,solver,hetero,dtype", list(small_grid()))
+def test_tile_seams(shape, dim, tile, iso, solver, hetero, dtype):
+    out, ref = run_pair(da, oracle, shape, dim, iso, solver, dtype=dtype, hetero=hetero, tile=tile)
+    assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_batched_channels_are_independent(fused):
+    out, ref = run_pair(da, oracle, (20, 70), 2, True, "j1", batch=(3,), tile=(32, 0, 6), fused=fused)
+    assert rel_l2(out, ref) <= 1e-12
+    out, ref = run_pair(da, oracle, (7, 12, 20), 3, False, "cg4", batch=(2,), tile=(8, 6, 3))
+    assert rel_l2(out, ref) <= 1e-12
+
+
+def test_eps_stops_each_problem_at_the_reference_iteration():
+    from golden.generate_golden import phantom
+
+    img = np.stack([phantom((24, 40), 3), 0.3 * phantom((24, 40), 4) + 0.3], axis=-1)
+    hist = []
+    ref = oracle.split_bregman_tvd(img, mu=0.1, ell=1.0, max_num_iter=60, eps=5e-3, history=hist,
+                                   solver=oracle.CG(maxiter=3, tol=0.0))
+    out, info = da.split_bregman_tvd(img, mu=0.1, ell=1.0, max_num_iter=60, eps=5e-3, return_info=True,
+                                     solver=da.CG(maxiter=3, tol=0.0))
+    assert [len(h) for h in hist] == list(info.iters)
+    assert len(set(info.iters)) == 2  # the two channels really stop at different iterations
+    assert rel_l2(out, ref) <= 1e-12
+    for b, h in enumerate(hist):
+        np.testing.assert_allclose(info.history[: len(h), b], h, rtol=1e-9)

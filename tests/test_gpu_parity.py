@@ -1,0 +1,132 @@
+"""GPU (B200): the sm_100a kernels, called through the C ABI, against the golden vectors of
+the reference and against the oracle on seeded inputs.  Tolerances are BASELINE.json's:
+relative L2 <= 1e-10 in fp64, <= 1e-5 in fp32 -- the tests assert far tighter fp64 bounds
+because the arithmetic is the reference's up to reciprocal-multiplies and FMA contraction.
+"""
+
+import numpy as np
+import pytest
+
+import oracle
+from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
+from parity_cases import run_pair, small_grid
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def da():
+    import torch
+
+    assert torch.cuda.is_available(), "the gpu tests need a CUDA device"
+    import darsia_b200
+    from darsia_b200 import _cabi
+
+    lib = _cabi.get_library()
+    assert not lib.is_emulator and lib.path.endswith("darsia_b200/csrc/libtvdk.so")
+    assert lib.device_ok(), lib.last_error()
+    return darsia_b200
+
+
+@pytest.mark.parametrize("name", golden_case_names())
+def test_golden(da, name):
+    arrays, params = load_golden(name)
+    out = run_case_with(da, arrays, params)
+    ref = arrays["out"]
+    assert out.shape == ref.shape and out.dtype == ref.dtype
+    err = rel_l2(out, ref)
+    assert err <= tolerance_for(ref.dtype), f"{name}: {err:.3e}"
+    if ref.dtype == np.float64:
+        assert err <= 1e-12, f"{name}: {err:.3e}"
+
+
+@pytest.mark.parametrize("shape,dim,tile,iso,solver,hetero,dtype", list(small_grid()))
+def test_tile_seams(da, shape, dim, tile, iso, solver, hetero, dtype):
+    out, ref = run_pair(da, oracle, shape, dim, iso, solver, dtype=dtype, hetero=hetero, tile=tile)
+    assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 2e-5)
+
+
+MEDIUM = [
+    ((301, 517), 2, False, "j1", False, np.float64, 25),
+    ((301, 517), 2, True, "j1", True, np.float64, 25),
+    ((301, 517), 2, True, "cg10", False, np.float64, 12),
+    ((300, 516), 2, False, "j20", True, np.float64, 8),
+    ((301, 517), 2, False, "cgtol", False, np.float64, 8),
+    ((301, 517), 2, False, "jtol", False, np.float64, 8),
+    ((301, 517), 2, False, "j1", False, np.float32, 25),
+    ((301, 517), 2, True, "cg4", True, np.float32, 10),
+    ((41, 70, 93), 3, False, "j1", False, np.float64, 20),
+    ((41, 70, 93), 3, True, "j1", True, np.float64, 20),
+    ((41, 70, 93), 3, True, "cg10", False, np.float64, 8),
+    ((40, 64, 96), 3, False, "j3", False, np.float64, 10),
+    ((41, 70, 93), 3, False, "j1", False, np.float32, 20),
+    ((41, 70, 93), 3, True, "cg4", False, np.float32, 8),
+]
+
+
+@pytest.mark.parametrize("shape,dim,iso,solver,hetero,dtype,nit", MEDIUM)
+def test_default_tiles_medium_shapes(da, shape, dim, iso, solver, hetero, dtype, nit):
+    """Default launch shapes (several tiles and chunks), odd extents, full iteration counts."""
+    out, ref = run_pair(da, oracle, shape, dim, iso, solver, dtype=dtype, hetero=hetero, nit=nit)
+    assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 1e-5)
+
+
+def test_batched_channels(da):
+    out, ref = run_pair(da, oracle, (120, 260), 2, True, "cg4", batch=(3,))
+    assert rel_l2(out, ref) <= 1e-12
+    out, ref = run_pair(da, oracle, (120, 260), 2, False, "j1", batch=(5,), hetero=True)
+    assert rel_l2(out, ref) <= 1e-12
+    out, ref = run_pair(da, oracle, (20, 30, 40), 3, False, "j1", batch=(2,))
+    assert rel_l2(out, ref) <= 1e-12
+
+
+def test_fused_equals_building_blocks(da):
+    from parity_cases import make_inputs
+
+    img, kw = make_inputs((257, 400), hetero=True)
+    a = da.split_bregman_tvd(img, max_num_iter=30, isotropic=True, **kw)
+    b = da.split_bregman_tvd(img, max_num_iter=30, isotropic=True, fused=False, **kw)
+    assert rel_l2(a, b) <= 1e-13
+
+
+def test_eps_stops_each_problem_at_the_reference_iteration(da):
+    from golden.generate_golden import phantom
+
+    img = np.stack([phantom((24, 40), 3), 0.3 * phantom((24, 40), 4) + 0.3], axis=-1)
+    hist = []
+    ref = oracle.split_bregman_tvd(img, mu=0.1, ell=1.0, max_num_iter=60, eps=5e-3, history=hist,
+                                   solver=oracle.CG(maxiter=3, tol=0.0))
+    out, info = da.split_bregman_tvd(img, mu=0.1, ell=1.0, max_num_iter=60, eps=5e-3, return_info=True,
+                                     solver=da.CG(maxiter=3, tol=0.0))
+    assert [len(h) for h in hist] == list(info.iters)
+    assert rel_l2(out, ref) <= 1e-12
+    assert info.launched < 60  # the host stopped enqueueing after the device flag fired
+
+
+def test_deterministic(da):
+    from parity_cases import make_inputs
+
+    img, kw = make_inputs((300, 500))
+    a = da.split_bregman_tvd(img, max_num_iter=20, isotropic=True, solver=da.CG(maxiter=5, tol=0.0), **kw)
+    b = da.split_bregman_tvd(img, max_num_iter=20, isotropic=True, solver=da.CG(maxiter=5, tol=0.0), **kw)
+    np.testing.assert_array_equal(a, b)
+
+
+def test_image_in_out_and_entry_point(da):
+    from parity_cases import make_inputs
+
+    img, _ = make_inputs((64, 80))
+    im = da.Image(img.copy(), space_dim=2)
+    out = da.tvd(im, method="heterogeneous bregman", weight=0.1, omega=1.0, max_num_iter=20, eps=1e-3)
+    ref = oracle.tvd(img, method="heterogeneous bregman", weight=0.1, omega=1.0, max_num_iter=20, eps=1e-3)
+    assert isinstance(out, da.Image) and rel_l2(out.img, ref) <= 1e-12
+
+
+def test_standalone_solvers(da):
+    rng = np.random.default_rng(2)
+    x0, rhs = rng.random((90, 140)), rng.standard_normal((90, 140))
+    for mk in (lambda m: m.Jacobi(maxiter=4, dim=2, mass_coeff=1.3, diffusion_coeff=0.7),
+               lambda m: m.CG(maxiter=6, tol=0.0, dim=2, mass_coeff=1.3, diffusion_coeff=0.7)):
+        s_ref = mk(oracle)
+        s_ref.reset()
+        assert rel_l2(mk(da)(x0=x0, rhs=rhs), s_ref(x0=x0, rhs=rhs)) < 1e-12
