@@ -116,6 +116,7 @@ SIGNATURES = {
     "tvdk_last_error": (C.c_char_p, []),
     "tvdk_device_ok": (C.c_int, []),
     "tvdk_launch_count": (_I64, [_I]),
+    "tvdk_set_tune": (C.c_int, [_I, _I, _I]),
     "tvdk_pitch": (C.c_int, [_I, _I]),
     "tvdk_field_elems": (_I64, [_PG]),
     "tvdk_workspace_bytes": (_SZ, [C.POINTER(Problem)]),

@@ -266,18 +266,25 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
 // ------------------------------------------------------------------------------------------
 // Thread <-> column mapping of the march kernels
 // ------------------------------------------------------------------------------------------
+// Every thread loads UNCONDITIONALLY from a position clamped into the allocation (no branches
+// around loads); what a thread outside the image loads is never consumed because the boundary
+// rules select the other operand.  Blocks whose whole region (interior + halo) lies strictly
+// inside the image take a fast path without any per-element boundary selects (`edge == false`).
 template <typename T, int D, int LH, int RH>
 struct Col {
   static constexpr int V = Vec<T>::N;
   static constexpr int RHX = RH > 0 ? 1 : 0;
-  int X, Y, b;    // global coordinates of the first element of the thread's vector; problem
-  int soff;       // shared-memory element offset of the vector inside one row array
-  int spitch;     // shared-memory row pitch (elements)
-  long long off;  // element offset of (b, plane 0, Y, X)
-  int z0, z1;     // planes [z0, z1) owned by this CTA
-  bool ld;        // the vector may be loaded (inside the allocation)
-  bool st;        // interior thread whose results are stored
-  bool okc[V];    // element inside the image
+  int X, Y, b;      // global coordinates of the first element of the thread's vector; problem
+  int soff;         // shared-memory element offset of the vector inside one row array
+  int spitch;       // shared-memory row pitch (elements)
+  long long base;   // BYTE offset of (b, plane 0, Yc, Xc), clamped into the allocation
+  long long cur;    // running BYTE offset of the current plane j
+  long long cdel;   // BYTES: -b * sb (to rebase onto a coefficient map's own batch stride)
+  long long s0b;    // BYTES between consecutive planes
+  int z0, z1;       // planes [z0, z1) owned by this CTA
+  bool st;          // interior thread whose results are stored
+  bool edge;        // block touches the image boundary / is a partial tile (block-uniform)
+  bool okc[V];      // element inside the image
   bool hl[V], hr[V];  // element has a left / right neighbour along x
   bool hylo, hyhi;    // row has a lower / upper neighbour along y (3-D)
 
@@ -287,20 +294,25 @@ struct Col {
 
   TVDK_DEV void setup(const Geom& g, const LaunchCtx& lc) {
     const int xt = lc.bx % g.xtiles, yt = lc.bx / g.xtiles;
-    X = xt * iw(lc.ntx) + (lc.tx - LH) * V;
+    const int x0 = xt * iw(lc.ntx);
+    X = x0 + (lc.tx - LH) * V;
     bool rowok = true;
     Y = 0;
+    bool edge_y = false;
     if (D == 3) {
-      Y = yt * ih(lc.nty) + (lc.ty - LH);
+      const int y0 = yt * ih(lc.nty);
+      Y = y0 + (lc.ty - LH);
       rowok = (Y >= 0) && (Y < g.ny);
+      edge_y = (y0 - LH < 0) || (y0 + ih(lc.nty) + RH > g.ny);
     }
+    edge = edge_y || (x0 - LH * V < 0) || (x0 + iw(lc.ntx) + RHX * V > g.nx);
     b = lc.bz;
     z0 = g.z_begin + lc.by * g.zchunk;
     z1 = z0 + g.zchunk < g.z_end ? z0 + g.zchunk : g.z_end;
-    ld = rowok && X >= 0 && X < g.pitch;
+    const bool inalloc = rowok && X >= 0 && X < g.pitch;
     const bool xin = lc.tx >= LH && lc.tx < lc.ntx - RHX;
     const bool yin = (D == 3) ? (lc.ty >= LH && lc.ty < lc.nty - RH) : true;
-    st = ld && xin && yin && X < g.nx;
+    st = inalloc && xin && yin && X < g.nx;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       okc[v] = rowok && (X + v >= 0) && (X + v < g.nx);
@@ -311,8 +323,20 @@ struct Col {
     hyhi = Y < g.ny - 1;
     spitch = (lc.ntx + 2) * V;
     soff = (lc.ty + 1) * spitch + (lc.tx + 1) * V;
-    off = (long long)b * g.sb + (long long)Y * g.pitch + X;
+    const int Xc = X < 0 ? 0 : (X > g.pitch - V ? g.pitch - V : X);
+    const int Yc = Y < 0 ? 0 : (Y > g.ny - 1 ? g.ny - 1 : Y);
+    constexpr long long W = (long long)sizeof(T);
+    cdel = -(long long)b * g.sb * W;
+    s0b = g.s0 * W;
+    base = ((long long)b * g.sb + (long long)Yc * g.pitch + Xc) * W;
+    cur = base + (long long)z0 * s0b;
+#if defined(__CUDACC__)
+    // keep the per-thread invariants in registers instead of re-deriving them from %tid / the
+    // kernel parameters on every plane (the compiler otherwise rematerialises them)
+    asm volatile("" : "+r"(soff), "+l"(cur), "+l"(s0b));
+#endif
   }
+  TVDK_DEV long long at(const Geom&, int z) const { return base + (long long)z * s0b; }
   // plane z exists in the local allocation and in the global domain
   TVDK_DEV bool plane_ok(const Geom& g, int z) const {
     const int gz = z + g.g0_off;
@@ -320,27 +344,47 @@ struct Col {
   }
   TVDK_DEV bool has_zlo(const Geom& g, int z) const { return z + g.g0_off > 0; }
   TVDK_DEV bool has_zhi(const Geom& g, int z) const { return z + g.g0_off < g.g0_n - 1; }
+  // boundary predicates; compile-time true on the interior fast path
+  template <bool E> TVDK_DEV bool HL(int v) const { return E ? hl[v] : true; }
+  template <bool E> TVDK_DEV bool HR(int v) const { return E ? hr[v] : true; }
+  template <bool E> TVDK_DEV bool OK(int v) const { return E ? okc[v] : true; }
+  template <bool E> TVDK_DEV bool YLO() const { return E ? hylo : true; }
+  template <bool E> TVDK_DEV bool YHI() const { return E ? hyhi : true; }
+  template <bool E> TVDK_DEV bool ZLO(const Geom& g, int z) const { return E ? has_zlo(g, z) : true; }
+  template <bool E> TVDK_DEV bool ZHI(const Geom& g, int z) const { return E ? has_zhi(g, z) : true; }
+  // plane z touches the global z boundary (block-uniform)
+  TVDK_DEV bool zedge(const Geom& g, int z) const { return !has_zlo(g, z) || !has_zhi(g, z); }
 };
 
-template <typename T, typename C>
-TVDK_DEV Vec<T> ldv(const C& c, const Geom& g, const T* base, int z) {
-  if (c.ld) return vload_ro(base + c.off + (long long)z * g.s0);
-  return vsplat<T>((T)0);
+// all offsets `o` below are BYTE offsets
+template <typename T>
+TVDK_DEV const T* bptr(const T* base, long long o) {
+  return reinterpret_cast<const T*>(reinterpret_cast<const char*>(base) + o);
 }
-template <typename T, typename C>
-TVDK_DEV Vec<T> ldv_rw(const C& c, const Geom& g, const T* base, int z) {
-  if (c.ld) return vload(base + c.off + (long long)z * g.s0);
-  return vsplat<T>((T)0);
+template <typename T>
+TVDK_DEV T* bptr(T* base, long long o) {
+  return reinterpret_cast<T*>(reinterpret_cast<char*>(base) + o);
 }
-template <typename T, typename C>
-TVDK_DEV Vec<T> ldcoef(const C& c, const Geom& g, const Coef<T>& k, int z) {
-  if (k.p && c.ld)
-    return vload_ro(k.p + (long long)c.b * k.sb + (c.off - (long long)c.b * g.sb) + (long long)z * g.s0);
+template <typename T>
+TVDK_DEV Vec<T> ldo(const T* base, long long o) {
+  return vload_ro(bptr(base, o));
+}
+template <typename T>
+TVDK_DEV Vec<T> ldw(const T* base, long long o) {  // plain load (data updated in place by this kernel)
+  return vload(bptr(base, o));
+}
+template <typename T>
+TVDK_DEV void stw(T* base, long long o, const Vec<T>& x) {
+  vstore(bptr(base, o), x);
+}
+template <bool HET, typename T, typename C>
+TVDK_DEV Vec<T> ldcoef(const C& c, const Coef<T>& k, long long o) {
+  if (HET && k.p) return vload_ro(bptr(k.p + (long long)c.b * k.sb, o + c.cdel));
   return vsplat<T>(k.val);
 }
 template <typename T, typename C>
-TVDK_DEV void stv(const C& c, const Geom& g, T* base, int z, const Vec<T>& x) {
-  if (c.st) vstore(base + c.off + (long long)z * g.s0, x);
+TVDK_DEV void sto(const C& c, T* base, long long o, const Vec<T>& x) {
+  if (c.st) vstore(bptr(base, o), x);
 }
 
 // shared-memory row arrays: [nty + 2][(ntx + 2) * V], one vector of padding on every side
@@ -405,10 +449,10 @@ template <typename T>
 struct VoxCoef {
   T kappa, ell, omega, inv_diag, c_nb;
 };
-template <typename T>
+template <bool HET, typename T>
 TVDK_DEV VoxCoef<T> voxcoef(const Scalars<T>& sc, T mu, T om, T el) {
   VoxCoef<T> r;
-  if (!sc.hetero) {
+  if (!HET) {
     r.kappa = sc.kappa;
     r.ell = sc.ell;
     r.omega = sc.omega;
@@ -440,7 +484,7 @@ TVDK_DEV T lap_axis(T xm, T xc, T xp, bool has_lo, bool has_hi, T lm, T lc, T lp
 // Neighbour helpers on a vector whose row has been published in shared memory
 // ------------------------------------------------------------------------------------------
 // N(x): sum of the 2*D edge-replicated neighbours in the reference's order (jacobi.py:40-55).
-template <typename T, int D, typename C>
+template <typename T, int D, bool E, typename C>
 TVDK_DEV Vec<T> nsum(const C& c, const Vec<T>& lo, const Vec<T>& hi, const Vec<T>& xc, const T* row) {
   constexpr int V = Vec<T>::N;
   Vec<T> s;
@@ -450,8 +494,8 @@ TVDK_DEV Vec<T> nsum(const C& c, const Vec<T>& lo, const Vec<T>& hi, const Vec<T
     const Vec<T> ym = sym(row, c), yp = syp(row, c);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      s.v[v] += c.hylo ? ym.v[v] : xc.v[v];
-      s.v[v] += c.hyhi ? yp.v[v] : xc.v[v];
+      s.v[v] += c.template YLO<E>() ? ym.v[v] : xc.v[v];
+      s.v[v] += c.template YHI<E>() ? yp.v[v] : xc.v[v];
     }
   }
   const T xl = sxm(row, c), xr = sxp(row, c);
@@ -459,19 +503,20 @@ TVDK_DEV Vec<T> nsum(const C& c, const Vec<T>& lo, const Vec<T>& hi, const Vec<T
   for (int v = 0; v < V; ++v) {
     const T left = v > 0 ? xc.v[v > 0 ? v - 1 : 0] : xl;
     const T right = v < V - 1 ? xc.v[v < V - 1 ? v + 1 : 0] : xr;
-    s.v[v] += c.hl[v] ? left : xc.v[v];
-    s.v[v] += c.hr[v] ? right : xc.v[v];
+    s.v[v] += c.template HL<E>(v) ? left : xc.v[v];
+    s.v[v] += c.template HR<E>(v) ? right : xc.v[v];
   }
   return s;
 }
 
-// A x = omega x - L_ell x (cg.py:37-44) with x's z-neighbours in registers and its row in smem.
-// Scalar ell only here; the per-voxel-ell variant loads ell's neighbours from global memory.
-template <typename T, int D, typename C>
-TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, const Vec<T>& lo, const Vec<T>& xc,
+// A x = omega x - L_ell x (cg.py:37-44) with x's z-neighbours in registers and its row in smem;
+// `o` is the element offset of the vector (for the per-voxel-ell variant, which loads ell's
+// neighbours straight from global memory: rare path, cg.py:43 / SURVEY Q18).
+template <typename T, int D, bool E, bool HET, typename C>
+TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, long long o, const Vec<T>& lo, const Vec<T>& xc,
                         const Vec<T>& hi, const T* row, const Vec<T>& om, const Coef<T>& ell) {
   constexpr int V = Vec<T>::N;
-  const bool zlo = c.has_zlo(g, z), zhi = c.has_zhi(g, z);
+  const bool zlo = c.template ZLO<E>(g, z), zhi = c.template ZHI<E>(g, z);
   Vec<T> lap;
   const T xl = sxm(row, c), xr = sxp(row, c);
   Vec<T> ym = xc, yp = xc;
@@ -479,24 +524,22 @@ TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, const Vec<T>& lo, cons
     ym = sym(row, c);
     yp = syp(row, c);
   }
-  if (!ell.p) {
+  if (!HET || !ell.p) {
     const T l = ell.val;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       T s = lap_axis(lo.v[v], xc.v[v], hi.v[v], zlo, zhi, l, l, l);
-      if (D == 3) s = s + lap_axis(ym.v[v], xc.v[v], yp.v[v], c.hylo, c.hyhi, l, l, l);
+      if (D == 3) s = s + lap_axis(ym.v[v], xc.v[v], yp.v[v], c.template YLO<E>(), c.template YHI<E>(), l, l, l);
       const T left = v > 0 ? xc.v[v > 0 ? v - 1 : 0] : xl;
       const T right = v < V - 1 ? xc.v[v < V - 1 ? v + 1 : 0] : xr;
-      s = s + lap_axis(left, xc.v[v], right, c.hl[v], c.hr[v], l, l, l);
+      s = s + lap_axis(left, xc.v[v], right, c.template HL<E>(v), c.template HR<E>(v), l, l, l);
       lap.v[v] = s;
     }
   } else {
-    // per-voxel ell inside the divergence (cg.py:43): rare path, ell's neighbours
-    // come straight from global memory (L1/L2 cached)
-    const T* lb = ell.p + (long long)c.b * ell.sb + (c.off - (long long)c.b * g.sb) + (long long)z * g.s0;
+    const T* lb = bptr(ell.p + (long long)c.b * ell.sb, o + c.cdel);
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      if (!c.okc[v] || !c.ld) {
+      if (!c.okc[v]) {
         lap.v[v] = (T)0;
         continue;
       }
@@ -504,13 +547,12 @@ TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, const Vec<T>& lo, cons
       T s = lap_axis(lo.v[v], xc.v[v], hi.v[v], zlo, zhi, zlo ? sload_ro(lb + v - g.s0) : lc, lc,
                      zhi ? sload_ro(lb + v + g.s0) : lc);
       if (D == 3)
-        s = s + lap_axis(ym.v[v], xc.v[v], yp.v[v], c.hylo, c.hyhi,
-                         c.hylo ? sload_ro(lb + v - g.pitch) : lc, lc,
+        s = s + lap_axis(ym.v[v], xc.v[v], yp.v[v], c.hylo, c.hyhi, c.hylo ? sload_ro(lb + v - g.pitch) : lc, lc,
                          c.hyhi ? sload_ro(lb + v + g.pitch) : lc);
       const T left = v > 0 ? xc.v[v > 0 ? v - 1 : 0] : xl;
       const T right = v < V - 1 ? xc.v[v < V - 1 ? v + 1 : 0] : xr;
-      s = s + lap_axis(left, xc.v[v], right, c.hl[v], c.hr[v], c.hl[v] ? sload_ro(lb + v - 1) : lc,
-                       lc, c.hr[v] ? sload_ro(lb + v + 1) : lc);
+      s = s + lap_axis(left, xc.v[v], right, c.hl[v], c.hr[v], c.hl[v] ? sload_ro(lb + v - 1) : lc, lc,
+                       c.hr[v] ? sload_ro(lb + v + 1) : lc);
       lap.v[v] = s;
     }
   }
@@ -520,16 +562,66 @@ TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, const Vec<T>& lo, cons
   return y;
 }
 
+// raw planes of the compressed state (or of the explicit warm-start arrays) + the coefficients
+// needed to turn them into b and w; loaded one plane ahead of their use
+template <typename T, int D>
+struct RawT {
+  Vec<T> t[D], d[D], mu, el;
+};
+// (RO = false: plain loads, for state that the same kernel updates in place)
+template <bool RO, bool HET, typename T, int D, typename C>
+TVDK_DEV void load_rawt(RawT<T, D>& r, const C& c, const Coefs<T>& k, const T* t, long long tcs, const T* xb,
+                        const T* xd, long long xcs, long long o) {
+  if (t) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) r.t[d] = RO ? ldo(t + d * tcs, o) : ldw(t + d * tcs, o);
+  } else {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      r.t[d] = ldo(xb + d * xcs, o);
+      r.d[d] = ldo(xd + d * xcs, o);
+    }
+  }
+  r.mu = ldcoef<HET>(c, k.mu, o);
+  r.el = ldcoef<HET>(c, k.ell, o);
+}
+// b and w = ell (b - d) of one plane from its raw state
+template <typename T, int D, bool ISO, bool HET>
+TVDK_DEV void bw_plane(const RawT<T, D>& r, const Scalars<T>& sc, bool expl, Vec<T> (&b)[D], Vec<T> (&w)[D]) {
+  constexpr int V = Vec<T>::N;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const VoxCoef<T> vc = voxcoef<HET>(sc, r.mu.v[v], (T)1, r.el.v[v]);
+    if (!expl) {
+      T t[D], bb[D], ww[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) t[d] = r.t[d].v[v];
+      bw_from_t<T, D, ISO>(t, vc.kappa, vc.ell, bb, ww);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        b[d].v[v] = bb[d];
+        w[d].v[v] = ww[d];
+      }
+    } else {
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        b[d].v[v] = r.t[d].v[v];
+        w[d].v[v] = vc.ell * (r.t[d].v[v] - r.d[d].v[v]);
+      }
+    }
+  }
+}
+
 // ==========================================================================================
 // K1  fused outer iteration for Jacobi(maxiter=1):  rhs -> sweep -> shrink -> Bregman update
 //     split_bregman_tvd.py:84-89 (rhs), jacobi.py:101-114 (sweep), :136-146 (shrink/update),
 //     :161 (increment).  u+ is recomputed on a +1 halo (threads of the RH rows / right vector).
+//     Shared rows: [slot*D + 0] = u(j), [slot*D + d] = w_d(j) (d >= 1), [2D + slot] = u+ ring.
 // ==========================================================================================
-template <typename T, int D, bool ISO>
+template <typename T, int D, bool ISO, bool HET>
 struct KFusedJ1 {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 2, NRED = 1, NROWS = 2 * D + 2;
-  // shared rows: [slot*D + 0] = u(j), [slot*D + d] = w_d(j) (d >= 1), [2D + slot] = u+ ring
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -545,29 +637,23 @@ struct KFusedJ1 {
   };
   C c;
   int j, rowe;
-  Vec<T> u_lo, u_c, u_hi;   // u(j-1), u(j), u(j+1)
-  Vec<T> w0_prev, w0_cur;   // ell (b_0 - d_0) at planes j-1, j
-  Vec<T> wa_cur[D];         // w_a(j), a >= 1 kept for the own-vector neighbour
+  Vec<T> u_lo, u_c, u_hi;     // u(j-1), u(j), u(j+1)
+  Vec<T> w0_prev, w0_cur;     // ell (b_0 - d_0) at planes j-1, j
+  Vec<T> wa_cur[D];           // w_a(j), a >= 1
   Vec<T> b_prev[D], b_cur[D];
-  Vec<T> up_prev, f_c, invd, cnb, om_f;  // u+(j-1); plane-j data
+  Vec<T> up_prev, om_f, invd, cnb;
+  // prefetched raw data of plane j+1 (u of plane j+2)
+  RawT<T, D> nx;
+  Vec<T> nx_u, nx_f, nx_om;
   bool have_row;
   double red[NRED];
 
-  TVDK_DEV void load_w0(const Args& a, int z, Vec<T>& w0) {
-    // w_0 of plane z (prologue only): needs all components of t for the isotropic norm
-    Vec<T> tv[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) tv[d] = ldv(c, a.g, a.t_in + d * a.tcs_in, z);
-    const Vec<T> mu = ldcoef(c, a.g, a.k.mu, z), el = ldcoef(c, a.g, a.k.ell, z);
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      T t[D], b[D], w[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) t[d] = tv[d].v[v];
-      const VoxCoef<T> vc = voxcoef(a.k.sc, mu.v[v], (T)1, el.v[v]);
-      bw_from_t<T, D, ISO>(t, vc.kappa, vc.ell, b, w);
-      w0.v[v] = w[0];
-    }
+  TVDK_DEV void prefetch(const Args& a, int z) {  // raw data needed to process plane z
+    const long long o = c.at(a.g, z);
+    load_rawt<true, HET>(nx, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o);
+    nx_f = ldo(a.f, o);
+    nx_om = ldcoef<HET>(c, a.k.omega, o);
+    if (c.has_zhi(a.g, z)) nx_u = ldo(a.u_in, o + c.s0b);
   }
 
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
@@ -576,87 +662,82 @@ struct KFusedJ1 {
     rowe = C::row_elems(lc.ntx, lc.nty);
     red[0] = 0.0;
     j = c.z0;
-    u_c = ldv(c, a.g, a.u_in, j);
+    const long long o = c.at(a.g, j);
+    u_c = ldo(a.u_in, o);
     u_lo = u_c;
     w0_prev = vsplat<T>((T)0);
     if (c.has_zlo(a.g, j)) {
-      u_lo = ldv(c, a.g, a.u_in, j - 1);
-      load_w0(a, j - 1, w0_prev);
+      u_lo = ldo(a.u_in, o - c.s0b);
+      RawT<T, D> r;
+      load_rawt<true, HET>(r, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o - c.s0b);
+      Vec<T> bb[D], ww[D];
+      bw_plane<T, D, ISO, HET>(r, a.k.sc, false, bb, ww);
+      w0_prev = ww[0];
     }
     up_prev = vsplat<T>((T)0);
 #pragma unroll
     for (int d = 0; d < D; ++d) b_prev[d] = vsplat<T>((T)0);
     have_row = false;
+    prefetch(a, j);
     return true;
   }
   TVDK_DEV bool more() const { return j <= c.z1; }
 
-  // phase 1: load plane j, form b/w from t, publish u(j) and w_a(j) (a >= 1)
+  // phase 1: consume the prefetched plane j (form b/w from t), publish u(j) and w_a(j) (a >= 1),
+  //          then issue the loads of plane j+1
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
     have_row = (j < c.z1) || c.plane_ok(a.g, j);
     if (!have_row) return;
     const int slot = j & 1;
-    u_hi = c.has_zhi(a.g, j) ? ldv(c, a.g, a.u_in, j + 1) : u_c;
-    f_c = ldv(c, a.g, a.f, j);
-    Vec<T> tv[D];
+    u_hi = c.has_zhi(a.g, j) ? nx_u : u_c;
+    Vec<T> ww[D];
+    bw_plane<T, D, ISO, HET>(nx, a.k.sc, false, b_cur, ww);
+    w0_cur = ww[0];
 #pragma unroll
-    for (int d = 0; d < D; ++d) tv[d] = ldv(c, a.g, a.t_in + d * a.tcs_in, j);
-    const Vec<T> mu = ldcoef(c, a.g, a.k.mu, j), om = ldcoef(c, a.g, a.k.omega, j),
-                 el = ldcoef(c, a.g, a.k.ell, j);
+    for (int d = 1; d < D; ++d) wa_cur[d] = ww[d];
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      T t[D], b[D], w[D];
-#pragma unroll
-      for (int d = 0; d < D; ++d) t[d] = tv[d].v[v];
-      const VoxCoef<T> vc = voxcoef(a.k.sc, mu.v[v], om.v[v], el.v[v]);
-      bw_from_t<T, D, ISO>(t, vc.kappa, vc.ell, b, w);
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        b_cur[d].v[v] = b[d];
-        if (d == 0)
-          w0_cur.v[v] = w[0];
-        else
-          wa_cur[d].v[v] = w[d];
-      }
+      const VoxCoef<T> vc = voxcoef<HET>(a.k.sc, (T)0, nx_om.v[v], nx.el.v[v]);
       invd.v[v] = vc.inv_diag;
       cnb.v[v] = vc.c_nb;
-      om_f.v[v] = vc.omega * f_c.v[v];
+      om_f.v[v] = vc.omega * nx_f.v[v];
     }
     sst(srow<T>(smem, slot * D + 0, rowe), c, u_c);
 #pragma unroll
     for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * D + d, rowe), c, wa_cur[d]);
+    // next plane is needed if another compute step follows
+    if (j + 1 < c.z1 || (j + 1 == c.z1 && c.plane_ok(a.g, j + 1))) prefetch(a, j + 1);
   }
 
-  // phase 2: u+(j); then outputs of plane j-1
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+  TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j) || c.zedge(a.g, j - 1); }
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
     const int slot = j & 1;
     Vec<T> up = vsplat<T>((T)0);
     if (have_row) {
       const T* urow = srow<T>(smem, slot * D + 0, rowe);
       // rhs = omega f + H_0 w_0 + H_1 w_1 (+ H_2 w_2), in the reference's order (:84-89)
       Vec<T> rhs = om_f;
-      if (c.has_zlo(a.g, j)) {
+      if (c.template ZLO<E>(a.g, j)) {
 #pragma unroll
         for (int v = 0; v < V; ++v) rhs.v[v] += w0_cur.v[v] - w0_prev.v[v];
       }
       if (D == 3) {
-        const T* wrow = srow<T>(smem, slot * D + 1, rowe);
-        const Vec<T> wm = sym(wrow, c);
-        if (c.hylo) {
+        const Vec<T> wm = sym(srow<T>(smem, slot * D + 1, rowe), c);
+        if (c.template YLO<E>()) {
 #pragma unroll
           for (int v = 0; v < V; ++v) rhs.v[v] += wa_cur[1].v[v] - wm.v[v];
         }
       }
       {
-        const T* wrow = srow<T>(smem, slot * D + (D - 1), rowe);
-        const T wl = sxm(wrow, c);
+        const T wl = sxm(srow<T>(smem, slot * D + (D - 1), rowe), c);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const T left = v > 0 ? wa_cur[D - 1].v[v > 0 ? v - 1 : 0] : wl;
-          if (c.hl[v]) rhs.v[v] += wa_cur[D - 1].v[v] - left;
+          if (c.template HL<E>(v)) rhs.v[v] += wa_cur[D - 1].v[v] - left;
         }
       }
-      const Vec<T> nb = nsum<T, D>(c, u_lo, u_hi, u_c, urow);
+      const Vec<T> nb = nsum<T, D, E>(c, u_lo, u_hi, u_c, urow);
 #pragma unroll
       for (int v = 0; v < V; ++v) up.v[v] = rhs.v[v] * invd.v[v] + nb.v[v] * cnb.v[v];
       sst(srow<T>(smem, 2 * D + slot, rowe), c, up);
@@ -664,33 +745,33 @@ struct KFusedJ1 {
     if (j > c.z0) {
       // outputs of plane j-1: t_new = G u+ + b, u_out = u+, increment (:136-146, :161)
       const int zo = j - 1;
+      const long long oo = c.cur - c.s0b;
       const T* prow = srow<T>(smem, 2 * D + (zo & 1), rowe);
       Vec<T> tn[D];
-      const bool zhi = c.has_zhi(a.g, zo);
+      const bool zhi = c.template ZHI<E>(a.g, zo);
 #pragma unroll
-      for (int v = 0; v < V; ++v)
-        tn[0].v[v] = (zhi ? up.v[v] - up_prev.v[v] : (T)0) + b_prev[0].v[v];
+      for (int v = 0; v < V; ++v) tn[0].v[v] = (zhi ? up.v[v] - up_prev.v[v] : (T)0) + b_prev[0].v[v];
       if (D == 3) {
         const Vec<T> yp = syp(prow, c);
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          tn[1].v[v] = (c.hyhi ? yp.v[v] - up_prev.v[v] : (T)0) + b_prev[1].v[v];
+          tn[1].v[v] = (c.template YHI<E>() ? yp.v[v] - up_prev.v[v] : (T)0) + b_prev[1].v[v];
       }
       {
         const T xr = sxp(prow, c);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           const T right = v < V - 1 ? up_prev.v[v < V - 1 ? v + 1 : 0] : xr;
-          tn[D - 1].v[v] = (c.hr[v] ? right - up_prev.v[v] : (T)0) + b_prev[D - 1].v[v];
+          tn[D - 1].v[v] = (c.template HR<E>(v) ? right - up_prev.v[v] : (T)0) + b_prev[D - 1].v[v];
         }
       }
-      stv(c, a.g, a.u_out, zo, up_prev);
+      sto(c, a.u_out, oo, up_prev);
 #pragma unroll
-      for (int d = 0; d < D; ++d) stv(c, a.g, a.t_out + d * a.tcs_out, zo, tn[d]);
-      if (c.st) {
+      for (int d = 0; d < D; ++d) sto(c, a.t_out + d * a.tcs_out, oo, tn[d]);
+      if (c.st) {  // u_lo still holds u(j-1) here (rolled below)
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-          if (c.okc[v]) {
+          if (c.template OK<E>(v)) {
             const double df = (double)up_prev.v[v] - (double)u_lo.v[v];
             red[0] += df * df;
           }
@@ -704,22 +785,28 @@ struct KFusedJ1 {
     up_prev = up;
 #pragma unroll
     for (int d = 0; d < D; ++d) b_prev[d] = b_cur[d];
+    c.cur += c.s0b;
     ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge || ZEDGE(a))
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };
-// NOTE on u_lo in the increment: when plane j-1 is output, u_lo still holds u(j-1) (it is rolled
-// afterwards), so (u+ - u)(j-1) uses the right old value.
 
 // ==========================================================================================
 // K2  rhs from the compressed state, optionally fused with the first Jacobi sweep (MODE 1)
 //     or with CG's r0 = rhs - A u, x = u (MODE 2).   split_bregman_tvd.py:84-89; jacobi.py:107-114;
-//     cg.py:37-47 + scipy cg (r = b - A x).  With `expl` the first outer iteration of a warm
-//     start reads the reference's explicit d and b (split_bregman_tvd.py:93-97).
+//     cg.py:37-47 + scipy cg (r = b - A x).  With t == nullptr the first outer iteration of a
+//     warm start reads the reference's explicit d and b (split_bregman_tvd.py:93-97).
+//     Shared rows: [slot*D + 0] = u(j), [slot*D + d] = w_d(j) (d >= 1).
 // ==========================================================================================
 enum { RHS_ONLY = 0, RHS_SWEEP = 1, RHS_CGINIT = 2 };
 
-template <typename T, int D, bool ISO, int MODE>
+template <typename T, int D, bool ISO, int MODE, bool HET>
 struct KRhs {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 2, NROWS = 2 * D;
@@ -728,7 +815,7 @@ struct KRhs {
     Geom g;
     Coefs<T> k;
     const T* f;
-    const T* t;        // compressed state, or nullptr when expl
+    const T* t;        // compressed state, or nullptr when the warm-start arrays are used
     long long tcs;
     const T* xd;       // explicit d0, b0 (warm start), component stride xcs
     const T* xb;
@@ -742,37 +829,17 @@ struct KRhs {
   };
   C c;
   int j, rowe;
-  Vec<T> u_lo, u_c, u_hi, w0_prev, w0_cur, wa_cur[D], om_c, f_c, invd, cnb;
+  Vec<T> u_lo, u_c, u_hi, w0_prev, w0_cur, wa_cur[D], om_c, f_c, el_c;
+  RawT<T, D> nx;
+  Vec<T> nx_u, nx_f, nx_om;
   double red[NRED];
 
-  TVDK_DEV void load_w(const Args& a, int z, Vec<T> (&w)[D]) {
-    Vec<T> tv[D], dv[D];
-    const bool expl = a.t == nullptr;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      if (!expl)
-        tv[d] = ldv(c, a.g, a.t + d * a.tcs, z);
-      else {
-        tv[d] = ldv(c, a.g, a.xb + d * a.xcs, z);
-        dv[d] = ldv(c, a.g, a.xd + d * a.xcs, z);
-      }
-    }
-    const Vec<T> mu = ldcoef(c, a.g, a.k.mu, z), el = ldcoef(c, a.g, a.k.ell, z);
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      const VoxCoef<T> vc = voxcoef(a.k.sc, mu.v[v], (T)1, el.v[v]);
-      if (!expl) {
-        T t[D], b[D], ww[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) t[d] = tv[d].v[v];
-        bw_from_t<T, D, ISO>(t, vc.kappa, vc.ell, b, ww);
-#pragma unroll
-        for (int d = 0; d < D; ++d) w[d].v[v] = ww[d];
-      } else {
-#pragma unroll
-        for (int d = 0; d < D; ++d) w[d].v[v] = vc.ell * (tv[d].v[v] - dv[d].v[v]);
-      }
-    }
+  TVDK_DEV void prefetch(const Args& a, int z) {
+    const long long o = c.at(a.g, z);
+    load_rawt<true, HET>(nx, c, a.k, a.t, a.tcs, a.xb, a.xd, a.xcs, o);
+    nx_f = ldo(a.f, o);
+    nx_om = ldcoef<HET>(c, a.k.omega, o);
+    if (MODE != RHS_ONLY && c.has_zhi(a.g, z)) nx_u = ldo(a.u, o + c.s0b);
   }
 
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
@@ -781,59 +848,57 @@ struct KRhs {
     rowe = C::row_elems(lc.ntx, lc.nty);
     red[0] = red[1] = 0.0;
     j = c.z0;
+    const long long o = c.at(a.g, j);
     w0_prev = vsplat<T>((T)0);
     u_c = vsplat<T>((T)0);
-    if (MODE != RHS_ONLY) u_c = ldv(c, a.g, a.u, j);
+    if (MODE != RHS_ONLY) u_c = ldo(a.u, o);
     u_lo = u_c;
     if (c.has_zlo(a.g, j)) {
-      Vec<T> w[D];
-      load_w(a, j - 1, w);
-      w0_prev = w[0];
-      if (MODE != RHS_ONLY) u_lo = ldv(c, a.g, a.u, j - 1);
+      RawT<T, D> r;
+      load_rawt<true, HET>(r, c, a.k, a.t, a.tcs, a.xb, a.xd, a.xcs, o - c.s0b);
+      Vec<T> bb[D], ww[D];
+      bw_plane<T, D, ISO, HET>(r, a.k.sc, a.t == nullptr, bb, ww);
+      w0_prev = ww[0];
+      if (MODE != RHS_ONLY) u_lo = ldo(a.u, o - c.s0b);
     }
+    prefetch(a, j);
     return true;
   }
   TVDK_DEV bool more() const { return j < c.z1; }
 
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
     const int slot = j & 1;
-    Vec<T> w[D];
-    load_w(a, j, w);
-    w0_cur = w[0];
+    Vec<T> bb[D], ww[D];
+    bw_plane<T, D, ISO, HET>(nx, a.k.sc, a.t == nullptr, bb, ww);
+    w0_cur = ww[0];
 #pragma unroll
-    for (int d = 1; d < D; ++d) wa_cur[d] = w[d];
-    f_c = ldv(c, a.g, a.f, j);
-    const Vec<T> om = ldcoef(c, a.g, a.k.omega, j);
-    om_c = om;
+    for (int d = 1; d < D; ++d) wa_cur[d] = ww[d];
+    f_c = nx_f;
+    om_c = nx_om;
+    el_c = nx.el;
     if (MODE != RHS_ONLY) {
-      u_hi = c.has_zhi(a.g, j) ? ldv(c, a.g, a.u, j + 1) : u_c;
+      u_hi = c.has_zhi(a.g, j) ? nx_u : u_c;
       sst(srow<T>(smem, slot * D + 0, rowe), c, u_c);
-      if (MODE == RHS_SWEEP) {
-        const Vec<T> el = ldcoef(c, a.g, a.k.ell, j);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          const VoxCoef<T> vc = voxcoef(a.k.sc, (T)0, om.v[v], el.v[v]);
-          invd.v[v] = vc.inv_diag;
-          cnb.v[v] = vc.c_nb;
-        }
-      }
     }
 #pragma unroll
     for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * D + d, rowe), c, wa_cur[d]);
+    if (j + 1 < c.z1) prefetch(a, j + 1);
   }
 
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+  TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
     const int slot = j & 1;
     Vec<T> rhs;
 #pragma unroll
     for (int v = 0; v < V; ++v) rhs.v[v] = om_c.v[v] * f_c.v[v];
-    if (c.has_zlo(a.g, j)) {
+    if (c.template ZLO<E>(a.g, j)) {
 #pragma unroll
       for (int v = 0; v < V; ++v) rhs.v[v] += w0_cur.v[v] - w0_prev.v[v];
     }
     if (D == 3) {
       const Vec<T> wm = sym(srow<T>(smem, slot * D + 1, rowe), c);
-      if (c.hylo) {
+      if (c.template YLO<E>()) {
 #pragma unroll
         for (int v = 0; v < V; ++v) rhs.v[v] += wa_cur[1].v[v] - wm.v[v];
       }
@@ -843,20 +908,23 @@ struct KRhs {
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const T left = v > 0 ? wa_cur[D - 1].v[v > 0 ? v - 1 : 0] : wl;
-        if (c.hl[v]) rhs.v[v] += wa_cur[D - 1].v[v] - left;
+        if (c.template HL<E>(v)) rhs.v[v] += wa_cur[D - 1].v[v] - left;
       }
     }
-    if (MODE == RHS_ONLY || MODE == RHS_SWEEP) stv(c, a.g, a.rhs, j, rhs);
+    if (MODE == RHS_ONLY || MODE == RHS_SWEEP) sto(c, a.rhs, c.cur, rhs);
     if (MODE == RHS_SWEEP) {
-      const Vec<T> nb = nsum<T, D>(c, u_lo, u_hi, u_c, srow<T>(smem, slot * D + 0, rowe));
+      const Vec<T> nb = nsum<T, D, E>(c, u_lo, u_hi, u_c, srow<T>(smem, slot * D + 0, rowe));
       Vec<T> xn;
 #pragma unroll
-      for (int v = 0; v < V; ++v) xn.v[v] = rhs.v[v] * invd.v[v] + nb.v[v] * cnb.v[v];
-      stv(c, a.g, a.x, j, xn);
+      for (int v = 0; v < V; ++v) {
+        const VoxCoef<T> vc = voxcoef<HET>(a.k.sc, (T)0, om_c.v[v], el_c.v[v]);
+        xn.v[v] = rhs.v[v] * vc.inv_diag + nb.v[v] * vc.c_nb;
+      }
+      sto(c, a.x, c.cur, xn);
       if (c.st) {  // Jacobi tol branch, first sweep: ||x_new - x||^2 and ||x0||^2
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (c.okc[v]) {
+          if (c.template OK<E>(v)) {
             const double df = (double)xn.v[v] - (double)u_c.v[v];
             red[0] += df * df;
             red[1] += (double)u_c.v[v] * (double)u_c.v[v];
@@ -864,17 +932,17 @@ struct KRhs {
       }
     }
     if (MODE == RHS_CGINIT) {
-      const Vec<T> au = apply_A<T, D>(c, a.g, j, u_lo, u_c, u_hi, srow<T>(smem, slot * D + 0, rowe), om_c,
-                                      a.k.ell);
+      const Vec<T> au = apply_A<T, D, E, HET>(c, a.g, j, c.cur, u_lo, u_c, u_hi, srow<T>(smem, slot * D + 0, rowe),
+                                         om_c, a.k.ell);
       Vec<T> r0;
 #pragma unroll
       for (int v = 0; v < V; ++v) r0.v[v] = rhs.v[v] - au.v[v];
-      stv(c, a.g, a.r, j, r0);
-      stv(c, a.g, a.x, j, u_c);
+      sto(c, a.r, c.cur, r0);
+      sto(c, a.x, c.cur, u_c);
       if (c.st) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (c.okc[v]) {
+          if (c.template OK<E>(v)) {
             red[0] += (double)rhs.v[v] * (double)rhs.v[v];
             red[1] += (double)r0.v[v] * (double)r0.v[v];
           }
@@ -883,7 +951,14 @@ struct KRhs {
     u_lo = u_c;
     u_c = u_hi;
     w0_prev = w0_cur;
+    c.cur += c.s0b;
     ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge || ZEDGE(a))
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };
@@ -891,7 +966,7 @@ struct KRhs {
 // ==========================================================================================
 // K4  Jacobi sweep  x_out = rhs/diag + N(x_in)/(diag/ell)       (jacobi.py:101-131)
 // ==========================================================================================
-template <typename T, int D>
+template <typename T, int D, bool HET>
 struct KSweep {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 2, NROWS = 2;
@@ -907,7 +982,7 @@ struct KSweep {
   };
   C c;
   int j, rowe;
-  Vec<T> x_lo, x_c, x_hi;
+  Vec<T> x_lo, x_c, x_hi, nx_x, nx_rhs, rhs_c;
   double red[NRED];
 
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
@@ -916,30 +991,39 @@ struct KSweep {
     rowe = C::row_elems(lc.ntx, lc.nty);
     red[0] = red[1] = 0.0;
     j = c.z0;
-    x_c = ldv(c, a.g, a.x_in, j);
-    x_lo = c.has_zlo(a.g, j) ? ldv(c, a.g, a.x_in, j - 1) : x_c;
+    const long long o = c.at(a.g, j);
+    x_c = ldo(a.x_in, o);
+    x_lo = c.has_zlo(a.g, j) ? ldo(a.x_in, o - c.s0b) : x_c;
+    nx_rhs = ldo(a.rhs, o);
+    if (c.has_zhi(a.g, j)) nx_x = ldo(a.x_in, o + c.s0b);
     return true;
   }
   TVDK_DEV bool more() const { return j < c.z1; }
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
-    x_hi = c.has_zhi(a.g, j) ? ldv(c, a.g, a.x_in, j + 1) : x_c;
+    x_hi = c.has_zhi(a.g, j) ? nx_x : x_c;
+    rhs_c = nx_rhs;
     sst(srow<T>(smem, j & 1, rowe), c, x_c);
+    if (j + 1 < c.z1) {
+      nx_rhs = ldo(a.rhs, c.cur + c.s0b);
+      if (c.has_zhi(a.g, j + 1)) nx_x = ldo(a.x_in, c.cur + 2 * c.s0b);
+    }
   }
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
-    const Vec<T> nb = nsum<T, D>(c, x_lo, x_hi, x_c, srow<T>(smem, j & 1, rowe));
-    const Vec<T> rhs = ldv(c, a.g, a.rhs, j);
-    const Vec<T> om = ldcoef(c, a.g, a.k.omega, j), el = ldcoef(c, a.g, a.k.ell, j);
+  TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
+    const Vec<T> nb = nsum<T, D, E>(c, x_lo, x_hi, x_c, srow<T>(smem, j & 1, rowe));
+    const Vec<T> om = ldcoef<HET>(c, a.k.omega, c.cur), el = ldcoef<HET>(c, a.k.ell, c.cur);
     Vec<T> xn;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-      const VoxCoef<T> vc = voxcoef(a.k.sc, (T)0, om.v[v], el.v[v]);
-      xn.v[v] = rhs.v[v] * vc.inv_diag + nb.v[v] * vc.c_nb;
+      const VoxCoef<T> vc = voxcoef<HET>(a.k.sc, (T)0, om.v[v], el.v[v]);
+      xn.v[v] = rhs_c.v[v] * vc.inv_diag + nb.v[v] * vc.c_nb;
     }
-    stv(c, a.g, a.x_out, j, xn);
+    sto(c, a.x_out, c.cur, xn);
     if (c.st) {
 #pragma unroll
       for (int v = 0; v < V; ++v)
-        if (c.okc[v]) {
+        if (c.template OK<E>(v)) {
           const double df = (double)xn.v[v] - (double)x_c.v[v];
           red[0] += df * df;
           red[1] += (double)x_c.v[v] * (double)x_c.v[v];
@@ -947,7 +1031,14 @@ struct KSweep {
     }
     x_lo = x_c;
     x_c = x_hi;
+    c.cur += c.s0b;
     ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge || ZEDGE(a))
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };
@@ -961,7 +1052,7 @@ struct KSweep {
 // ==========================================================================================
 enum { CG_PQ = 0, CG_UPDATE = 1, CG_MATVEC = 2 };
 
-template <typename T, int D, int MODE>
+template <typename T, int D, int MODE, bool HET>
 struct KCg {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 1, NROWS = 2;
@@ -985,19 +1076,27 @@ struct KCg {
   T coef;
   bool first;
   Vec<T> p_lo, p_c, p_hi;
+  Vec<T> nx_p, nx_r;  // raw plane j+1 (PQ: old p and r; else p), loaded one step ahead
+  Vec<T> cx, cr;      // UPDATE: x(j), r(j), loaded one step ahead (interior threads only)
   double red[NRED];
 
-  TVDK_DEV Vec<T> load_p(const Args& a, int z) {
+  TVDK_DEV void load_raw(const Args& a, long long o) {
     if (MODE == CG_PQ) {
-      const Vec<T> r = ldv(c, a.g, a.r_in, z);
-      if (first) return r;
-      const Vec<T> p = ldv(c, a.g, a.p_in, z);
+      nx_r = ldo(a.r_in, o);
+      if (!first) nx_p = ldo(a.p_in, o);
+    } else {
+      nx_p = ldo(a.p_in, o);
+    }
+  }
+  TVDK_DEV Vec<T> make_p() const {
+    if (MODE == CG_PQ) {
+      if (first) return nx_r;
       Vec<T> o;
 #pragma unroll
-      for (int v = 0; v < V; ++v) o.v[v] = coef * p.v[v] + r.v[v];  // p *= beta; p += r
+      for (int v = 0; v < V; ++v) o.v[v] = coef * nx_p.v[v] + nx_r.v[v];  // p *= beta; p += r
       return o;
     }
-    return ldv(c, a.g, a.p_in, z);
+    return nx_p;
   }
 
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
@@ -1008,45 +1107,70 @@ struct KCg {
     coef = (MODE == CG_MATVEC || !a.coef.p) ? (T)0 : (T)a.coef.at(c.b);
     first = (MODE == CG_PQ) && (a.first_all || a.first.at(c.b));
     j = c.z0;
-    p_c = load_p(a, j);
-    p_lo = c.has_zlo(a.g, j) ? load_p(a, j - 1) : p_c;
+    const long long o = c.at(a.g, j);
+    load_raw(a, o);
+    p_c = make_p();
+    p_lo = p_c;
+    if (c.has_zlo(a.g, j)) {
+      load_raw(a, o - c.s0b);
+      p_lo = make_p();
+    }
+    if (c.has_zhi(a.g, j)) load_raw(a, o + c.s0b);
+    if (MODE == CG_UPDATE && c.st) {
+      cx = ldw(a.x, o);
+      cr = ldw(a.r, o);
+    }
     return true;
   }
   TVDK_DEV bool more() const { return j < c.z1; }
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
-    p_hi = c.has_zhi(a.g, j) ? load_p(a, j + 1) : p_c;
+    p_hi = c.has_zhi(a.g, j) ? make_p() : p_c;
     sst(srow<T>(smem, j & 1, rowe), c, p_c);
+    if (j + 1 < c.z1 && c.has_zhi(a.g, j + 1)) load_raw(a, c.cur + 2 * c.s0b);
   }
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
-    const Vec<T> om = ldcoef(c, a.g, a.k.omega, j);
-    const Vec<T> q = apply_A<T, D>(c, a.g, j, p_lo, p_c, p_hi, srow<T>(smem, j & 1, rowe), om, a.k.ell);
+  TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
+    const Vec<T> om = ldcoef<HET>(c, a.k.omega, c.cur);
+    const Vec<T> q = apply_A<T, D, E, HET>(c, a.g, j, c.cur, p_lo, p_c, p_hi, srow<T>(smem, j & 1, rowe), om, a.k.ell);
     if (MODE == CG_PQ) {
-      stv(c, a.g, a.p_out, j, p_c);
+      sto(c, a.p_out, c.cur, p_c);
       if (c.st) {
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (c.okc[v]) red[0] += (double)p_c.v[v] * (double)q.v[v];
+          if (c.template OK<E>(v)) red[0] += (double)p_c.v[v] * (double)q.v[v];
       }
     } else if (MODE == CG_UPDATE) {
       if (c.st) {  // x and r are updated in place: only the owning thread touches them
-        Vec<T> x = ldv_rw(c, a.g, a.x, j), r = ldv_rw(c, a.g, a.r, j);
+        Vec<T> x = cx, r = cr;
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           x.v[v] += coef * p_c.v[v];
           r.v[v] -= coef * q.v[v];
         }
-        stv(c, a.g, a.x, j, x);
-        stv(c, a.g, a.r, j, r);
+        stw(a.x, c.cur, x);
+        stw(a.r, c.cur, r);
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          if (c.okc[v]) red[0] += (double)r.v[v] * (double)r.v[v];
+          if (c.template OK<E>(v)) red[0] += (double)r.v[v] * (double)r.v[v];
+        if (j + 1 < c.z1) {
+          cx = ldw(a.x, c.cur + c.s0b);
+          cr = ldw(a.r, c.cur + c.s0b);
+        }
       }
     } else {
-      stv(c, a.g, a.p_out, j, q);
+      sto(c, a.p_out, c.cur, q);
     }
     p_lo = p_c;
     p_c = p_hi;
+    c.cur += c.s0b;
     ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge || ZEDGE(a))
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };
@@ -1055,7 +1179,7 @@ struct KCg {
 // K3  shrinkage + Bregman update on the compressed state (split_bregman_tvd.py:136-146),
 //     increment partials (:161), in-place update of the iterate (:170).
 // ==========================================================================================
-template <typename T, int D, bool ISO>
+template <typename T, int D, bool ISO, bool HET>
 struct KShrink {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 0, RH = 1, NRED = 1, NROWS = 2;
@@ -1078,9 +1202,19 @@ struct KShrink {
   C c;
   int j, rowe;
   const T* un;
-  Vec<T> up_c, up_hi;
+  Vec<T> up_c, up_hi, nx_up;
+  // t and u may be updated in place (t_out == t_in, u_out == u_old): only the owning (interior)
+  // thread touches them, one plane ahead of their use; halo threads merely publish u+ rows
+  RawT<T, D> nx;
+  Vec<T> nx_uo;
   double red[NRED];
 
+  TVDK_DEV void prefetch_own(const Args& a, long long o) {
+    if (c.st) {
+      load_rawt<false, HET>(nx, c, a.k, a.t_in, a.tcs, a.xb, a.xb, a.xcs, o);
+      nx_uo = ldw(a.u_old, o);
+    }
+  }
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
     if (a.skip && a.skip[lc.bz].done) return false;
     c.setup(a.g, lc);
@@ -1088,77 +1222,67 @@ struct KShrink {
     red[0] = 0.0;
     un = a.unew[a.use_sel ? a.skip[lc.bz].jac_sel : 0];
     j = c.z0;
-    up_c = ldv(c, a.g, un, j);
+    const long long o = c.at(a.g, j);
+    up_c = ldo(un, o);
+    if (c.has_zhi(a.g, j)) nx_up = ldo(un, o + c.s0b);
+    prefetch_own(a, o);
     return true;
   }
   TVDK_DEV bool more() const { return j < c.z1; }
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
-    up_hi = c.has_zhi(a.g, j) ? ldv(c, a.g, un, j + 1) : up_c;
+    up_hi = c.has_zhi(a.g, j) ? nx_up : up_c;
     sst(srow<T>(smem, j & 1, rowe), c, up_c);
+    if (j + 1 < c.z1 && c.has_zhi(a.g, j + 1)) nx_up = ldo(un, c.cur + 2 * c.s0b);
   }
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+  TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
     const T* prow = srow<T>(smem, j & 1, rowe);
     const bool expl = a.t_in == nullptr;
-    // t and u may be updated in place (t_out == t_in, u_out == u_old): only the owning
-    // (interior) thread touches them; halo threads merely publish u+ rows.
-    Vec<T> tv[D];
-    Vec<T> uo = vsplat<T>((T)0);
-#pragma unroll
-    for (int d = 0; d < D; ++d) tv[d] = vsplat<T>((T)0);
-    if (c.st) {
-#pragma unroll
-      for (int d = 0; d < D; ++d)
-        tv[d] = expl ? ldv_rw(c, a.g, a.xb + d * a.xcs, j) : ldv_rw(c, a.g, a.t_in + d * a.tcs, j);
-      uo = ldv_rw(c, a.g, a.u_old, j);
-    }
-    const Vec<T> mu = ldcoef(c, a.g, a.k.mu, j), el = ldcoef(c, a.g, a.k.ell, j);
     Vec<T> g[D];
-    const bool zhi = c.has_zhi(a.g, j);
+    const bool zhi = c.template ZHI<E>(a.g, j);
 #pragma unroll
     for (int v = 0; v < V; ++v) g[0].v[v] = zhi ? up_hi.v[v] - up_c.v[v] : (T)0;
     if (D == 3) {
       const Vec<T> yp = syp(prow, c);
 #pragma unroll
-      for (int v = 0; v < V; ++v) g[1].v[v] = c.hyhi ? yp.v[v] - up_c.v[v] : (T)0;
+      for (int v = 0; v < V; ++v) g[1].v[v] = c.template YHI<E>() ? yp.v[v] - up_c.v[v] : (T)0;
     }
     {
       const T xr = sxp(prow, c);
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         const T right = v < V - 1 ? up_c.v[v < V - 1 ? v + 1 : 0] : xr;
-        g[D - 1].v[v] = c.hr[v] ? right - up_c.v[v] : (T)0;
+        g[D - 1].v[v] = c.template HR<E>(v) ? right - up_c.v[v] : (T)0;
       }
     }
-    Vec<T> tn[D];
-#pragma unroll
-    for (int v = 0; v < V; ++v) {
-      T b[D];
-      if (expl) {
-#pragma unroll
-        for (int d = 0; d < D; ++d) b[d] = tv[d].v[v];
-      } else {
-        T t[D], w[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) t[d] = tv[d].v[v];
-        const VoxCoef<T> vc = voxcoef(a.k.sc, mu.v[v], (T)1, el.v[v]);
-        bw_from_t<T, D, ISO>(t, vc.kappa, vc.ell, b, w);
-      }
-#pragma unroll
-      for (int d = 0; d < D; ++d) tn[d].v[v] = g[d].v[v] + b[d];
-    }
-#pragma unroll
-    for (int d = 0; d < D; ++d) stv(c, a.g, a.t_out + d * a.tcs, j, tn[d]);
-    if (a.u_out) stv(c, a.g, a.u_out, j, up_c);
     if (c.st) {
+      Vec<T> bb[D], ww[D], tn[D];
+      bw_plane<T, D, ISO, HET>(nx, a.k.sc, expl, bb, ww);
+#pragma unroll
+      for (int d = 0; d < D; ++d)
+#pragma unroll
+        for (int v = 0; v < V; ++v) tn[d].v[v] = g[d].v[v] + bb[d].v[v];
+#pragma unroll
+      for (int d = 0; d < D; ++d) stw(a.t_out + d * a.tcs, c.cur, tn[d]);
+      if (a.u_out) stw(a.u_out, c.cur, up_c);
 #pragma unroll
       for (int v = 0; v < V; ++v)
-        if (c.okc[v]) {
-          const double df = (double)up_c.v[v] - (double)uo.v[v];
+        if (c.template OK<E>(v)) {
+          const double df = (double)up_c.v[v] - (double)nx_uo.v[v];
           red[0] += df * df;
         }
+      if (j + 1 < c.z1) prefetch_own(a, c.cur + c.s0b);
     }
     up_c = up_hi;
+    c.cur += c.s0b;
     ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge || ZEDGE(a))
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };
@@ -1169,6 +1293,7 @@ struct KShrink {
 template <typename T, int D>
 struct KEnergy {
   static constexpr int V = Vec<T>::N;
+  static constexpr bool HET = true;
   static constexpr int LH = 0, RH = 1, NRED = 2, NROWS = 2;
   typedef Col<T, D, LH, RH> C;
   struct Args {
@@ -1189,18 +1314,18 @@ struct KEnergy {
     rowe = C::row_elems(lc.ntx, lc.nty);
     red[0] = red[1] = 0.0;
     j = c.z0;
-    x_c = ldv(c, a.g, a.x, j);
+    x_c = ldo(a.x, c.cur);
     return true;
   }
   TVDK_DEV bool more() const { return j < c.z1; }
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
-    x_hi = c.has_zhi(a.g, j) ? ldv(c, a.g, a.x, j + 1) : x_c;
+    x_hi = c.has_zhi(a.g, j) ? ldo(a.x, c.cur + c.s0b) : x_c;
     sst(srow<T>(smem, j & 1, rowe), c, x_c);
   }
   TVDK_DEV void post(const Args& a, unsigned char* smem) {
     const T* prow = srow<T>(smem, j & 1, rowe);
-    const Vec<T> f = ldv(c, a.g, a.f, j);
-    const Vec<T> mu = ldcoef(c, a.g, a.k.mu, j), om = ldcoef(c, a.g, a.k.omega, j);
+    const Vec<T> f = ldo(a.f, c.cur);
+    const Vec<T> mu = ldcoef<HET>(c, a.k.mu, c.cur), om = ldcoef<HET>(c, a.k.omega, c.cur);
     const bool zhi = c.has_zhi(a.g, j);
     Vec<T> yp = x_c;
     if (D == 3) yp = syp(prow, c);
@@ -1219,6 +1344,7 @@ struct KEnergy {
         }
     }
     x_c = x_hi;
+    c.cur += c.s0b;
     ++j;
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
@@ -1246,8 +1372,9 @@ struct KDot {
     c.setup(a.g, lc);
     red[0] = 0.0;
     if (c.st) {
-      for (int z = c.z0; z < c.z1; ++z) {
-        const Vec<T> x = ldv(c, a.g, a.x, z), y = ldv(c, a.g, a.y, z);
+      long long o = c.cur;
+      for (int z = c.z0; z < c.z1; ++z, o += c.s0b) {
+        const Vec<T> x = ldo(a.x, o), y = ldo(a.y, o);
 #pragma unroll
         for (int v = 0; v < V; ++v)
           if (c.okc[v]) {
@@ -1272,6 +1399,7 @@ struct KDot {
 template <typename T, int D, bool ISO>
 struct KExpand {
   static constexpr int V = Vec<T>::N;
+  static constexpr bool HET = true;
   static constexpr int LH = 0, RH = 0, NRED = 0, NROWS = 0;
   typedef Col<T, D, LH, RH> C;
   struct Args {
@@ -1289,28 +1417,19 @@ struct KExpand {
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
     c.setup(a.g, lc);
     if (c.st) {
-      for (int z = c.z0; z < c.z1; ++z) {
-        Vec<T> tv[D], dv[D], bv[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) tv[d] = ldv(c, a.g, a.t + d * a.tcs, z);
-        const Vec<T> mu = ldcoef(c, a.g, a.k.mu, z), el = ldcoef(c, a.g, a.k.ell, z);
-#pragma unroll
-        for (int v = 0; v < V; ++v) {
-          T t[D], b[D], w[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) t[d] = tv[d].v[v];
-          const VoxCoef<T> vc = voxcoef(a.k.sc, mu.v[v], (T)1, el.v[v]);
-          bw_from_t<T, D, ISO>(t, vc.kappa, vc.ell, b, w);
-#pragma unroll
-          for (int d = 0; d < D; ++d) {
-            bv[d].v[v] = b[d];
-            dv[d].v[v] = t[d] - b[d];  // d = t - b  (b = t - d in the reference)
-          }
-        }
+      long long o = c.cur;
+      for (int z = c.z0; z < c.z1; ++z, o += c.s0b) {
+        RawT<T, D> r;
+        load_rawt<true, HET>(r, c, a.k, a.t, a.tcs, (const T*)nullptr, (const T*)nullptr, 0, o);
+        Vec<T> bb[D], ww[D];
+        bw_plane<T, D, ISO, HET>(r, a.k.sc, false, bb, ww);
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          stv(c, a.g, a.d + d * a.ocs, z, dv[d]);
-          stv(c, a.g, a.b + d * a.ocs, z, bv[d]);
+          Vec<T> dv;
+#pragma unroll
+          for (int v = 0; v < V; ++v) dv.v[v] = r.t[d].v[v] - bb[d].v[v];  // d = t - b
+          stw(a.d + d * a.ocs, o, dv);
+          stw(a.b + d * a.ocs, o, bb[d]);
         }
       }
     }
@@ -1341,8 +1460,10 @@ struct KSelectCopy {
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
     if (a.stats && a.stats[lc.bz].cur_buf != a.want) return false;
     c.setup(a.g, lc);
-    if (c.st)
-      for (int z = c.z0; z < c.z1; ++z) stv(c, a.g, a.dst, z, ldv(c, a.g, a.src, z));
+    if (c.st) {
+      long long o = c.cur;
+      for (int z = c.z0; z < c.z1; ++z, o += c.s0b) stw(a.dst, o, ldo(a.src, o));
+    }
     return true;
   }
   TVDK_DEV bool more() const { return false; }

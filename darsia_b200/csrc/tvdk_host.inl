@@ -19,6 +19,7 @@
 
 #include <algorithm>
 #include <string>
+#include <type_traits>
 
 namespace tvdk {
 
@@ -126,6 +127,16 @@ struct LaunchCfg {
   Geom g;
 };
 
+static thread_local Tune g_tune = {0, 0, 0};
+
+static Tune merge_tune(int tx, int ty, int zc) {
+  Tune t;
+  t.tile_x = tx > 0 ? tx : g_tune.tile_x;
+  t.tile_y = ty > 0 ? ty : g_tune.tile_y;
+  t.zchunk = zc > 0 ? zc : g_tune.zchunk;
+  return t;
+}
+
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 template <class K, typename T, int D>
@@ -136,7 +147,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
   const int halo_x = K::LH + C::RHX;
   const int need_x = (g.nx + V - 1) / V + halo_x;  // vectors to cover one row incl. halo
   if (D == 2) {
-    int ntx = tune.tile_x > 0 ? tune.tile_x : 128;
+    int ntx = tune.tile_x > 0 ? round_up(tune.tile_x, 32) : 128;
     ntx = std::min(ntx, round_up(need_x, 32));
     ntx = std::max(ntx, 32);
     L.ntx = ntx;
@@ -161,11 +172,15 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
   const int nz = g.z_end - g.z_begin;
   int zc = tune.zchunk;
   if (zc <= 0) {
+    // Many more CTAs than resident slots (148 SMs x 4..8 CTAs): several waves, so the tail wave
+    // is a small fraction, while a chunk stays long enough to amortise its 1-2 plane prologue.
+    // Measured on B200 (profiles/r1_tune_2d_f64.txt): 32 planes per CTA is the sweet spot in 2-D.
     const long long tiles = (long long)g.xtiles * g.ytiles * g.nb;
-    const long long target = 148LL * 8;
+    const long long target = 148LL * 32;
     const long long want = std::max(1LL, (target + tiles - 1) / tiles);
     zc = (int)((nz + want - 1) / want);
-    zc = std::max(zc, 16);
+    zc = std::max(zc, 8);
+    zc = std::min(zc, D == 2 ? 32 : 16);
   }
   zc = std::min(zc, nz);
   g.zchunk = zc;
@@ -192,9 +207,9 @@ static size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 template <typename T, int D>
 static size_t partial_capacity(const Geom& g, const Tune& tune) {
   // the fused kernel has the widest halo (fewest interior columns per block) => most blocks
-  LaunchCfg a = plan_launch<KFusedJ1<T, D, false>, T, D>(g, tune, true);
-  LaunchCfg b = plan_launch<KSweep<T, D>, T, D>(g, tune, false);
-  LaunchCfg c = plan_launch<KShrink<T, D, false>, T, D>(g, tune, false);
+  LaunchCfg a = plan_launch<KFusedJ1<T, D, false, false>, T, D>(g, tune, true);
+  LaunchCfg b = plan_launch<KSweep<T, D, false>, T, D>(g, tune, false);
+  LaunchCfg c = plan_launch<KShrink<T, D, false, false>, T, D>(g, tune, false);
   LaunchCfg d = plan_launch<KDot<T, D, 0>, T, D>(g, tune, false);
   size_t m = 0;
   for (const LaunchCfg* L : {&a, &b, &c, &d}) m = std::max(m, (size_t)L->gx * L->gy * L->gz);
@@ -228,6 +243,17 @@ static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_ti
     return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
   ++g_launches;
   return backend::launch<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
+}
+
+// run f(std::bool_constant<a>, std::bool_constant<b>) -- maps runtime flags onto template args
+template <class F>
+static int dispatch2(bool a, bool b, F&& f) {
+  if (a) {
+    if (b) return f(std::true_type{}, std::true_type{});
+    return f(std::true_type{}, std::false_type{});
+  }
+  if (b) return f(std::false_type{}, std::true_type{});
+  return f(std::false_type{}, std::false_type{});
 }
 
 static Fin no_fin() {
@@ -270,7 +296,7 @@ static FieldPlan field_plan(const tvdk_problem_t* p) {
 template <typename T, int D>
 static size_t workspace_bytes_impl(const tvdk_problem_t* p) {
   Geom g = make_geom(p->geom);
-  Tune tune = {p->tile_x, p->tile_y, p->zchunk};
+  Tune tune = merge_tune(p->tile_x, p->tile_y, p->zchunk);
   const size_t cap = partial_capacity<T, D>(g, tune);
   const FieldPlan fp = field_plan(p);
   const size_t field_bytes = align_up((size_t)g.sb * g.nb * sizeof(T), 256);
@@ -280,7 +306,7 @@ static size_t workspace_bytes_impl(const tvdk_problem_t* p) {
 template <typename T, int D>
 static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched) {
   const Geom g = make_geom(p->geom);
-  const Tune tune = {p->tile_x, p->tile_y, p->zchunk};
+  const Tune tune = merge_tune(p->tile_x, p->tile_y, p->zchunk);
   const bool iso = p->isotropic != 0;
   const FieldPlan fp = field_plan(p);
   const size_t need = workspace_bytes_impl<T, D>(p);
@@ -358,28 +384,22 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
     return fn;
   };
 
+  const bool het = k.sc.hetero != 0;
+
   // shrink + Bregman update + in-place u update, shared by the unfused routes
   auto launch_shrink = [&](int it, int cur, const T* u0, const T* u1, const T* u2, int use_sel, bool expl_now) {
-    Fin fn = outer_fin(it, cur);
-    if (iso) {
-      typename KShrink<T, D, true>::Args a;
+    const Fin fn = outer_fin(it, cur);
+    return dispatch2(iso, het, [&](auto I, auto H) {
+      typedef KShrink<T, D, decltype(I)::value, decltype(H)::value> K;
+      typename K::Args a;
       memset(&a, 0, sizeof a);
       a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
       a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
       a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
       a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;
       a.skip = st; a.fin = fn;
-      return run<KShrink<T, D, true>, T, D>(a, g, tune, false, sc, stream);
-    } else {
-      typename KShrink<T, D, false>::Args a;
-      memset(&a, 0, sizeof a);
-      a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
-      a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
-      a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
-      a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;
-      a.skip = st; a.fin = fn;
-      return run<KShrink<T, D, false>, T, D>(a, g, tune, false, sc, stream);
-    }
+      return run<K, T, D>(a, g, tune, false, sc, stream);
+    });
   };
 
 #define TVDK_RHS_ARGS(a, cur, expl_now)                                   \
@@ -391,30 +411,22 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
   a.u = ubuf[cur]; a.skip = st; a.fin = no_fin();
 
   auto launch_rhs_sweep = [&](int cur, bool expl_now, T* rhs, T* x, const Fin& fn) {
-    if (iso) {
-      typename KRhs<T, D, true, RHS_SWEEP>::Args a;
+    return dispatch2(iso, het, [&](auto I, auto H) {
+      typedef KRhs<T, D, decltype(I)::value, RHS_SWEEP, decltype(H)::value> K;
+      typename K::Args a;
       TVDK_RHS_ARGS(a, cur, expl_now)
       a.rhs = rhs; a.x = x; a.fin = fn;
-      return run<KRhs<T, D, true, RHS_SWEEP>, T, D>(a, g, tune, false, sc, stream);
-    } else {
-      typename KRhs<T, D, false, RHS_SWEEP>::Args a;
-      TVDK_RHS_ARGS(a, cur, expl_now)
-      a.rhs = rhs; a.x = x; a.fin = fn;
-      return run<KRhs<T, D, false, RHS_SWEEP>, T, D>(a, g, tune, false, sc, stream);
-    }
+      return run<K, T, D>(a, g, tune, false, sc, stream);
+    });
   };
   auto launch_rhs_cginit = [&](int cur, bool expl_now, T* x, T* r, const Fin& fn) {
-    if (iso) {
-      typename KRhs<T, D, true, RHS_CGINIT>::Args a;
+    return dispatch2(iso, het, [&](auto I, auto H) {
+      typedef KRhs<T, D, decltype(I)::value, RHS_CGINIT, decltype(H)::value> K;
+      typename K::Args a;
       TVDK_RHS_ARGS(a, cur, expl_now)
       a.x = x; a.r = r; a.fin = fn;
-      return run<KRhs<T, D, true, RHS_CGINIT>, T, D>(a, g, tune, false, sc, stream);
-    } else {
-      typename KRhs<T, D, false, RHS_CGINIT>::Args a;
-      TVDK_RHS_ARGS(a, cur, expl_now)
-      a.x = x; a.r = r; a.fin = fn;
-      return run<KRhs<T, D, false, RHS_CGINIT>, T, D>(a, g, tune, false, sc, stream);
-    }
+      return run<K, T, D>(a, g, tune, false, sc, stream);
+    });
   };
 
   const bool tolmode = !fp.cg && p->solver_tol >= 0.0;
@@ -436,40 +448,40 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
     }
     if (fp.fusedj1 && !expl_now) {
       const Fin fn = outer_fin(it, 1 - cur);
-      if (iso) {
-        typename KFusedJ1<T, D, true>::Args a;
+      TVDK_TRY(dispatch2(iso, het, [&](auto I, auto H) {
+        typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
+        typename K::Args a;
         memset(&a, 0, sizeof a);
         a.k = k; a.f = f; a.u_in = ubuf[cur]; a.u_out = ubuf[1 - cur];
         a.t_in = tbuf[cur]; a.t_out = tbuf[1 - cur]; a.tcs_in = tcs[cur]; a.tcs_out = tcs[1 - cur];
         a.skip = st; a.fin = fn;
-        TVDK_TRY((run<KFusedJ1<T, D, true>, T, D>(a, g, tune, true, sc, stream)));
-      } else {
-        typename KFusedJ1<T, D, false>::Args a;
-        memset(&a, 0, sizeof a);
-        a.k = k; a.f = f; a.u_in = ubuf[cur]; a.u_out = ubuf[1 - cur];
-        a.t_in = tbuf[cur]; a.t_out = tbuf[1 - cur]; a.tcs_in = tcs[cur]; a.tcs_out = tcs[1 - cur];
-        a.skip = st; a.fin = fn;
-        TVDK_TRY((run<KFusedJ1<T, D, false>, T, D>(a, g, tune, true, sc, stream)));
-      }
+        return run<K, T, D>(a, g, tune, true, sc, stream);
+      }));
       cur = 1 - cur;
     } else if (fp.cg) {
       Fin fn = no_fin();
       fn.kind = FIN_CGINIT; fn.stats = st; fn.tol = p->solver_tol;
       TVDK_TRY(launch_rhs_cginit(cur, expl_now, X, RB, fn));
       for (int i = 0; i < p->solver_maxiter; ++i) {
-        typename KCg<T, D, CG_PQ>::Args a;
-        memset(&a, 0, sizeof a);
-        a.k = k; a.p_in = P[(i & 1) ^ 1]; a.r_in = RB; a.p_out = P[i & 1];
-        a.coef.p = &st[0].beta; a.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
-        a.first.p = &st[0].cg_first; a.first.stride = (int)(sizeof(tvdk_stat_t) / sizeof(int));
-        a.skip = st; a.fin = no_fin(); a.fin.kind = FIN_CGPQ; a.fin.stats = st;
-        TVDK_TRY((run<KCg<T, D, CG_PQ>, T, D>(a, g, tune, false, sc, stream)));
-        typename KCg<T, D, CG_UPDATE>::Args b;
-        memset(&b, 0, sizeof b);
-        b.k = k; b.p_in = P[i & 1]; b.x = X; b.r = RB;
-        b.coef.p = &st[0].alpha; b.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
-        b.skip = st; b.fin = no_fin(); b.fin.kind = FIN_CGRR; b.fin.stats = st;
-        TVDK_TRY((run<KCg<T, D, CG_UPDATE>, T, D>(b, g, tune, false, sc, stream)));
+        TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+          typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
+          typename K::Args a;
+          memset(&a, 0, sizeof a);
+          a.k = k; a.p_in = P[(i & 1) ^ 1]; a.r_in = RB; a.p_out = P[i & 1];
+          a.coef.p = &st[0].beta; a.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
+          a.first.p = &st[0].cg_first; a.first.stride = (int)(sizeof(tvdk_stat_t) / sizeof(int));
+          a.skip = st; a.fin = no_fin(); a.fin.kind = FIN_CGPQ; a.fin.stats = st;
+          return run<K, T, D>(a, g, tune, false, sc, stream);
+        }));
+        TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+          typedef KCg<T, D, CG_UPDATE, decltype(H)::value> K;
+          typename K::Args b;
+          memset(&b, 0, sizeof b);
+          b.k = k; b.p_in = P[i & 1]; b.x = X; b.r = RB;
+          b.coef.p = &st[0].alpha; b.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
+          b.skip = st; b.fin = no_fin(); b.fin.kind = FIN_CGRR; b.fin.stats = st;
+          return run<K, T, D>(b, g, tune, false, sc, stream);
+        }));
       }
       TVDK_TRY(launch_shrink(it, cur, X, nullptr, nullptr, 0, expl_now));
     } else {
@@ -483,13 +495,16 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       T* xout = XB;
       int out_id = 2;
       for (int s = 2; s <= p->solver_maxiter; ++s) {
-        typename KSweep<T, D>::Args a;
-        memset(&a, 0, sizeof a);
-        a.k = k; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
-        if (tolmode) {
-          a.fin.kind = FIN_JTOL; a.fin.stats = st; a.fin.tol = p->solver_tol; a.fin.buf_id = out_id;
-        }
-        TVDK_TRY((run<KSweep<T, D>, T, D>(a, g, tune, false, sc, stream)));
+        TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+          typedef KSweep<T, D, decltype(H)::value> K;
+          typename K::Args a;
+          memset(&a, 0, sizeof a);
+          a.k = k; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
+          if (tolmode) {
+            a.fin.kind = FIN_JTOL; a.fin.stats = st; a.fin.tol = p->solver_tol; a.fin.buf_id = out_id;
+          }
+          return run<K, T, D>(a, g, tune, false, sc, stream);
+        }));
         std::swap(xin, xout);
         out_id = 3 - out_id;
       }
@@ -550,14 +565,14 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
 template <typename T, int D>
 static size_t op_ws_impl(const tvdk_geom_t* gg) {
   Geom g = make_geom(*gg);
-  Tune tune = {0, 0, 0};
+  Tune tune = merge_tune(0, 0, 0);
   return scratch_bytes(partial_capacity<T, D>(g, tune), g.nb) + 256;
 }
 
 template <typename T, int D>
 static int op_scratch(const tvdk_geom_t* gg, void* ws, size_t ws_bytes, Scratch* sc, void* stream) {
   Geom g = make_geom(*gg);
-  Tune tune = {0, 0, 0};
+  Tune tune = merge_tune(0, 0, 0);
   const size_t cap = partial_capacity<T, D>(g, tune);
   if (!ws || ws_bytes < scratch_bytes(cap, g.nb))
     return fail(TVDK_ERR_WORKSPACE, "operator workspace of %zu bytes needed, %zu given", scratch_bytes(cap, g.nb), ws_bytes);
@@ -594,6 +609,14 @@ int64_t tvdk_launch_count(int reset) {
   const long long n = g_launches;
   if (reset) g_launches = 0;
   return n;
+}
+
+int tvdk_set_tune(int tile_x, int tile_y, int zchunk) {
+  if (tile_x < 0 || tile_y < 0 || zchunk < 0 || (tile_x % 8) != 0) return fail(TVDK_ERR_INVALID, "bad tune values");
+  g_tune.tile_x = tile_x;
+  g_tune.tile_y = tile_y;
+  g_tune.zchunk = zchunk;
+  return 0;
 }
 
 int tvdk_pitch(int dtype, int n_last) {
@@ -680,292 +703,272 @@ int tvdk_unpack(const tvdk_geom_t* gg, int dst_dtype, const void* src, void* dst
 }
 
 // ---- operators ---------------------------------------------------------------------------
-#define TVDK_OP_PROLOGUE(gg)                                  \
-  TVDK_TRY(check_geom(gg));                                   \
-  Scratch sc;                                                 \
-  const Geom g = make_geom(*gg);                              \
-  const Tune tune = {0, 0, 0};                                \
-  (void)tune;
+// Every operator: check, carve the scratch, build Args, dispatch (isotropic, heterogeneous) onto
+// the template instantiation, launch.
+namespace tvdk {
 
-#define TVDK_ISO_CALL(iso, KT, FILL, BIG)                                   \
-  if (iso) {                                                                \
-    typedef KT(true) K_;                                                    \
-    typename K_::Args a; memset(&a, 0, sizeof a); FILL;                     \
-    rc = run<K_, T, D>(a, g, tune, BIG, sc, stream);                        \
-  } else {                                                                  \
-    typedef KT(false) K_;                                                   \
-    typename K_::Args a; memset(&a, 0, sizeof a); FILL;                     \
-    rc = run<K_, T, D>(a, g, tune, BIG, sc, stream);                        \
+template <typename T, int D>
+struct OpCtx {
+  Geom g;
+  Tune tune;
+  Scratch sc;
+  int init(const tvdk_geom_t* gg, void* ws, size_t wsb, void* stream) {
+    g = make_geom(*gg);
+    tune = merge_tune(0, 0, 0);
+    return op_scratch<T, D>(gg, ws, wsb, &sc, stream);
   }
+};
 
 template <typename T, int D>
 static int rhs_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
                     const tvdk_coef_t* el, const void* f, const void* t, int64_t tcs, void* rhs, void* ws,
                     size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  int rc = 0;
-#define KT(I) KRhs<T, D, I, RHS_ONLY>
-  TVDK_ISO_CALL(iso, KT,
-                (a.k = make_coefs<T>(mu, om, el, D), a.f = (const T*)f, a.t = (const T*)t, a.tcs = tcs,
-                 a.rhs = (T*)rhs, a.fin = no_fin()),
-                false)
-#undef KT
-  return rc;
-}
-
-int tvdk_rhs(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
-             const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, void* rhs,
-             void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (rhs_impl<T, D>(g, isotropic, mu, omega, ell, f, t, t_comp_stride, rhs, workspace,
-                                         workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(mu, om, el, D);
+  return dispatch2(iso != 0, k.sc.hetero != 0, [&](auto I, auto H) {
+    typedef KRhs<T, D, decltype(I)::value, RHS_ONLY, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.f = (const T*)f; a.t = (const T*)t; a.tcs = tcs; a.rhs = (T*)rhs; a.fin = no_fin();
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int sweep_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* x_in,
                       const void* rhs, void* x_out, void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  typename KSweep<T, D>::Args a;
-  memset(&a, 0, sizeof a);
-  a.k = make_coefs<T>(nullptr, om, el, D);
-  a.x_in = (const T*)x_in; a.rhs = (const T*)rhs; a.x_out = (T*)x_out; a.fin = no_fin();
-  return run<KSweep<T, D>, T, D>(a, g, tune, false, sc, stream);
-}
-
-int tvdk_jacobi_sweep(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x_in,
-                      const void* rhs, void* x_out, void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (sweep_impl<T, D>(g, omega, ell, x_in, rhs, x_out, workspace, workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KSweep<T, D, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.x_in = (const T*)x_in; a.rhs = (const T*)rhs; a.x_out = (T*)x_out; a.fin = no_fin();
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int matvec_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* x, void* y,
                        void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  typename KCg<T, D, CG_MATVEC>::Args a;
-  memset(&a, 0, sizeof a);
-  a.k = make_coefs<T>(nullptr, om, el, D);
-  a.p_in = (const T*)x; a.p_out = (T*)y; a.fin = no_fin();
-  return run<KCg<T, D, CG_MATVEC>, T, D>(a, g, tune, false, sc, stream);
-}
-
-int tvdk_cg_matvec(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x, void* y,
-                   void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (matvec_impl<T, D>(g, omega, ell, x, y, workspace, workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KCg<T, D, CG_MATVEC, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = (const T*)x; a.p_out = (T*)y; a.fin = no_fin();
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int shrink_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* el,
                        const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t tcs,
                        double* sum_out, void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  int rc = 0;
-#define KT(I) KShrink<T, D, I>
-  TVDK_ISO_CALL(iso, KT,
-                (a.k = make_coefs<T>(mu, nullptr, el, D), a.unew[0] = (const T*)u_new, a.u_old = (const T*)u_old,
-                 a.u_out = nullptr, a.t_in = (const T*)t_in, a.t_out = (T*)t_out, a.tcs = tcs,
-                 a.fin = sum_fin(sum_out)),
-                false)
-#undef KT
-  return rc;
-}
-
-int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
-                const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t t_comp_stride,
-                double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, t_in, t_out, t_comp_stride,
-                                            sum_out, workspace, workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(mu, nullptr, el, D);
+  return dispatch2(iso != 0, k.sc.hetero != 0, [&](auto I, auto H) {
+    typedef KShrink<T, D, decltype(I)::value, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.unew[0] = (const T*)u_new; a.u_old = (const T*)u_old; a.u_out = nullptr;
+    a.t_in = (const T*)t_in; a.t_out = (T*)t_out; a.tcs = tcs; a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int expand_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* el, const void* t,
                        int64_t tcs, void* d, void* b, int64_t ocs, void* stream) {
-  TVDK_TRY(check_geom(gg));
   const Geom g = make_geom(*gg);
-  const Tune tune = {0, 0, 0};
+  const Tune tune = merge_tune(0, 0, 0);
   Scratch sc;
   memset(&sc, 0, sizeof sc);
   sc.partial_cap = (size_t)-1;
-  int rc = 0;
-#define KT(I) KExpand<T, D, I>
-  TVDK_ISO_CALL(iso, KT,
-                (a.k = make_coefs<T>(mu, nullptr, el, D), a.t = (const T*)t, a.tcs = tcs, a.d = (T*)d,
-                 a.b = (T*)b, a.ocs = ocs, a.fin = no_fin()),
-                false)
-#undef KT
-  return rc;
-}
-
-int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
-                      const void* t, int64_t t_comp_stride, void* d, void* b, int64_t db_comp_stride,
-                      void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (expand_impl<T, D>(g, isotropic, mu, ell, t, t_comp_stride, d, b, db_comp_stride, stream)));
-  return rc;
+  const Coefs<T> k = make_coefs<T>(mu, nullptr, el, D);
+  return dispatch2(iso != 0, false, [&](auto I, auto) {
+    typedef KExpand<T, D, decltype(I)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.t = (const T*)t; a.tcs = tcs; a.d = (T*)d; a.b = (T*)b; a.ocs = ocs; a.fin = no_fin();
+    return run<K, T, D>(a, g, tune, false, sc, stream);
+  });
 }
 
 template <typename T, int D, int MODE>
 static int dot_impl(const tvdk_geom_t* gg, const void* x, const void* y, double* out, void* ws, size_t wsb,
                     void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
   typename KDot<T, D, MODE>::Args a;
   memset(&a, 0, sizeof a);
   a.x = (const T*)x; a.y = (const T*)y; a.fin = sum_fin(out);
-  return run<KDot<T, D, MODE>, T, D>(a, g, tune, false, sc, stream);
-}
-
-int tvdk_dot(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
-             size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (dot_impl<T, D, 0>(g, x, y, out, workspace, workspace_bytes, stream)));
-  return rc;
-}
-
-int tvdk_norm_diff2(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
-                    size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (dot_impl<T, D, 1>(g, x, y, out, workspace, workspace_bytes, stream)));
-  return rc;
+  return run<KDot<T, D, MODE>, T, D>(a, o.g, o.tune, false, o.sc, stream);
 }
 
 template <typename T, int D>
 static int energy_impl(const tvdk_geom_t* gg, const tvdk_coef_t* mu, const tvdk_coef_t* om, const void* x,
                        const void* f, double* out, void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
   typename KEnergy<T, D>::Args a;
   memset(&a, 0, sizeof a);
   a.k = make_coefs<T>(mu, om, nullptr, D);
   a.x = (const T*)x; a.f = (const T*)f; a.fin = sum_fin(out);
-  return run<KEnergy<T, D>, T, D>(a, g, tune, false, sc, stream);
-}
-
-int tvdk_energy(const tvdk_geom_t* g, const tvdk_coef_t* mu, const tvdk_coef_t* omega, const void* x,
-                const void* f, double* out, void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (energy_impl<T, D>(g, mu, omega, x, f, out, workspace, workspace_bytes, stream)));
-  return rc;
+  return run<KEnergy<T, D>, T, D>(a, o.g, o.tune, false, o.sc, stream);
 }
 
 template <typename T, int D>
 static int fj1_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
                     const tvdk_coef_t* el, const void* f, const void* u_in, void* u_out, const void* t_in,
                     void* t_out, int64_t tcs, double* sum_out, void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  int rc = 0;
-#define KT(I) KFusedJ1<T, D, I>
-  TVDK_ISO_CALL(iso, KT,
-                (a.k = make_coefs<T>(mu, om, el, D), a.f = (const T*)f, a.u_in = (const T*)u_in,
-                 a.u_out = (T*)u_out, a.t_in = (const T*)t_in, a.t_out = (T*)t_out, a.tcs_in = tcs,
-                 a.tcs_out = tcs, a.fin = sum_fin(sum_out)),
-                true)
-#undef KT
-  return rc;
-}
-
-int tvdk_fused_jacobi1(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
-                       const tvdk_coef_t* ell, const void* f, const void* u_in, void* u_out, const void* t_in,
-                       void* t_out, int64_t t_comp_stride, double* sum_out, void* workspace,
-                       size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  if (u_in == u_out || t_in == t_out) return fail(TVDK_ERR_INVALID, "fused kernel is out-of-place");
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (fj1_impl<T, D>(g, isotropic, mu, omega, ell, f, u_in, u_out, t_in, t_out,
-                                         t_comp_stride, sum_out, workspace, workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(mu, om, el, D);
+  return dispatch2(iso != 0, k.sc.hetero != 0, [&](auto I, auto H) {
+    typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.f = (const T*)f; a.u_in = (const T*)u_in; a.u_out = (T*)u_out;
+    a.t_in = (const T*)t_in; a.t_out = (T*)t_out; a.tcs_in = tcs; a.tcs_out = tcs; a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, true, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int cginit_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
                        const tvdk_coef_t* el, const void* f, const void* t, int64_t tcs, const void* u, void* x,
                        void* r, double* sum_out, void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  int rc = 0;
-#define KT(I) KRhs<T, D, I, RHS_CGINIT>
-  TVDK_ISO_CALL(iso, KT,
-                (a.k = make_coefs<T>(mu, om, el, D), a.f = (const T*)f, a.t = (const T*)t, a.tcs = tcs,
-                 a.u = (const T*)u, a.x = (T*)x, a.r = (T*)r, a.fin = sum_fin(sum_out)),
-                false)
-#undef KT
-  return rc;
-}
-
-int tvdk_cg_init(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
-                 const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, const void* u, void* x,
-                 void* r, double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (cginit_impl<T, D>(g, isotropic, mu, omega, ell, f, t, t_comp_stride, u, x, r, sum_out,
-                                            workspace, workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(mu, om, el, D);
+  return dispatch2(iso != 0, k.sc.hetero != 0, [&](auto I, auto H) {
+    typedef KRhs<T, D, decltype(I)::value, RHS_CGINIT, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.f = (const T*)f; a.t = (const T*)t; a.tcs = tcs; a.u = (const T*)u; a.x = (T*)x; a.r = (T*)r;
+    a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int cgpq_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* p_in,
                      const void* r, void* p_out, const double* beta, int first, double* sum_out, void* ws,
                      size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  typename KCg<T, D, CG_PQ>::Args a;
-  memset(&a, 0, sizeof a);
-  a.k = make_coefs<T>(nullptr, om, el, D);
-  a.p_in = (const T*)p_in; a.r_in = (const T*)r; a.p_out = (T*)p_out;
-  a.coef.p = beta; a.coef.stride = 1; a.first_all = first; a.fin = sum_fin(sum_out);
-  return run<KCg<T, D, CG_PQ>, T, D>(a, g, tune, false, sc, stream);
-}
-
-int tvdk_cg_pq(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* p_in,
-               const void* r, void* p_out, const double* beta, int first, double* sum_out, void* workspace,
-               size_t workspace_bytes, void* stream) {
-  TVDK_TRY(check_geom(g));
-  if (p_in == p_out) return fail(TVDK_ERR_INVALID, "cg_pq is out-of-place in p");
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (cgpq_impl<T, D>(g, omega, ell, p_in, r, p_out, beta, first, sum_out, workspace,
-                                          workspace_bytes, stream)));
-  return rc;
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = (const T*)p_in; a.r_in = (const T*)r; a.p_out = (T*)p_out;
+    a.coef.p = beta; a.coef.stride = 1; a.first_all = first; a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
 }
 
 template <typename T, int D>
 static int cgupd_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* pp, void* x,
                       void* r, const double* alpha, double* sum_out, void* ws, size_t wsb, void* stream) {
-  TVDK_OP_PROLOGUE(gg)
-  TVDK_TRY((op_scratch<T, D>(gg, ws, wsb, &sc, stream)));
-  typename KCg<T, D, CG_UPDATE>::Args a;
-  memset(&a, 0, sizeof a);
-  a.k = make_coefs<T>(nullptr, om, el, D);
-  a.p_in = (const T*)pp; a.x = (T*)x; a.r = (T*)r;
-  a.coef.p = alpha; a.coef.stride = 1; a.fin = sum_fin(sum_out);
-  return run<KCg<T, D, CG_UPDATE>, T, D>(a, g, tune, false, sc, stream);
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KCg<T, D, CG_UPDATE, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = (const T*)pp; a.x = (T*)x; a.r = (T*)r;
+    a.coef.p = alpha; a.coef.stride = 1; a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
+}
+
+}  // namespace tvdk
+
+#define TVDK_C_ENTRY(g, CALL)        \
+  TVDK_TRY(check_geom(g));           \
+  int rc = 0;                        \
+  TVDK_DISPATCH(*g, rc = (CALL));    \
+  return rc;
+
+int tvdk_rhs(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+             const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, void* rhs,
+             void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (rhs_impl<T, D>(g, isotropic, mu, omega, ell, f, t, t_comp_stride, rhs, workspace,
+                                  workspace_bytes, stream)))
+}
+
+int tvdk_jacobi_sweep(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x_in,
+                      const void* rhs, void* x_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (sweep_impl<T, D>(g, omega, ell, x_in, rhs, x_out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_cg_matvec(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x, void* y,
+                   void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (matvec_impl<T, D>(g, omega, ell, x, y, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t t_comp_stride,
+                double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, t_in, t_out, t_comp_stride, sum_out,
+                                     workspace, workspace_bytes, stream)))
+}
+
+int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                      const void* t, int64_t t_comp_stride, void* d, void* b, int64_t db_comp_stride,
+                      void* stream) {
+  TVDK_C_ENTRY(g, (expand_impl<T, D>(g, isotropic, mu, ell, t, t_comp_stride, d, b, db_comp_stride, stream)))
+}
+
+int tvdk_dot(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
+             size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (dot_impl<T, D, 0>(g, x, y, out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_norm_diff2(const tvdk_geom_t* g, const void* x, const void* y, double* out, void* workspace,
+                    size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (dot_impl<T, D, 1>(g, x, y, out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_energy(const tvdk_geom_t* g, const tvdk_coef_t* mu, const tvdk_coef_t* omega, const void* x,
+                const void* f, double* out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (energy_impl<T, D>(g, mu, omega, x, f, out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_fused_jacobi1(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+                       const tvdk_coef_t* ell, const void* f, const void* u_in, void* u_out, const void* t_in,
+                       void* t_out, int64_t t_comp_stride, double* sum_out, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (u_in == u_out || t_in == t_out) return fail(TVDK_ERR_INVALID, "fused kernel is out-of-place");
+  TVDK_C_ENTRY(g, (fj1_impl<T, D>(g, isotropic, mu, omega, ell, f, u_in, u_out, t_in, t_out, t_comp_stride,
+                                  sum_out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_cg_init(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+                 const tvdk_coef_t* ell, const void* f, const void* t, int64_t t_comp_stride, const void* u, void* x,
+                 void* r, double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (cginit_impl<T, D>(g, isotropic, mu, omega, ell, f, t, t_comp_stride, u, x, r, sum_out,
+                                     workspace, workspace_bytes, stream)))
+}
+
+int tvdk_cg_pq(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* p_in,
+               const void* r, void* p_out, const double* beta, int first, double* sum_out, void* workspace,
+               size_t workspace_bytes, void* stream) {
+  if (p_in == p_out) return fail(TVDK_ERR_INVALID, "cg_pq is out-of-place in p");
+  TVDK_C_ENTRY(g, (cgpq_impl<T, D>(g, omega, ell, p_in, r, p_out, beta, first, sum_out, workspace,
+                                   workspace_bytes, stream)))
 }
 
 int tvdk_cg_update(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* p, void* x,
                    void* r, const double* alpha, double* sum_out, void* workspace, size_t workspace_bytes,
                    void* stream) {
-  TVDK_TRY(check_geom(g));
-  int rc = 0;
-  TVDK_DISPATCH(*g, rc = (cgupd_impl<T, D>(g, omega, ell, p, x, r, alpha, sum_out, workspace, workspace_bytes,
-                                           stream)));
-  return rc;
+  TVDK_C_ENTRY(g, (cgupd_impl<T, D>(g, omega, ell, p, x, r, alpha, sum_out, workspace, workspace_bytes, stream)))
 }
-

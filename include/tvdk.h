@@ -126,6 +126,9 @@ const char* tvdk_last_error(void);
 int tvdk_device_ok(void);
 /* Number of kernels this thread has launched through the library since the last reset. */
 int64_t tvdk_launch_count(int reset);
+/* Thread-local default launch shape used wherever a call passes 0 (tuning / tests):
+ * thread-block x, thread-block y (3-D), planes per CTA. */
+int tvdk_set_tune(int tile_x, int tile_y, int zchunk);
 
 /* Recommended pitch (elements) for a last-axis extent. */
 int tvdk_pitch(int dtype, int n_last);
