@@ -100,16 +100,52 @@ TVDK_DEV void vstore(T* p, const Vec<T>& x) {
   *reinterpret_cast<Vec<T>*>(p) = x;
 }
 
+#if defined(__CUDACC__)
+// Branch-free fp64 reciprocal / division / square root: hardware seed (MUFU.RCP64H / RSQ64H,
+// >= 20 good bits) + Newton steps in DFMA.  Operands on this path are positive and far from the
+// subnormal / overflow range (s + 1e-18, omega + 2*dim*ell, ell), so the IEEE routines' slow
+// paths -- a dozen extra instructions and two branches per call -- are dead weight here.
+// Results agree with correctly rounded sqrt / division to <= 1 ulp.
+TVDK_DEV double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+TVDK_DEV double tdiv(double a, double x) {
+  const double r = fast_rcp(x);
+  const double q = a * r;
+  return fma(fma(-x, q, a), r, q);
+}
+TVDK_DEV double tsqrt(double q) {  // q >= 0
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(q));
+  const double h = 0.5 * q;
+  y = y * fma(-h * y, y, 1.5);
+  y = y * fma(-h * y, y, 1.5);
+  double s = q * y;
+  s = fma(fma(-s, s, q), 0.5 * y, s);
+  return q > 0.0 ? s : 0.0;
+}
+TVDK_DEV float tdiv(float a, float x) { return __fdividef(a, x); }
+TVDK_DEV float tsqrt(float x) { return sqrtf(x); }
+TVDK_DEV double tcopysign(double m, double s) { return copysign(m, s); }
+TVDK_DEV float tcopysign(float m, float s) { return copysignf(m, s); }
+#else
+TVDK_DEV double tdiv(double a, double x) { return a / x; }
+TVDK_DEV float tdiv(float a, float x) { return a / x; }
 TVDK_DEV double tsqrt(double x) { return sqrt(x); }
 TVDK_DEV float tsqrt(float x) { return sqrtf(x); }
+TVDK_DEV double tcopysign(double m, double s) { return std::copysign(m, s); }
+TVDK_DEV float tcopysign(float m, float s) { return std::copysign(m, s); }
+#endif
 TVDK_DEV double tabs(double x) { return fabs(x); }
 TVDK_DEV float tabs(float x) { return fabsf(x); }
 TVDK_DEV double tmax(double a, double b) { return a > b ? a : b; }  // NaN-free inputs assumed
 TVDK_DEV float tmax(float a, float b) { return a > b ? a : b; }
-template <typename T>
-TVDK_DEV T tsign(T x) {
-  return (T)((x > (T)0) - (x < (T)0));
-}
 
 // ------------------------------------------------------------------------------------------
 // Geometry and coefficients (device-side mirrors of tvdk_geom_t / tvdk_coef_t)
@@ -427,7 +463,7 @@ TVDK_DEV void bw_from_t(const T (&t)[D], T kappa, T ell, T (&b)[D], T (&w)[D]) {
 #pragma unroll
     for (int a = 1; a < D; ++a) s = s + t[a] * t[a];
     s = tsqrt(s);
-    const T phi = tmax(s - kappa, (T)0) / (s + (T)1e-18);
+    const T phi = tdiv(tmax(s - kappa, (T)0), s + (T)1e-18);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       const T d = t[a] * phi;
@@ -437,7 +473,8 @@ TVDK_DEV void bw_from_t(const T (&t)[D], T kappa, T ell, T (&b)[D], T (&w)[D]) {
   } else {
 #pragma unroll
     for (int a = 0; a < D; ++a) {
-      const T d = tmax(tabs(t[a]) - kappa, (T)0) * tsign(t[a]);
+      // sign(t) * max(|t| - kappa, 0); kappa >= 0 (validated by the host) makes the t = 0 case 0
+      const T d = tcopysign(tmax(tabs(t[a]) - kappa, (T)0), t[a]);
       b[a] = t[a] - d;
       w[a] = ell * (b[a] - d);
     }
@@ -459,11 +496,11 @@ TVDK_DEV VoxCoef<T> voxcoef(const Scalars<T>& sc, T mu, T om, T el) {
     r.inv_diag = sc.inv_diag;
     r.c_nb = sc.c_nb;
   } else {
-    r.kappa = mu / el;
+    r.kappa = tdiv(mu, el);
     r.ell = el;
     r.omega = om;
     const T diag = om + el * (T)2 * sc.dim_t;  // omega + ell*2*dim/h**2, h = 1 (jacobi.py:72)
-    r.inv_diag = (T)1 / diag;
+    r.inv_diag = tdiv((T)1, diag);
     r.c_nb = el * r.inv_diag;  // N/(diag/ell) == N*ell/diag
   }
   return r;
@@ -569,10 +606,10 @@ struct RawT {
   Vec<T> t[D], d[D], mu, el;
 };
 // (RO = false: plain loads, for state that the same kernel updates in place)
-template <bool RO, bool HET, typename T, int D, typename C>
+template <bool RO, bool HET, bool XOK, typename T, int D, typename C>
 TVDK_DEV void load_rawt(RawT<T, D>& r, const C& c, const Coefs<T>& k, const T* t, long long tcs, const T* xb,
                         const T* xd, long long xcs, long long o) {
-  if (t) {
+  if (!XOK || t) {  // XOK: the explicit warm-start arrays may be selected at run time
 #pragma unroll
     for (int d = 0; d < D; ++d) r.t[d] = RO ? ldo(t + d * tcs, o) : ldw(t + d * tcs, o);
   } else {
@@ -648,9 +685,8 @@ struct KFusedJ1 {
   bool have_row;
   double red[NRED];
 
-  TVDK_DEV void prefetch(const Args& a, int z) {  // raw data needed to process plane z
-    const long long o = c.at(a.g, z);
-    load_rawt<true, HET>(nx, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o);
+  TVDK_DEV void prefetch(const Args& a, int z, long long o) {  // raw data needed to process plane z (offset o)
+    load_rawt<true, HET, false>(nx, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o);
     nx_f = ldo(a.f, o);
     nx_om = ldcoef<HET>(c, a.k.omega, o);
     if (c.has_zhi(a.g, z)) nx_u = ldo(a.u_in, o + c.s0b);
@@ -669,7 +705,7 @@ struct KFusedJ1 {
     if (c.has_zlo(a.g, j)) {
       u_lo = ldo(a.u_in, o - c.s0b);
       RawT<T, D> r;
-      load_rawt<true, HET>(r, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o - c.s0b);
+      load_rawt<true, HET, false>(r, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o - c.s0b);
       Vec<T> bb[D], ww[D];
       bw_plane<T, D, ISO, HET>(r, a.k.sc, false, bb, ww);
       w0_prev = ww[0];
@@ -678,7 +714,7 @@ struct KFusedJ1 {
 #pragma unroll
     for (int d = 0; d < D; ++d) b_prev[d] = vsplat<T>((T)0);
     have_row = false;
-    prefetch(a, j);
+    prefetch(a, j, o);
     return true;
   }
   TVDK_DEV bool more() const { return j <= c.z1; }
@@ -706,7 +742,7 @@ struct KFusedJ1 {
 #pragma unroll
     for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * D + d, rowe), c, wa_cur[d]);
     // next plane is needed if another compute step follows
-    if (j + 1 < c.z1 || (j + 1 == c.z1 && c.plane_ok(a.g, j + 1))) prefetch(a, j + 1);
+    if (j + 1 < c.z1 || (j + 1 == c.z1 && c.plane_ok(a.g, j + 1))) prefetch(a, j + 1, c.cur + c.s0b);
   }
 
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j) || c.zedge(a.g, j - 1); }
@@ -834,9 +870,8 @@ struct KRhs {
   Vec<T> nx_u, nx_f, nx_om;
   double red[NRED];
 
-  TVDK_DEV void prefetch(const Args& a, int z) {
-    const long long o = c.at(a.g, z);
-    load_rawt<true, HET>(nx, c, a.k, a.t, a.tcs, a.xb, a.xd, a.xcs, o);
+  TVDK_DEV void prefetch(const Args& a, int z, long long o) {
+    load_rawt<true, HET, true>(nx, c, a.k, a.t, a.tcs, a.xb, a.xd, a.xcs, o);
     nx_f = ldo(a.f, o);
     nx_om = ldcoef<HET>(c, a.k.omega, o);
     if (MODE != RHS_ONLY && c.has_zhi(a.g, z)) nx_u = ldo(a.u, o + c.s0b);
@@ -855,13 +890,13 @@ struct KRhs {
     u_lo = u_c;
     if (c.has_zlo(a.g, j)) {
       RawT<T, D> r;
-      load_rawt<true, HET>(r, c, a.k, a.t, a.tcs, a.xb, a.xd, a.xcs, o - c.s0b);
+      load_rawt<true, HET, true>(r, c, a.k, a.t, a.tcs, a.xb, a.xd, a.xcs, o - c.s0b);
       Vec<T> bb[D], ww[D];
       bw_plane<T, D, ISO, HET>(r, a.k.sc, a.t == nullptr, bb, ww);
       w0_prev = ww[0];
       if (MODE != RHS_ONLY) u_lo = ldo(a.u, o - c.s0b);
     }
-    prefetch(a, j);
+    prefetch(a, j, o);
     return true;
   }
   TVDK_DEV bool more() const { return j < c.z1; }
@@ -882,7 +917,7 @@ struct KRhs {
     }
 #pragma unroll
     for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * D + d, rowe), c, wa_cur[d]);
-    if (j + 1 < c.z1) prefetch(a, j + 1);
+    if (j + 1 < c.z1) prefetch(a, j + 1, c.cur + c.s0b);
   }
 
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
@@ -1211,7 +1246,7 @@ struct KShrink {
 
   TVDK_DEV void prefetch_own(const Args& a, long long o) {
     if (c.st) {
-      load_rawt<false, HET>(nx, c, a.k, a.t_in, a.tcs, a.xb, a.xb, a.xcs, o);
+      load_rawt<false, HET, true>(nx, c, a.k, a.t_in, a.tcs, a.xb, a.xb, a.xcs, o);
       nx_uo = ldw(a.u_old, o);
     }
   }
@@ -1420,7 +1455,7 @@ struct KExpand {
       long long o = c.cur;
       for (int z = c.z0; z < c.z1; ++z, o += c.s0b) {
         RawT<T, D> r;
-        load_rawt<true, HET>(r, c, a.k, a.t, a.tcs, (const T*)nullptr, (const T*)nullptr, 0, o);
+        load_rawt<true, HET, false>(r, c, a.k, a.t, a.tcs, (const T*)nullptr, (const T*)nullptr, 0, o);
         Vec<T> bb[D], ww[D];
         bw_plane<T, D, ISO, HET>(r, a.k.sc, false, bb, ww);
 #pragma unroll

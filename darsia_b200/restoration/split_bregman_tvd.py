@@ -98,6 +98,8 @@ def split_bregman_tvd(
     if ell is None:  # split_bregman_tvd.py:62-63
         ell = 2 * mu
     _check_positive("ell", ell)
+    if not np.all(np.asarray(mu) >= 0):
+        raise ValueError("mu (the TV weight) must be non-negative")
 
     if precision is None:
         cdtype = img.dtype

@@ -67,8 +67,8 @@ def main():
         for m in RAW:
             if m in idx:
                 print(f"  {m:85s} {r[idx[m]]} {units[idx[m]]}")
-        if li < len(blocks):
-            rd = list(csv.reader(io.StringIO("\n".join(blocks[li][1:]))))
+        if 2 * li < len(blocks):
+            rd = list(csv.reader(io.StringIO("\n".join(blocks[2 * li][1:]))))
             h = {k: i for i, k in enumerate(rd[0])}
             ins = rd[1:]
             ops = collections.Counter()
