@@ -180,7 +180,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     const long long want = std::max(1LL, (target + tiles - 1) / tiles);
     zc = (int)((nz + want - 1) / want);
     zc = std::max(zc, 8);
-    zc = std::min(zc, D == 2 ? 32 : 16);
+    zc = std::min(zc, 32);
   }
   zc = std::min(zc, nz);
   g.zchunk = zc;
