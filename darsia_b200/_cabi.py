@@ -127,7 +127,7 @@ SIGNATURES = {
     "tvdk_rhs": (C.c_int, [_PG, _I, _PC, _PC, _PC, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
     "tvdk_jacobi_sweep": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_matvec": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _SZ, _VP]),
-    "tvdk_shrink": (C.c_int, [_PG, _I, _PC, _PC, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
+    "tvdk_shrink": (C.c_int, [_PG, _I, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
     "tvdk_expand_state": (C.c_int, [_PG, _I, _PC, _PC, _VP, _I64, _VP, _VP, _I64, _VP]),
     "tvdk_dot": (C.c_int, [_PG, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_norm_diff2": (C.c_int, [_PG, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -57,8 +57,10 @@ static int check_geom(const tvdk_geom_t* g) {
   if (g->nb < 1 || g->nb > 65535) return fail(TVDK_ERR_INVALID, "nb = %d out of range [1, 65535]", g->nb);
   if (g->z_begin < 0 || g->z_end > g->n[0] || g->z_begin >= g->z_end)
     return fail(TVDK_ERR_INVALID, "bad owned plane range [%d, %d) of %d", g->z_begin, g->z_end, g->n[0]);
-  if (g->g0_off < 0 || g->g0_off + g->z_end > g->g0_n)
-    return fail(TVDK_ERR_INVALID, "slab [%d + %d) exceeds global extent %d", g->g0_off, g->z_end, g->g0_n);
+  // g0_off may be slightly negative: the (unused) lower ghost planes of the first slab
+  if (g->g0_off + g->z_begin < 0 || g->g0_off + g->z_end > g->g0_n)
+    return fail(TVDK_ERR_INVALID, "owned planes [%d, %d) + offset %d exceed the global extent %d", g->z_begin,
+                g->z_end, g->g0_off, g->g0_n);
   return 0;
 }
 
@@ -767,8 +769,8 @@ static int matvec_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_
 
 template <typename T, int D>
 static int shrink_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* el,
-                       const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t tcs,
-                       double* sum_out, void* ws, size_t wsb, void* stream) {
+                       const void* u_new, const void* u_old, void* u_out, const void* t_in, void* t_out,
+                       int64_t tcs, double* sum_out, void* ws, size_t wsb, void* stream) {
   OpCtx<T, D> o;
   TVDK_TRY(o.init(gg, ws, wsb, stream));
   const Coefs<T> k = make_coefs<T>(mu, nullptr, el, D);
@@ -776,7 +778,7 @@ static int shrink_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, co
     typedef KShrink<T, D, decltype(I)::value, decltype(H)::value> K;
     typename K::Args a;
     memset(&a, 0, sizeof a);
-    a.k = k; a.unew[0] = (const T*)u_new; a.u_old = (const T*)u_old; a.u_out = nullptr;
+    a.k = k; a.unew[0] = (const T*)u_new; a.u_old = (const T*)u_old; a.u_out = (T*)u_out;
     a.t_in = (const T*)t_in; a.t_out = (T*)t_out; a.tcs = tcs; a.fin = sum_fin(sum_out);
     return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
   });
@@ -916,10 +918,11 @@ int tvdk_cg_matvec(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_co
 }
 
 int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
-                const void* u_new, const void* u_old, const void* t_in, void* t_out, int64_t t_comp_stride,
-                double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
-  TVDK_C_ENTRY(g, (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, t_in, t_out, t_comp_stride, sum_out,
-                                     workspace, workspace_bytes, stream)))
+                const void* u_new, const void* u_old, void* u_out, const void* t_in, void* t_out,
+                int64_t t_comp_stride, double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (u_out && u_out == u_new) return fail(TVDK_ERR_INVALID, "u_out must not alias u_new (it may alias u_old)");
+  TVDK_C_ENTRY(g, (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, u_out, t_in, t_out, t_comp_stride,
+                                     sum_out, workspace, workspace_bytes, stream)))
 }
 
 int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,

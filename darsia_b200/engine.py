@@ -56,7 +56,11 @@ class Engine:
         dtype=np.float64,
         device=None,
         tile: Tuple[int, int, int] = (0, 0, 0),
+        slab: Optional[Tuple[int, int, int, int]] = None,
     ) -> None:
+        """``spatial_shape`` is the LOCAL extent.  ``slab = (g0_off, g0_n, z_begin, z_end)`` marks
+        the array as one slab of a volume cut along axis 0 (see ``tvdk_geom_t``); by default the
+        array is the whole volume."""
         self.lib = _cabi.get_library()
         self.device = resolve_device(device)
         self.spatial = tuple(int(n) for n in spatial_shape)
@@ -77,13 +81,17 @@ class Engine:
             g.n[a] = self.spatial[a] if a < self.dim else 1
         g.pitch = self.lib.pitch(self.code, self.spatial[-1])
         g.nb = self.nb
-        g.g0_off, g.g0_n, g.z_begin, g.z_end = 0, self.spatial[0], 0, self.spatial[0]
+        if slab is None:
+            slab = (0, self.spatial[0], 0, self.spatial[0])
+        g.g0_off, g.g0_n, g.z_begin, g.z_end = (int(v) for v in slab)
+        self.slab = tuple(int(v) for v in slab)
         self.geom = g
         self.field_elems = int(self.lib.field_elems(C.byref(g)))  # one problem
         if self.field_elems <= 0:
             raise ValueError(self.lib.last_error().decode())
         self.batch_elems = self.field_elems * self.nb  # one field over all problems
         self.nvox = int(np.prod(self.spatial))
+        self.plane_elems = self.field_elems // self.spatial[0]  # one plane of axis 0 (contiguous)
         self._op_ws: Optional[torch.Tensor] = None
 
     # ------------------------------------------------------------------ allocation / layout

@@ -60,8 +60,10 @@ typedef struct tvdk_geom {
   int32_t pitch;    /* elements per row of the last axis, multiple of 16 bytes */
   int32_t nb;       /* number of independent problems (channels / frames), >= 1 */
   /* Slab decomposition along axis 0 (multi-GPU, one volume): the local array holds planes
-   * [0, n[0]) of which [z_begin, z_end) are owned/computed; local plane 0 is global plane
-   * g0_off of g0_n.  Single GPU: g0_off = 0, g0_n = n[0], z_begin = 0, z_end = n[0]. */
+   * [0, n[0]) of which [z_begin, z_end) are owned/computed, the rest are ghost planes filled by
+   * the caller's halo exchange; local plane 0 is global plane g0_off of g0_n (g0_off may be
+   * negative for the unused lower ghosts of the first slab).
+   * Single GPU: g0_off = 0, g0_n = n[0], z_begin = 0, z_end = n[0]. */
   int32_t g0_off;
   int32_t g0_n;
   int32_t z_begin;
@@ -168,9 +170,11 @@ int tvdk_cg_matvec(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_co
                    const void* x, void* y, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Shrinkage + Bregman update on the compressed state: t_out = grad(u_new) + b(t_in)
- * (split_bregman_tvd.py:136-146); sum_out[b] (device, doubles) = ||u_new - u_old||^2. */
+ * (split_bregman_tvd.py:136-146); sum_out[b] (device, doubles) = ||u_new - u_old||^2; if u_out is
+ * not NULL the owned planes of u_new are copied into it (split_bregman_tvd.py:170; it may alias
+ * u_old, t_out may alias t_in). */
 int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
-                const void* u_new, const void* u_old, const void* t_in, void* t_out,
+                const void* u_new, const void* u_old, void* u_out, const void* t_in, void* t_out,
                 int64_t t_comp_stride, double* sum_out, void* workspace, size_t workspace_bytes,
                 void* stream);
 

@@ -84,7 +84,7 @@ def main():
                                        sums.data_ptr(), *ws(), s)),
         "cg_init": (4 + dim, lambda: lib.cg_init(bg, 1, bm, bo, be, f.data_ptr(), t.data_ptr(), eng.batch_elems,
                                                  u.data_ptr(), x.data_ptr(), r.data_ptr(), sums.data_ptr(), *ws(), s)),
-        "shrink": (2 + 2 * dim, lambda: lib.shrink(bg, 1, bm, be, u.data_ptr(), u2.data_ptr(), t.data_ptr(),
+        "shrink": (2 + 2 * dim, lambda: lib.shrink(bg, 1, bm, be, u.data_ptr(), u2.data_ptr(), None, t.data_ptr(),
                                                    t2.data_ptr(), eng.batch_elems, sums.data_ptr(), *ws(), s)),
         "sweep": (3, lambda: lib.jacobi_sweep(bg, bo, be, u.data_ptr(), f.data_ptr(), u2.data_ptr(), *ws(), s)),
         "matvec": (2, lambda: lib.cg_matvec(bg, bo, be, u.data_ptr(), u2.data_ptr(), *ws(), s)),
