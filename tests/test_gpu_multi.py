@@ -1,0 +1,75 @@
+"""GPU, >= 2 devices (NCCL): slab-decomposed solve == single-GPU solve; frame sharding.  Skipped on
+a one-GPU box (the same host logic runs under gloo in tests/test_distributed_cpu.py)."""
+
+import os
+import socket
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _worker(rank, world, port, case, outdir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    import torch
+    import torch.distributed as dist
+
+    import bench
+    import darsia_b200 as da
+
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        vol = bench.phantom_np(case["shape"], 4, np.dtype(case["dtype"]))
+        s, e = da.slab_range(vol.shape[0], rank, world)
+        solver = da.CG(maxiter=5, tol=0.0) if case["solver"] == "cg" else da.Jacobi(maxiter=1)
+        out, hist = da.split_bregman_tvd_slab(np.ascontiguousarray(vol[s:e]), vol.shape, mu=0.1, omega=1.0, ell=1.0,
+                                              dim=3, max_num_iter=case["nit"], isotropic=case["iso"], solver=solver,
+                                              return_info=True)
+        np.savez(os.path.join(outdir, f"r{rank}.npz"), out=out, hist=np.array(hist))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+@pytest.mark.parametrize("case", [
+    dict(shape=(96, 80, 120), dtype="float64", iso=False, solver="j1", nit=12),
+    dict(shape=(96, 80, 120), dtype="float64", iso=True, solver="cg", nit=6),
+    dict(shape=(96, 80, 120), dtype="float32", iso=False, solver="j1", nit=12),
+])
+def test_slab_nccl_equals_single_gpu(case):
+    import torch.multiprocessing as mp
+
+    import bench
+    import darsia_b200 as da
+    from conftest import rel_l2
+
+    world = min(_ngpu(), 4)
+    with tempfile.TemporaryDirectory() as d:
+        mp.spawn(_worker, args=(world, _free_port(), case, d), nprocs=world, join=True)
+        parts = [dict(np.load(os.path.join(d, f"r{r}.npz"))) for r in range(world)]
+    vol = bench.phantom_np(case["shape"], 4, np.dtype(case["dtype"]))
+    solver = da.CG(maxiter=5, tol=0.0) if case["solver"] == "cg" else da.Jacobi(maxiter=1)
+    ref = da.split_bregman_tvd(vol, mu=0.1, omega=1.0, ell=1.0, dim=3, max_num_iter=case["nit"],
+                               isotropic=case["iso"], solver=solver)
+    out = np.concatenate([p["out"] for p in parts], axis=0)
+    assert rel_l2(out, ref) <= (1e-12 if vol.dtype == np.float64 else 1e-5)
