@@ -177,7 +177,10 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     // Many more CTAs than resident slots (148 SMs x 4..8 CTAs): several waves, so the tail wave
     // is a small fraction, while a chunk stays long enough to amortise its 1-2 plane prologue.
     // Measured on B200 (profiles/r1_tune_2d_f64.txt): 32 planes per CTA is the sweet spot in 2-D.
-    const long long tiles = (long long)g.xtiles * g.ytiles * g.nb;
+    // (per problem, NOT times nb: the launch shape -- hence the summation order of every
+    // reduction -- must not depend on how many problems share a launch, so that a frame gives
+    // bitwise the same result alone, in a batch, or on another rank)
+    const long long tiles = (long long)g.xtiles * g.ytiles;
     const long long target = 148LL * 32;
     const long long want = std::max(1LL, (target + tiles - 1) / tiles);
     zc = (int)((nz + want - 1) / want);
