@@ -45,6 +45,13 @@ WORKLOADS = {
                               outer=100, hetero=True),
     "cfg5_3d_aniso_j1_f32": dict(shape=(512, 512, 512), nb=1, dtype="float32", iso=False,
                                  solver=("jacobi", 1, None), outer=50, hetero=False),
+    # one volume cut into slabs along axis 0 over the ranks (halo exchange + all-reduce): strong scaling
+    "cfg4_3d_slab_cg10": dict(shape=(1024, 1024, 1024), nb=1, dtype="float64", iso=True, solver=("cg", 10, 0.0),
+                              outer=20, hetero=False, slab=True),
+    "cfg5_3d_slab_j1_f32": dict(shape=(2048, 2048, 512), nb=1, dtype="float32", iso=False,
+                                solver=("jacobi", 1, None), outer=50, hetero=False, slab=True),
+    "cfg5_3d_slab_j1_f64": dict(shape=(2048, 2048, 512), nb=1, dtype="float64", iso=False,
+                                solver=("jacobi", 1, None), outer=50, hetero=False, slab=True),
     "small": dict(shape=(512, 768), nb=3, dtype="float64", iso=True, solver=("cg", 10, 0.0), outer=10, hetero=False),
 }
 DEFAULT_WORKLOAD = "cfg2_2d_iso_cg10"
@@ -426,6 +433,96 @@ def run_ours(args, w, wname):
     print(json.dumps(line))
 
 
+def run_slab(args, w, wname):
+    """One volume, slab-decomposed over the ranks (BASELINE configs 4/5): strong scaling."""
+    import torch
+    import torch.distributed as dist
+
+    import darsia_b200 as da
+    from darsia_b200.slab import SlabSolver
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    shape = tuple(w["shape"])
+    dim = len(shape)
+    kind, m, tol = w["solver"]
+    solver = da.CG(maxiter=m, tol=tol) if kind == "cg" else da.Jacobi(maxiter=m, tol=tol)
+    s, e = da.slab_range(shape[0], rank, world)
+    owned = phantom_np((e - s,) + shape[1:], 4 + rank, w["dtype"])
+    sol = SlabSolver(shape, dim, np.dtype(w["dtype"]), MU, OMEGA, ELL, w["iso"], solver, device=dev)
+    sol.setup(owned)
+    outer = w["outer"]
+    nvox = int(np.prod(shape))
+    for _ in range(args.warmup):
+        sol.reset()
+        sol.iterate(outer)
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    sol.eng.lib.launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        sol.reset()
+        sol.iterate(outer)
+    ev1.record()
+    barrier()
+    launches = int(sol.eng.lib.launch_count(1))
+    clocks = sampler.stop() if rank == 0 else None
+    tm = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms_per_step = float(tm.item()) / args.steps
+    value = nvox * outer / (ms_per_step * 1e-3) / 1e6
+    res = sol.result()
+    assert np.isfinite(res).all()
+    W = np.dtype(w["dtype"]).itemsize
+    words = algo_words_per_voxel_iter(dim, w["solver"], 0)
+    peak, peak_src = measured_peak()
+    gbs = words * W * nvox * outer / (ms_per_step * 1e-3) / 1e9
+    # e2e: host planes in, host planes out
+    t0 = time.perf_counter()
+    out = da.split_bregman_tvd_slab(owned, shape, mu=MU, omega=OMEGA, ell=ELL, dim=dim, max_num_iter=outer,
+                                    isotropic=w["iso"], solver=solver, device=dev)
+    torch.cuda.synchronize(dev)
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "tvd_mvoxel_iter_per_s", "value": value, "unit": "Mvoxel*iter/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if W == 8 else "f32", "data": "synthetic",
+        "config": {"workload": wname, "shape": list(shape), "isotropic": w["iso"], "solver": list(w["solver"]),
+                   "outer_iterations": outer, "sharding": "slabs along axis 0, halo exchange + all-reduce (NCCL)",
+                   "l2_policy": "inputs larger than L2"},
+        "roofline": {"bound": "hbm", "kernel": "whole step (all kernels + halo exchange)", "achieved": gbs / world,
+                     "peak": peak, "unit": "GB/s", "frac": gbs / world / peak, "traffic": None,
+                     "peak_source": peak_src, "algo_words_per_voxel_iter": words, "per_gpu": True},
+        "cpu_baseline": None,
+        "e2e": {"value": nvox * outer / float(te.item()) / 1e6, "unit": "Mvoxel*iter/s",
+                "h2d_bytes_per_step": int(owned.nbytes), "d2h_bytes_per_step": int(out.nbytes)},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -434,10 +531,15 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--shape", type=int, nargs="+", default=None, help="override the workload's spatial shape")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
+    if args.shape:
+        w = dict(w, shape=tuple(args.shape))
     if args.impl == "reference":
         run_reference_arm(args, w, args.workload)
+    elif w.get("slab"):
+        run_slab(args, w, args.workload)
     else:
         run_ours(args, w, args.workload)
 

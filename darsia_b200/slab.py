@@ -105,6 +105,164 @@ class SlabEngine(Engine):
         return t
 
 
+class SlabSolver:
+    """Device-resident state of one slab-decomposed ``split_bregman_tvd`` run.
+
+    ``setup`` uploads this rank's planes and exchanges the static halos; ``iterate(n)`` enqueues
+    ``n`` outer iterations (halo exchanges + kernels + all-reduces) without any host
+    synchronisation unless ``eps`` or a positive CG tolerance asks for one; ``result`` downloads
+    the owned planes.  ``bench.py`` times ``iterate``.
+    """
+
+    def __init__(self, global_shape, dim, dtype, mu, omega, ell, isotropic, solver, eps=None, group=None,
+                 device=None):
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if len(global_shape) != dim:
+            raise AssertionError("slab decomposition handles one volume (no batch axes)")
+        self.spec = _solver_spec(solver)
+        if self.spec.kind == _cabi.TVDK_SOLVER_JACOBI and self.spec.tol is not None:
+            raise NotImplementedError("Jacobi with tol is not implemented for slabs")
+        if ell is None:
+            ell = 2 * mu
+        _check_positive("ell", ell)
+        self.dim, self.iso, self.eps = dim, 1 if isotropic else 0, eps
+        self.cdtype = np.dtype(dtype)
+        self.eng = eng = SlabEngine(global_shape, rank, world, dtype=self.cdtype, device=device, group=group)
+        self._coefs = [self._coef(v, n) for v, n in ((mu, "mu"), (omega, "omega"), (ell, "ell"))]
+        self.fused = self.spec.kind == _cabi.TVDK_SOLVER_JACOBI and self.spec.maxiter == 1
+        self.cur = 0
+        self.incs: List[torch.Tensor] = []
+        self.done = False
+        self.iters = 0
+
+    def _coef(self, value, name):
+        eng = self.eng
+        if np.ndim(value) == 0:
+            return eng.coef(float(value), name=name)
+        fld = eng.upload_owned(np.asarray(value, dtype=self.cdtype))
+        eng.exchange([(fld, 0, GL, GH)])
+        return eng.coef(fld, name=name)
+
+    def setup(self, img_owned: np.ndarray) -> None:
+        eng, D = self.eng, self.dim
+        lib, g = eng.lib, eng.geom
+        self.f = eng.upload_owned(np.asarray(img_owned, dtype=self.cdtype))
+        eng.exchange([(self.f, 0, GL, GH)])
+        self.u = self.f.clone()
+        self.t = eng.zero_fields(D)
+        ws = eng.op_workspace()
+        self.sums = torch.zeros(2, dtype=torch.float64, device=eng.device)
+        with device_guard(eng.device):  # ||img|| over all ranks (split_bregman_tvd.py:58)
+            lib.check(lib.dot(C.byref(g), self.f.data_ptr(), self.f.data_ptr(), self.sums.data_ptr(), ws.data_ptr(),
+                              ws.numel(), eng.stream()), "tvdk_dot")
+        self.nrm2 = eng.allreduce(self.sums[:1].clone())
+        if self.fused:
+            self.bufs = [(self.u, self.t), (eng.empty_fields(1), eng.zero_fields(D))]
+        elif self.spec.kind == _cabi.TVDK_SOLVER_JACOBI:
+            self.rhs, self.xa, self.xb = eng.empty_fields(1), eng.zero_fields(1), eng.zero_fields(1)
+        else:
+            self.x, self.r = eng.zero_fields(1), eng.zero_fields(1)
+            self.p = [eng.zero_fields(1), eng.zero_fields(1)]
+            self.rho, self.rho_prev, self.pq, self.alpha, self.beta = (
+                torch.zeros(1, dtype=torch.float64, device=eng.device) for _ in range(5))
+
+    def iterate(self, n: int) -> int:
+        """Enqueue up to ``n`` outer iterations; returns how many were run (eps may stop early)."""
+        eng, spec, D, iso = self.eng, self.spec, self.dim, self.iso
+        lib, g = eng.lib, eng.geom
+        (mu_c, _), (om_c, _), (el_c, _) = self._coefs
+        bm, bo, be, bg = C.byref(mu_c), C.byref(om_c), C.byref(el_c), C.byref(g)
+        ws = eng.op_workspace()
+        wsp, wsn = ws.data_ptr(), ws.numel()
+        sums, tcs = self.sums, eng.batch_elems
+        call = lib.check
+        ran = 0
+        while ran < n and not self.done:
+            with device_guard(eng.device):
+                s_ = eng.stream()
+                if self.fused:
+                    (ui, ti), (uo, to) = self.bufs[self.cur], self.bufs[1 - self.cur]
+                    eng.exchange([(ui, 0, 1, 2)] + [(ti, d, 1, 1) for d in range(D)])
+                    call(lib.fused_jacobi1(bg, iso, bm, bo, be, self.f.data_ptr(), ui.data_ptr(), uo.data_ptr(),
+                                           ti.data_ptr(), to.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, s_),
+                         "tvdk_fused_jacobi1")
+                    self.cur = 1 - self.cur
+                elif spec.kind == _cabi.TVDK_SOLVER_JACOBI:
+                    u, t = self.u, self.t
+                    eng.exchange([(t, d, 1, 1) for d in range(D)])
+                    call(lib.rhs(bg, iso, bm, bo, be, self.f.data_ptr(), t.data_ptr(), tcs, self.rhs.data_ptr(), wsp, wsn,
+                                 s_), "tvdk_rhs")
+                    xin = u
+                    for k in range(spec.maxiter):
+                        xout = self.xa if k % 2 == 0 else self.xb
+                        eng.exchange([(xin, 0, 1, 1)])
+                        call(lib.jacobi_sweep(bg, bo, be, xin.data_ptr(), self.rhs.data_ptr(), xout.data_ptr(), wsp, wsn,
+                                              s_), "tvdk_jacobi_sweep")
+                        xin = xout
+                    eng.exchange([(xin, 0, 0, 1)])
+                    call(lib.shrink(bg, iso, bm, be, xin.data_ptr(), u.data_ptr(), u.data_ptr(), t.data_ptr(),
+                                    t.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_shrink")
+                else:
+                    u, t, x, r, p = self.u, self.t, self.x, self.r, self.p
+                    rho, rho_prev, pq, alpha, beta = self.rho, self.rho_prev, self.pq, self.alpha, self.beta
+                    eng.exchange([(u, 0, 1, 1)] + [(t, d, 1, 1) for d in range(D)])
+                    call(lib.cg_init(bg, iso, bm, bo, be, self.f.data_ptr(), t.data_ptr(), tcs, u.data_ptr(), x.data_ptr(),
+                                     r.data_ptr(), sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_init")
+                    eng.allreduce(sums)
+                    bnrm = torch.sqrt(sums[0:1])
+                    atol = float(spec.tol) * bnrm
+                    rho.copy_(sums[1:2])
+                    stop = False
+                    if spec.tol > 0.0 or self.iters == 0:  # host check only when a tolerance can fire
+                        stop = bool((bnrm == 0).item()) or bool((torch.sqrt(rho) < atol).item())
+                    for i in range(spec.maxiter):
+                        if stop:
+                            break
+                        eng.exchange([(r, 0, 1, 1)])
+                        if i > 0:
+                            torch.div(rho, rho_prev, out=beta)
+                        call(lib.cg_pq(bg, bo, be, p[(i & 1) ^ 1].data_ptr(), r.data_ptr(), p[i & 1].data_ptr(),
+                                       beta.data_ptr(), 1 if i == 0 else 0, sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_pq")
+                        pq.copy_(eng.allreduce(sums[0:1]))
+                        torch.div(rho, pq, out=alpha)
+                        eng.exchange([(p[i & 1], 0, 1, 1)])
+                        call(lib.cg_update(bg, bo, be, p[i & 1].data_ptr(), x.data_ptr(), r.data_ptr(), alpha.data_ptr(),
+                                           sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_update")
+                        rho_prev.copy_(rho)
+                        rho.copy_(eng.allreduce(sums[0:1]))
+                        if spec.tol > 0.0:
+                            stop = bool((torch.sqrt(rho) < atol).item())
+                    eng.exchange([(x, 0, 0, 1)])
+                    call(lib.shrink(bg, iso, bm, be, x.data_ptr(), u.data_ptr(), u.data_ptr(), t.data_ptr(), t.data_ptr(),
+                                    tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_shrink")
+            inc2 = eng.allreduce(sums[0:1].clone())
+            self.incs.append(torch.sqrt(inc2 / self.nrm2))
+            ran += 1
+            self.iters += 1
+            if self.eps is not None:  # split_bregman_tvd.py:173-175 (one host sync per iteration, only with eps)
+                if float(self.incs[-1].item()) < self.eps:
+                    self.done = True
+        return ran
+
+    def reset(self) -> None:
+        """Back to the initial state (u = img, t = 0) without re-uploading."""
+        if self.fused:
+            self.cur = 0
+        self.u.copy_(self.f)
+        self.t.zero_()
+        self.incs, self.done, self.iters = [], False, 0
+
+    def result_field(self) -> torch.Tensor:
+        return self.bufs[self.cur][0] if self.fused else self.u
+
+    def result(self, out_dtype=None) -> np.ndarray:
+        return self.eng.download_owned(self.result_field(), out_dtype)
+
+    def history(self) -> List[float]:
+        return [float(v.item()) for v in self.incs]
+
+
 def split_bregman_tvd_slab(
     img_owned: np.ndarray,
     global_shape: Sequence[int],
@@ -126,134 +284,16 @@ def split_bregman_tvd_slab(
     Args:
         img_owned: this rank's planes ``[s, e) = slab_range(global_shape[0], rank, world)`` of the image.
         global_shape: shape of the whole volume.
-        mu, omega, ell: scalars (per-voxel maps: pass this rank's owned planes).
+        mu, omega, ell: scalars, or per-voxel maps given as this rank's owned planes.
         Other arguments as ``split_bregman_tvd``; ``solver`` is ``Jacobi(maxiter=K)`` (no tol) or
         ``CG(maxiter=m, tol=...)``.
-    Returns this rank's owned planes of the result (and the list of relative increments).
+    Returns this rank's owned planes of the result (and, with ``return_info``, the relative increments).
     """
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    if len(global_shape) != dim:
-        raise AssertionError("slab decomposition handles one volume (no batch axes)")
     if not isinstance(img_owned, np.ndarray) or img_owned.dtype not in (np.float32, np.float64):
         raise TypeError("float32/float64 ndarray expected")
-    spec = _solver_spec(solver)
-    if spec.kind == _cabi.TVDK_SOLVER_JACOBI and spec.tol is not None:
-        raise NotImplementedError("Jacobi with tol is not implemented for slabs")
-    if ell is None:
-        ell = 2 * mu
-    _check_positive("ell", ell)
     cdtype = img_owned.dtype if precision is None else np.dtype({"fp64": np.float64, "fp32": np.float32}[precision])
-    eng = SlabEngine(global_shape, rank, world, dtype=cdtype, device=device, group=group)
-    lib, g = eng.lib, eng.geom
-    iso = 1 if isotropic else 0
-    D = dim
-
-    def coef(value, name):
-        if np.ndim(value) == 0:
-            return eng.coef(float(value), name=name)
-        fld = eng.upload_owned(np.asarray(value, dtype=cdtype))
-        eng.exchange([(fld, 0, GL, GH)])
-        return eng.coef(fld, name=name)
-
-    (mu_c, k1), (om_c, k2), (el_c, k3) = coef(mu, "mu"), coef(omega, "omega"), coef(ell, "ell")
-    bm, bo, be, bg = C.byref(mu_c), C.byref(om_c), C.byref(el_c), C.byref(g)
-    f = eng.upload_owned(img_owned)
-    eng.exchange([(f, 0, GL, GH)])
-    u = f.clone()
-    t = eng.zero_fields(D)
-    ws = eng.op_workspace()
-    wsp, wsn = ws.data_ptr(), ws.numel()
-    sums = torch.zeros(2, dtype=torch.float64, device=eng.device)
-    tcs = eng.batch_elems
-
-    def call(rc, what):
-        lib.check(rc, what)
-
-    # ||img|| over all ranks (split_bregman_tvd.py:58)
-    with device_guard(eng.device):
-        call(lib.dot(bg, f.data_ptr(), f.data_ptr(), sums.data_ptr(), wsp, wsn, eng.stream()), "tvdk_dot")
-    nrm2 = eng.allreduce(sums[:1].clone())
-    incs: List[torch.Tensor] = []
-    hist: List[float] = []
-    tviews = [(t, d, 1, 1) for d in range(D)]
-
-    if spec.kind == _cabi.TVDK_SOLVER_JACOBI and spec.maxiter == 1:
-        u2, t2 = eng.empty_fields(1), eng.zero_fields(D)
-        bufs = [(u, t), (u2, t2)]
-    elif spec.kind == _cabi.TVDK_SOLVER_JACOBI:
-        rhs, xa, xb = eng.empty_fields(1), eng.zero_fields(1), eng.zero_fields(1)
-    else:
-        x, r = eng.zero_fields(1), eng.zero_fields(1)
-        p = [eng.zero_fields(1), eng.zero_fields(1)]
-        rho, rho_prev, pq, alpha, beta = (torch.zeros(1, dtype=torch.float64, device=eng.device) for _ in range(5))
-
-    cur = 0
-    done = False
-    it = 0
-    while it < max_num_iter and not done:
-        with device_guard(eng.device):
-            s_ = eng.stream()
-            if spec.kind == _cabi.TVDK_SOLVER_JACOBI and spec.maxiter == 1:
-                (ui, ti), (uo, to) = bufs[cur], bufs[1 - cur]
-                eng.exchange([(ui, 0, 1, 2)] + [(ti, d, 1, 1) for d in range(D)])
-                call(lib.fused_jacobi1(bg, iso, bm, bo, be, f.data_ptr(), ui.data_ptr(), uo.data_ptr(), ti.data_ptr(),
-                                       to.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_fused_jacobi1")
-                cur = 1 - cur
-            elif spec.kind == _cabi.TVDK_SOLVER_JACOBI:
-                eng.exchange(tviews)
-                call(lib.rhs(bg, iso, bm, bo, be, f.data_ptr(), t.data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, s_), "tvdk_rhs")
-                xin = u
-                for k in range(spec.maxiter):
-                    xout = xa if k % 2 == 0 else xb
-                    eng.exchange([(xin, 0, 1, 1)])
-                    call(lib.jacobi_sweep(bg, bo, be, xin.data_ptr(), rhs.data_ptr(), xout.data_ptr(), wsp, wsn, s_),
-                         "tvdk_jacobi_sweep")
-                    xin = xout
-                eng.exchange([(xin, 0, 0, 1)])
-                call(lib.shrink(bg, iso, bm, be, xin.data_ptr(), u.data_ptr(), u.data_ptr(), t.data_ptr(), t.data_ptr(),
-                                tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_shrink")
-            else:
-                eng.exchange([(u, 0, 1, 1)] + tviews)
-                call(lib.cg_init(bg, iso, bm, bo, be, f.data_ptr(), t.data_ptr(), tcs, u.data_ptr(), x.data_ptr(),
-                                 r.data_ptr(), sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_init")
-                eng.allreduce(sums)
-                bnrm = torch.sqrt(sums[0:1])
-                atol = float(spec.tol) * bnrm
-                rho.copy_(sums[1:2])
-                stop = False
-                if spec.tol > 0.0 or it == 0:  # host check only when a tolerance can fire (or once: zero rhs)
-                    stop = bool((bnrm == 0).item()) or bool((torch.sqrt(rho) < atol).item())
-                for i in range(spec.maxiter):
-                    if stop:
-                        break
-                    eng.exchange([(r, 0, 1, 1)])
-                    if i > 0:
-                        torch.div(rho, rho_prev, out=beta)
-                    call(lib.cg_pq(bg, bo, be, p[(i & 1) ^ 1].data_ptr(), r.data_ptr(), p[i & 1].data_ptr(),
-                                   beta.data_ptr(), 1 if i == 0 else 0, sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_pq")
-                    pq.copy_(eng.allreduce(sums[0:1]))
-                    torch.div(rho, pq, out=alpha)
-                    eng.exchange([(p[i & 1], 0, 1, 1)])
-                    call(lib.cg_update(bg, bo, be, p[i & 1].data_ptr(), x.data_ptr(), r.data_ptr(), alpha.data_ptr(),
-                                       sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_update")
-                    rho_prev.copy_(rho)
-                    rho.copy_(eng.allreduce(sums[0:1]))
-                    if spec.tol > 0.0:
-                        stop = bool((torch.sqrt(rho) < atol).item())
-                eng.exchange([(x, 0, 0, 1)])
-                call(lib.shrink(bg, iso, bm, be, x.data_ptr(), u.data_ptr(), u.data_ptr(), t.data_ptr(), t.data_ptr(),
-                                tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_shrink")
-        inc2 = eng.allreduce(sums[0:1].clone())
-        incs.append(torch.sqrt(inc2 / nrm2))
-        it += 1
-        if eps is not None:  # split_bregman_tvd.py:173-175 (one host sync per iteration, only with eps)
-            v = float(incs[-1].item())
-            if v < eps:
-                done = True
-    res_field = bufs[cur][0] if (spec.kind == _cabi.TVDK_SOLVER_JACOBI and spec.maxiter == 1) else u
-    out = eng.download_owned(res_field, img_owned.dtype)
-    if return_info:
-        hist = [float(v.item()) for v in incs]
-        return out, hist
-    return out
+    sol = SlabSolver(global_shape, dim, cdtype, mu, omega, ell, isotropic, solver, eps=eps, group=group, device=device)
+    sol.setup(img_owned)
+    sol.iterate(max_num_iter)
+    out = sol.result(img_owned.dtype)
+    return (out, sol.history()) if return_info else out
