@@ -10,6 +10,7 @@ from .image import Image, is_image_like  # noqa: F401
 from .utils.linear_solvers import CG, Jacobi, Solver  # noqa: F401
 from .restoration.split_bregman_tvd import split_bregman_tvd  # noqa: F401
 from .restoration.tvd import TVD, tvd  # noqa: F401
+from .restoration.h1_regularization import H1_regularization  # noqa: F401
 from .engine import Engine, SolveInfo, SolverSpec  # noqa: F401
 from .series import frame_range, tvd_series  # noqa: F401
 from .slab import slab_range, split_bregman_tvd_slab  # noqa: F401

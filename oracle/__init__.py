@@ -16,6 +16,7 @@ fixtures under ``tests/golden/*.npz``.
 
 from .tvd_oracle import (  # noqa: F401
     CG,
+    H1_regularization,
     Jacobi,
     Solver,
     backward_diff,

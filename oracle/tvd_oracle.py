@@ -459,3 +459,25 @@ def tvd(img, method: str = "chambolle", weight: Coeff = 1.0, max_num_iter: int =
         eps: float = 2e-4, **kwargs):
     """Restatement of ``darsia.tvd`` (tvd.py:132-163)."""
     return TVD(method=method, weight=weight, max_num_iter=max_num_iter, eps=eps, **kwargs)(img)
+
+
+# --------------------------------------------------------------------------- #
+# H1 regularisation (restoration/h1_regularization.py:15-146) -- SURVEY 8f "next"
+# --------------------------------------------------------------------------- #
+def H1_regularization(img: np.ndarray, mu: float, omega: float = 1.0, dim: int = 2,
+                      solver: Optional[Solver] = None) -> np.ndarray:
+    """One inner solve ``omega u - mu laplace(u) = omega img`` from ``img``; channels separately
+    (h1_regularization.py:46-70)."""
+    if solver is None:
+        solver = Jacobi()
+    solver.update_params(mass_coeff=omega, diffusion_coeff=mu, dim=dim)
+    if img.ndim == dim:
+        solver.reset()
+        return solver(x0=img, rhs=omega * img)
+    out = np.empty_like(img)
+    for idx in np.ndindex(img.shape[dim:]):
+        sel = (slice(None),) * dim + idx
+        chan = np.ascontiguousarray(img[sel])
+        solver.reset()
+        out[sel] = solver(x0=chan, rhs=omega * chan)
+    return out

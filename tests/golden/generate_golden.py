@@ -85,6 +85,7 @@ def load_reference():
         "utils/linear_solvers/cg.py",
         "restoration/tvd.py",
         "restoration/split_bregman_tvd.py",
+        "restoration/h1_regularization.py",
     ]
     for rel in order:
         name = "darsia._ref_" + rel.replace("/", "_")[:-3]
@@ -255,6 +256,22 @@ def operator_cases(da):
     return store
 
 
+def h1_cases(da):
+    """H1 regularisation (restoration/h1_regularization.py) -- SURVEY 8f "next" row 1."""
+    store = {}
+    vol = phantom((11, 14, 9), 51)
+    store["vol"] = vol
+    store["vol_jac_tol"] = da.H1_regularization(vol.copy(), mu=1, omega=1, dim=3,
+                                                solver=da.Jacobi(maxiter=30, tol=1e-6))  # examples/regularization.py:33-40
+    store["vol_cg"] = da.H1_regularization(vol.copy(), mu=0.5, omega=2.0, dim=3, solver=da.CG(maxiter=8, tol=0.0))
+    rgb = phantom((23, 31, 3), 52)
+    store["rgb"] = rgb
+    store["rgb_jac5"] = da.H1_regularization(rgb.copy(), mu=0.7, omega=1.0, dim=2, solver=da.Jacobi(maxiter=5))
+    store["rgb_jac_tol"] = da.H1_regularization(rgb.copy(), mu=0.7, omega=1.0, dim=2,
+                                                solver=da.Jacobi(maxiter=40, tol=1e-3))
+    return store
+
+
 def main():
     da = load_reference()
     for c in CASES:
@@ -263,6 +280,8 @@ def main():
         print(f"{c['name']:28s} shape={c['shape']} out_norm={np.linalg.norm(store['out']):.12g}")
     np.savez_compressed(os.path.join(OUT, "operators.npz"), **operator_cases(da))
     print("operators.npz written")
+    np.savez_compressed(os.path.join(OUT, "h1.npz"), **h1_cases(da))
+    print("h1.npz written")
 
 
 if __name__ == "__main__":

@@ -1,0 +1,24 @@
+"""H1 regularisation golden cases (reference outputs in tests/golden/h1.npz)."""
+import os
+
+import numpy as np
+
+from conftest import GOLDEN_DIR
+
+CASES = {
+    "vol_jac_tol": ("vol", dict(mu=1, omega=1, dim=3), ("jacobi", dict(maxiter=30, tol=1e-6))),
+    "vol_cg": ("vol", dict(mu=0.5, omega=2.0, dim=3), ("cg", dict(maxiter=8, tol=0.0))),
+    "rgb_jac5": ("rgb", dict(mu=0.7, omega=1.0, dim=2), ("jacobi", dict(maxiter=5))),
+    "rgb_jac_tol": ("rgb", dict(mu=0.7, omega=1.0, dim=2), ("jacobi", dict(maxiter=40, tol=1e-3))),
+}
+
+
+def load():
+    with np.load(os.path.join(GOLDEN_DIR, "h1.npz")) as z:
+        return {k: z[k] for k in z.files}
+
+
+def run(api, data, name):
+    src, kw, (kind, skw) = CASES[name]
+    solver = {"jacobi": api.Jacobi, "cg": api.CG}[kind](**skw)
+    return api.H1_regularization(data[src].copy(), solver=solver, **kw), data[name]

@@ -60,3 +60,11 @@ def test_eps_stops_each_problem_at_the_reference_iteration():
     assert rel_l2(out, ref) <= 1e-12
     for b, h in enumerate(hist):
         np.testing.assert_allclose(info.history[: len(h), b], h, rtol=1e-9)
+
+
+@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol"])
+def test_h1_regularization_golden(name):
+    import h1_cases
+
+    out, ref = h1_cases.run(da, h1_cases.load(), name)
+    assert out.shape == ref.shape and rel_l2(out, ref) <= 1e-12

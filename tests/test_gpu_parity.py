@@ -130,3 +130,11 @@ def test_standalone_solvers(da):
         s_ref = mk(oracle)
         s_ref.reset()
         assert rel_l2(mk(da)(x0=x0, rhs=rhs), s_ref(x0=x0, rhs=rhs)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol"])
+def test_h1_regularization_golden(da, name):
+    import h1_cases
+
+    out, ref = h1_cases.run(da, h1_cases.load(), name)
+    assert out.shape == ref.shape and rel_l2(out, ref) <= 1e-12

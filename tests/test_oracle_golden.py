@@ -80,3 +80,11 @@ def test_oracle_properties():
         np.testing.assert_array_equal(out[..., c], one)
     with pytest.raises(TypeError):
         oracle.split_bregman_tvd((img * 255).astype(np.uint8))
+
+
+@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol"])
+def test_oracle_h1_regularization(name):
+    import h1_cases
+
+    out, ref = h1_cases.run(oracle, h1_cases.load(), name)
+    assert rel_l2(out, ref) <= 1e-13
