@@ -424,14 +424,24 @@ def run_ours(args, w, wname):
     kw = dict(method="heterogeneous bregman", weight=(mu_host if w["hetero"] else MU),
               omega=(om_host if w["hetero"] else OMEGA), regularization=ELL, dim=dim, isotropic=w["iso"],
               max_num_iter=outer, eps=None, solver=solver_obj)
-    e2e_steps = max(1, min(args.steps, 2))
-    out = da.tvd(pinned_np, **kw)  # warm-up (allocator, pinned staging)
+    e2e_steps = max(1, min(args.steps, 3))
+    # steady state of a caller that processes image after image: two warm-up calls fill torch's
+    # device and pinned-host allocator caches (a fresh 672 MB cudaHostAlloc alone costs ~0.2 s)
+    for _ in range(2):
+        out = da.tvd(pinned_np, **kw)
+        del out
     barrier()
+    os.environ["DARSIA_B200_TIMING"] = "1"
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         out = da.tvd(pinned_np, **kw)
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
+    os.environ.pop("DARSIA_B200_TIMING", None)
+    import importlib
+
+    _sbt = importlib.import_module("darsia_b200.restoration.split_bregman_tvd")
+    e2e_breakdown = {k: round(v, 4) for k, v in _sbt.LAST_TIMINGS.items()}
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -468,7 +478,8 @@ def run_ours(args, w, wname):
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "Mvoxel*iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                "s_per_step": float(te.item()), "matches_device_timed_result": same},
+                "s_per_step": float(te.item()), "matches_device_timed_result": same,
+                "breakdown_s": e2e_breakdown},
         "gpu_launches": launches,
         "clocks": clocks,
     }

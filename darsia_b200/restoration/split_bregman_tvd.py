@@ -12,6 +12,8 @@ Policy on the reference's quirks:
 
 from __future__ import annotations
 
+import os
+import time
 from typing import Optional, Union
 
 import numpy as np
@@ -21,6 +23,9 @@ from ..engine import Engine, SolveInfo, SolverSpec
 from ..utils.linear_solvers import CG, Jacobi, Solver
 
 Coeff = Union[float, int, np.ndarray]
+
+# wall-clock breakdown of the last call when DARSIA_B200_TIMING=1 (upload / solve / download), seconds
+LAST_TIMINGS: dict = {}
 
 
 def _solver_spec(solver: Optional[Solver]) -> SolverSpec:
@@ -114,6 +119,8 @@ def split_bregman_tvd(
     nb = int(np.prod(img.shape[dim:], dtype=np.int64))
     if img.size == 0:
         return (img.copy(), None) if return_info else img.copy()
+    timing = os.environ.get("DARSIA_B200_TIMING") == "1"
+    t_start = time.perf_counter()
     eng = Engine(spatial, nb=nb, dtype=cdtype, device=device, tile=tile)
 
     f = eng.upload(img)
@@ -135,6 +142,9 @@ def split_bregman_tvd(
         u = f.clone()
     t = eng.zero_fields(dim)
 
+    if timing:
+        _sync(eng)
+        t_up = time.perf_counter()
     if isinstance(verbose, bool):
         verbose_every = 1 if verbose else 0
     else:
@@ -147,8 +157,20 @@ def split_bregman_tvd(
     )
     if verbose_every:
         _print_verbose(info, verbose_every)
+    if timing:
+        t_solve = time.perf_counter()
     out = eng.download(u, img.dtype, img.shape)  # convert_dtype, split_bregman_tvd.py:177
+    if timing:
+        LAST_TIMINGS.clear()
+        LAST_TIMINGS.update(upload=t_up - t_start, solve=t_solve - t_up, download=time.perf_counter() - t_solve)
     return (out, info) if return_info else out
+
+
+def _sync(eng: Engine) -> None:
+    if eng.device.type == "cuda":
+        import torch
+
+        torch.cuda.synchronize(eng.device)
 
 
 def _print_verbose(info: SolveInfo, every: int) -> None:
