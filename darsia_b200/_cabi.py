@@ -100,6 +100,7 @@ class Problem(C.Structure):
         ("tile_x", C.c_int32),
         ("tile_y", C.c_int32),
         ("zchunk", C.c_int32),
+        ("adaptive_mask", C.c_void_p),
     ]
 
 

@@ -160,6 +160,7 @@ struct Geom {
   int z_begin, z_end;  // owned planes (local indices)
   int zchunk;          // planes per CTA
   int xtiles, ytiles;  // in-plane tiling (depends on the kernel's halo widths)
+  int pf;              // L2 prefetch distance in planes (0 = off)
 };
 
 template <typename T>
@@ -317,6 +318,8 @@ struct Col {
   long long cur;    // running BYTE offset of the current plane j
   long long cdel;   // BYTES: -b * sb (to rebase onto a coefficient map's own batch stride)
   long long s0b;    // BYTES between consecutive planes
+  long long pfb;    // BYTES of the L2 prefetch distance (pf planes)
+  int pfz;          // last plane index from which a prefetch still lands inside the allocation
   int z0, z1;       // planes [z0, z1) owned by this CTA
   bool st;          // interior thread whose results are stored
   bool edge;        // block touches the image boundary / is a partial tile (block-uniform)
@@ -366,6 +369,8 @@ struct Col {
     s0b = g.s0 * W;
     base = ((long long)b * g.sb + (long long)Yc * g.pitch + Xc) * W;
     cur = base + (long long)z0 * s0b;
+    pfb = (long long)g.pf * s0b;
+    pfz = g.pf > 0 ? g.n0 - g.pf : -1;  // prefetch from plane j iff j < pfz
 #if defined(__CUDACC__)
     // keep the per-thread invariants in registers instead of re-deriving them from %tid / the
     // kernel parameters on every plane (the compiler otherwise rematerialises them)
@@ -373,6 +378,7 @@ struct Col {
 #endif
   }
   TVDK_DEV long long at(const Geom&, int z) const { return base + (long long)z * s0b; }
+  TVDK_DEV bool pf_ok(int z) const { return z < pfz; }
   // plane z exists in the local allocation and in the global domain
   TVDK_DEV bool plane_ok(const Geom& g, int z) const {
     const int gz = z + g.g0_off;
@@ -392,6 +398,15 @@ struct Col {
   TVDK_DEV bool zedge(const Geom& g, int z) const { return !has_zlo(g, z) || !has_zhi(g, z); }
 };
 
+#if defined(__CUDACC__)
+// L2 prefetch hint (no register is tied up, no scoreboard): pulls a line that this CTA will load
+// a few planes later from HBM into L2, so that the march's one-plane-ahead register prefetch
+// sees L2 latency instead of DRAM latency.
+TVDK_DEV void pf_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+#else
+TVDK_DEV void pf_l2(const void*) {}
+#endif
+
 // all offsets `o` below are BYTE offsets
 template <typename T>
 TVDK_DEV const T* bptr(const T* base, long long o) {
@@ -404,6 +419,10 @@ TVDK_DEV T* bptr(T* base, long long o) {
 template <typename T>
 TVDK_DEV Vec<T> ldo(const T* base, long long o) {
   return vload_ro(bptr(base, o));
+}
+template <typename T>
+TVDK_DEV void pfo(const T* base, long long o) {
+  pf_l2(bptr(base, o));
 }
 template <typename T>
 TVDK_DEV Vec<T> ldw(const T* base, long long o) {  // plain load (data updated in place by this kernel)
@@ -743,6 +762,18 @@ struct KFusedJ1 {
     for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * D + d, rowe), c, wa_cur[d]);
     // next plane is needed if another compute step follows
     if (j + 1 < c.z1 || (j + 1 == c.z1 && c.plane_ok(a.g, j + 1))) prefetch(a, j + 1, c.cur + c.s0b);
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      pfo(a.u_in, o);
+      pfo(a.f, o);
+#pragma unroll
+      for (int d = 0; d < D; ++d) pfo(a.t_in + d * a.tcs_in, o);
+      if (HET) {
+        if (a.k.mu.p) pfo(a.k.mu.p + (long long)c.b * a.k.mu.sb, o + c.cdel);
+        if (a.k.omega.p) pfo(a.k.omega.p + (long long)c.b * a.k.omega.sb, o + c.cdel);
+        if (a.k.ell.p) pfo(a.k.ell.p + (long long)c.b * a.k.ell.sb, o + c.cdel);
+      }
+    }
   }
 
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j) || c.zedge(a.g, j - 1); }
@@ -918,6 +949,15 @@ struct KRhs {
 #pragma unroll
     for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * D + d, rowe), c, wa_cur[d]);
     if (j + 1 < c.z1) prefetch(a, j + 1, c.cur + c.s0b);
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      pfo(a.f, o);
+      if (a.t) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) pfo(a.t + d * a.tcs, o);
+      }
+      if (MODE != RHS_ONLY) pfo(a.u, o);
+    }
   }
 
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
@@ -1042,6 +1082,10 @@ struct KSweep {
       nx_rhs = ldo(a.rhs, c.cur + c.s0b);
       if (c.has_zhi(a.g, j + 1)) nx_x = ldo(a.x_in, c.cur + 2 * c.s0b);
     }
+    if (c.pf_ok(j)) {
+      pfo(a.rhs, c.cur + c.pfb);
+      pfo(a.x_in, c.cur + c.pfb);
+    }
   }
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
   template <bool E>
@@ -1162,6 +1206,15 @@ struct KCg {
     p_hi = c.has_zhi(a.g, j) ? make_p() : p_c;
     sst(srow<T>(smem, j & 1, rowe), c, p_c);
     if (j + 1 < c.z1 && c.has_zhi(a.g, j + 1)) load_raw(a, c.cur + 2 * c.s0b);
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      if (MODE != CG_PQ || !first) pfo(a.p_in, o);
+      if (MODE == CG_PQ) pfo(a.r_in, o);
+      if (MODE == CG_UPDATE && c.st) {
+        pfo(a.x, o);
+        pfo(a.r, o);
+      }
+    }
   }
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
   template <bool E>
@@ -1268,6 +1321,17 @@ struct KShrink {
     up_hi = c.has_zhi(a.g, j) ? nx_up : up_c;
     sst(srow<T>(smem, j & 1, rowe), c, up_c);
     if (j + 1 < c.z1 && c.has_zhi(a.g, j + 1)) nx_up = ldo(un, c.cur + 2 * c.s0b);
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      pfo(un, o);
+      if (c.st) {
+        pfo(a.u_old, o);
+        if (a.t_in) {
+#pragma unroll
+          for (int d = 0; d < D; ++d) pfo(a.t_in + d * a.tcs, o);
+        }
+      }
+    }
   }
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j); }
   template <bool E>
@@ -1383,6 +1447,62 @@ struct KEnergy {
     ++j;
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
+};
+
+// ==========================================================================================
+// Adaptive regularisation (split_bregman_tvd.py:149-158):
+//     ell = 1 / max( sum_a |G_a u+| , 1e-12 )         (1-norm of the gradient per voxel)
+// ==========================================================================================
+template <typename T, int D>
+struct KAdapt {
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = 0, RH = 1, NRED = 0, NROWS = 2;
+  typedef Col<T, D, LH, RH> C;
+  struct Args {
+    Geom g;
+    const T* x;
+    T* ell;
+    const tvdk_stat_t* skip;
+    Fin fin;
+  };
+  C c;
+  int j, rowe;
+  Vec<T> x_c, x_hi;
+  double red[1];
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
+    if (a.skip && a.skip[lc.bz].done) return false;
+    c.setup(a.g, lc);
+    rowe = C::row_elems(lc.ntx, lc.nty);
+    j = c.z0;
+    x_c = ldo(a.x, c.cur);
+    return true;
+  }
+  TVDK_DEV bool more() const { return j < c.z1; }
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    x_hi = c.has_zhi(a.g, j) ? ldo(a.x, c.cur + c.s0b) : x_c;
+    sst(srow<T>(smem, j & 1, rowe), c, x_c);
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    const T* prow = srow<T>(smem, j & 1, rowe);
+    const bool zhi = c.has_zhi(a.g, j);
+    Vec<T> yp = x_c;
+    if (D == 3) yp = syp(prow, c);
+    const T xr = sxp(prow, c);
+    Vec<T> el;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      T g1 = tabs(zhi ? x_hi.v[v] - x_c.v[v] : (T)0);
+      if (D == 3) g1 += tabs(c.hyhi ? yp.v[v] - x_c.v[v] : (T)0);
+      const T right = v < V - 1 ? x_c.v[v < V - 1 ? v + 1 : 0] : xr;
+      g1 += tabs(c.hr[v] ? right - x_c.v[v] : (T)0);
+      el.v[v] = (T)1 / tmax(g1, (T)1e-12);
+    }
+    sto(c, a.ell, c.cur, el);
+    x_c = x_hi;
+    c.cur += c.s0b;
+    ++j;
+  }
+  static TVDK_DEV void finalize(const Args&, int, const double*) {}
 };
 
 // ==========================================================================================

@@ -15,6 +15,7 @@
 // the CPU test-suite.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -64,6 +65,16 @@ static int check_geom(const tvdk_geom_t* g) {
   return 0;
 }
 
+// L2 prefetch distance of the march kernels in planes (TVDK_PF overrides; 0 = off)
+static int prefetch_planes() {
+  static const int v = [] {
+    const char* e = getenv("TVDK_PF");
+    const int d = e ? atoi(e) : 4;
+    return d < 0 ? 0 : (d > 64 ? 64 : d);
+  }();
+  return v;
+}
+
 static Geom make_geom(const tvdk_geom_t& g) {
   Geom r;
   r.n0 = g.n[0];
@@ -79,6 +90,7 @@ static Geom make_geom(const tvdk_geom_t& g) {
   r.z_end = g.z_end;
   r.zchunk = g.z_end - g.z_begin;
   r.xtiles = r.ytiles = 1;
+  r.pf = prefetch_planes();
   return r;
 }
 
@@ -130,6 +142,7 @@ struct LaunchCfg {
 };
 
 static thread_local Tune g_tune = {0, 0, 0};
+
 
 static Tune merge_tune(int tx, int ty, int zc) {
   Tune t;
@@ -274,7 +287,7 @@ static Fin no_fin() {
 // ---------------------------------------------------------------------------------------
 struct FieldPlan {
   // number of extra fields taken from the workspace
-  bool fusedj1, cg, jac, expl;
+  bool fusedj1, cg, jac, expl, adapt;
   int n_fields;
 };
 
@@ -282,10 +295,16 @@ static FieldPlan field_plan(const tvdk_problem_t* p) {
   FieldPlan fp;
   fp.expl = p->x0_b != nullptr || p->x0_d != nullptr;
   fp.cg = p->solver_kind == TVDK_SOLVER_CG;
-  fp.fusedj1 = p->fused && !fp.cg && p->solver_maxiter == 1 && p->solver_tol < 0.0;
+  fp.adapt = false;
+  if (p->adaptive_mask)
+    for (int i = 0; i < p->max_num_iter; ++i) fp.adapt = fp.adapt || p->adaptive_mask[i] != 0;
+  // the adaptive schedule runs on the building-block route: Jacobi keeps the diagonal of the
+  // initial ell (jacobi.py:101-106 caches it), rhs and shrink use the current one
+  fp.fusedj1 = p->fused && !fp.cg && p->solver_maxiter == 1 && p->solver_tol < 0.0 && !fp.adapt;
   fp.jac = !fp.cg;
   const int D = p->geom.dim;
   int n = 0;
+  if (fp.adapt) n += 1 + 2 * D;  // ell field, explicit d and b after an update of ell
   if (fp.fusedj1) {
     n += 1 + D;           // U2, T2
     if (fp.expl) n += 2;  // rhs + xa for the explicit first iteration
@@ -336,12 +355,24 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
     return r;
   };
 
-  const Coefs<T> k = make_coefs<T>(&p->mu, &p->omega, &p->ell, D);
+  Coefs<T> k = make_coefs<T>(&p->mu, &p->omega, &p->ell, D);  // current coefficients (ell may adapt)
+  const Coefs<T> k0 = k;  // Jacobi sweeps keep the initial ell's diagonal (jacobi.py:101-106)
   const T* f = reinterpret_cast<const T*>(p->f);
   T* ubuf[2] = {reinterpret_cast<T*>(p->u), nullptr};
   T* tbuf[2] = {reinterpret_cast<T*>(p->t), nullptr};
   long long tcs[2] = {p->t_comp_stride, (long long)fe};
   T *RB = nullptr, *XA = nullptr, *XB = nullptr, *X = nullptr, *P[2] = {nullptr, nullptr};
+  T *ELL = nullptr, *XD = nullptr, *XBB = nullptr;
+  if (fp.adapt) {
+    ELL = take(1);
+    XD = take(D);
+    XBB = take(D);
+  }
+  // explicit d, b of the next iteration: the caller's warm start, or the expansion made after
+  // an update of ell (the state is compressed with the kappa it was shrunk with)
+  const T* xd_cur = reinterpret_cast<const T*>(p->x0_d);
+  const T* xb_cur = reinterpret_cast<const T*>(p->x0_b);
+  long long xcs_cur = p->x0_comp_stride;
   if (fp.fusedj1) {
     ubuf[1] = take(1);
     tbuf[1] = take(D);
@@ -389,7 +420,8 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
     return fn;
   };
 
-  const bool het = k.sc.hetero != 0;
+  bool het = k.sc.hetero != 0;
+  const bool het0 = het;
 
   // shrink + Bregman update + in-place u update, shared by the unfused routes
   auto launch_shrink = [&](int it, int cur, const T* u0, const T* u1, const T* u2, int use_sel, bool expl_now) {
@@ -401,7 +433,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
       a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
       a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
-      a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;
+      a.xb = xb_cur; a.xcs = xcs_cur;
       a.skip = st; a.fin = fn;
       return run<K, T, D>(a, g, tune, false, sc, stream);
     });
@@ -411,8 +443,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
   memset(&a, 0, sizeof a);                                                \
   a.k = k; a.f = f;                                                       \
   a.t = (expl_now) ? nullptr : tbuf[cur]; a.tcs = tcs[cur];               \
-  a.xd = reinterpret_cast<const T*>(p->x0_d);                             \
-  a.xb = reinterpret_cast<const T*>(p->x0_b); a.xcs = p->x0_comp_stride;  \
+  a.xd = xd_cur; a.xb = xb_cur; a.xcs = xcs_cur;                          \
   a.u = ubuf[cur]; a.skip = st; a.fin = no_fin();
 
   auto launch_rhs_sweep = [&](int cur, bool expl_now, T* rhs, T* x, const Fin& fn) {
@@ -434,14 +465,26 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
     });
   };
 
+  auto launch_rhs_only = [&](int cur, bool expl_now, T* rhs) {
+    return dispatch2(iso, het, [&](auto I, auto H) {
+      typedef KRhs<T, D, decltype(I)::value, RHS_ONLY, decltype(H)::value> K;
+      typename K::Args a;
+      TVDK_RHS_ARGS(a, cur, expl_now)
+      a.rhs = rhs;
+      return run<K, T, D>(a, g, tune, false, sc, stream);
+    });
+  };
+
   const bool tolmode = !fp.cg && p->solver_tol >= 0.0;
+  bool expl_next = fp.expl;
   const int check_every = p->check_every > 0 ? p->check_every : 8;
   int cur = 0, launched = 0, slot = 0;
   bool pending[2] = {false, false};
   bool all_done = false;
 
   for (int it = 0; it < p->max_num_iter && !all_done; ++it) {
-    const bool expl_now = fp.expl && it == 0;
+    const bool expl_now = expl_next;
+    expl_next = false;
     if (p->verbose_every > 0 && it % p->verbose_every == 0 && p->energy_history) {
       // energy of the current iterate (split_bregman_tvd.py:162-167 prints _functional(img_iter))
       typename KEnergy<T, D>::Args a;
@@ -495,28 +538,71 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       if (tolmode) {
         fn.kind = FIN_JTOL; fn.stats = st; fn.tol = p->solver_tol; fn.buf_id = 1; fn.first_sweep = 1;
       }
-      TVDK_TRY(launch_rhs_sweep(cur, expl_now, RB, XA, fn));
       T* xin = XA;
       T* xout = XB;
       int out_id = 2;
-      for (int s = 2; s <= p->solver_maxiter; ++s) {
-        TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+      int s_first = 2;
+      if (fp.adapt) {  // rhs with the current ell; every sweep with the initial ell's diagonal
+        TVDK_TRY(launch_rhs_only(cur, expl_now, RB));
+        xin = ubuf[cur];
+        xout = XA;
+        out_id = 1;
+        s_first = 1;
+      } else {
+        TVDK_TRY(launch_rhs_sweep(cur, expl_now, RB, XA, fn));
+      }
+      for (int s = s_first; s <= p->solver_maxiter; ++s) {
+        TVDK_TRY(dispatch2(het0, false, [&](auto H, auto) {
           typedef KSweep<T, D, decltype(H)::value> K;
           typename K::Args a;
           memset(&a, 0, sizeof a);
-          a.k = k; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
+          a.k = k0; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
           if (tolmode) {
             a.fin.kind = FIN_JTOL; a.fin.stats = st; a.fin.tol = p->solver_tol; a.fin.buf_id = out_id;
+            a.fin.first_sweep = (s == 1);
           }
           return run<K, T, D>(a, g, tune, false, sc, stream);
         }));
-        std::swap(xin, xout);
-        out_id = 3 - out_id;
+        if (s == 1) {
+          xin = XA;
+          xout = XB;
+          out_id = 2;
+        } else {
+          std::swap(xin, xout);
+          out_id = 3 - out_id;
+        }
       }
       if (tolmode)
         TVDK_TRY(launch_shrink(it, cur, ubuf[cur], XA, XB ? XB : XA, 1, expl_now));
       else
         TVDK_TRY(launch_shrink(it, cur, xin, nullptr, nullptr, 0, expl_now));
+    }
+    if (fp.adapt && p->adaptive_mask[it] && it + 1 < p->max_num_iter) {
+      // split_bregman_tvd.py:149-158.  d and b stay what the shrinkage with the OLD kappa made
+      // them: expand them from the compressed state before ell changes, the next iteration
+      // reads them explicitly.
+      TVDK_TRY(dispatch2(iso, false, [&](auto I, auto) {
+        typedef KExpand<T, D, decltype(I)::value> K;
+        typename K::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.t = tbuf[cur]; a.tcs = tcs[cur]; a.d = XD; a.b = XBB; a.ocs = (long long)fe; a.fin = no_fin();
+        return run<K, T, D>(a, g, tune, false, sc, stream);
+      }));
+      {
+        typename KAdapt<T, D>::Args a;
+        memset(&a, 0, sizeof a);
+        a.x = ubuf[cur]; a.ell = ELL; a.skip = st; a.fin = no_fin();
+        TVDK_TRY((run<KAdapt<T, D>, T, D>(a, g, tune, false, sc, stream)));
+      }
+      k.ell.p = ELL;
+      k.ell.val = (T)0;
+      k.ell.sb = g.sb;
+      k.sc.hetero = 1;
+      het = true;
+      xd_cur = XD;
+      xb_cur = XBB;
+      xcs_cur = (long long)fe;
+      expl_next = true;
     }
     ++launched;
     // convergence polling (split_bregman_tvd.py:173-175) without stalling the queue: the flag

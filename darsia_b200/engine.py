@@ -216,6 +216,7 @@ class Engine:
         check_every: int = 8,
         full_shape: Optional[tuple] = None,
         sync: bool = True,
+        adaptive_mask: Optional[np.ndarray] = None,
     ) -> Optional[SolveInfo]:
         """Run ``tvdk_solve`` on resident fields: ``u`` (in: initial iterate, out: result) and the
         compressed state ``t`` are updated in place.  With ``sync=False`` nothing is read back
@@ -244,6 +245,11 @@ class Engine:
         p.check_every = int(check_every)
         p.fused = 1 if fused else 0
         p.tile_x, p.tile_y, p.zchunk = self.tile
+        if adaptive_mask is not None:
+            adaptive_mask = np.ascontiguousarray(adaptive_mask, dtype=np.uint8)
+            if adaptive_mask.shape != (int(max_num_iter),):
+                raise AssertionError("adaptive_mask needs one flag per outer iteration")
+            p.adaptive_mask = adaptive_mask.ctypes.data  # host memory, read during the call only
         nbytes = int(lib.workspace_bytes(C.byref(p)))
         if nbytes == 0:
             raise ValueError(lib.last_error().decode())

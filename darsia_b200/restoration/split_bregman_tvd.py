@@ -79,7 +79,10 @@ def split_bregman_tvd(
         mu, omega, ell: scalar, an array of the spatial shape (shared by all problems) or of
             the full image shape.  ``ell=None`` means ``2 * mu``.
         dim, max_num_iter, eps, x0, isotropic, verbose, solver: as the reference.
-        adaptive: not implemented on the GPU (``NotImplementedError`` when not ``None``).
+        adaptive: callable ``iter -> bool`` (``split_bregman_tvd.py:149-158``): after the shrinkage of
+            an iteration for which it is true, ``ell <- 1 / max(sum_a |grad_a u|, 1e-12)`` per voxel.
+            It is evaluated up front for ``iter = 0 .. max_num_iter - 1`` (the loop is device-resident).
+            As in the reference, Jacobi keeps the diagonal of the initial ``ell``.
     Additive keyword-only arguments:
         precision: ``"fp64"`` / ``"fp32"`` compute precision (default: the image's dtype).
         device: CUDA device (default: the current one).
@@ -93,8 +96,11 @@ def split_bregman_tvd(
         raise TypeError(
             f"float32/float64 images only, got {img.dtype} (the reference mixes rescaled and raw integers, SURVEY Q10)"
         )
+    adaptive_mask = None
     if adaptive is not None:
-        raise NotImplementedError("the adaptive ell schedule is not implemented on the GPU path")
+        if not callable(adaptive):
+            raise TypeError("adaptive must be a callable iter -> bool (or None)")
+        adaptive_mask = np.array([1 if adaptive(it) else 0 for it in range(int(max_num_iter))], dtype=np.uint8)
     if dim not in (2, 3):
         raise ValueError(f"dim must be 2 or 3, got {dim}")
     if img.ndim < dim:
@@ -153,7 +159,7 @@ def split_bregman_tvd(
     info: SolveInfo = eng.solve(
         f, u, t, mu, omega, ell, isotropic, spec, max_num_iter, eps,
         x0_db=x0_db, verbose_every=verbose_every, record_history=return_info, fused=fused,
-        full_shape=img.shape,
+        full_shape=img.shape, adaptive_mask=adaptive_mask,
     )
     if verbose_every:
         _print_verbose(info, verbose_every)

@@ -120,6 +120,10 @@ typedef struct tvdk_problem {
   int32_t check_every;     /* host polls the device "all done" flag every N outer iterations */
   int32_t fused;           /* 1 = allow the fused per-iteration kernels (default), 0 = building blocks only */
   int32_t tile_x, tile_y, zchunk; /* 0 = library default; thread-block shape / planes per CTA */
+  /* `adaptive` schedule (split_bregman_tvd.py:26, :149-158): HOST array of max_num_iter flags,
+   * adaptive_mask[it] != 0 <=> adaptive(it) is true: after the shrinkage of iteration `it`
+   * ell <- 1 / max(sum_a |grad_a u+|, 1e-12) per voxel.  NULL = no adaptivity. */
+  const uint8_t* adaptive_mask;
 } tvdk_problem_t;
 
 int tvdk_version(void);

@@ -40,3 +40,22 @@ def small_grid():
     opts = itertools.product((False, True), ("j1", "j3", "cg4", "jtol"), (False, True), (np.float64, np.float32))
     for (shape, dim, tile), (iso, solver, hetero, dtype) in itertools.product(geoms, opts):
         yield shape, dim, tile, iso, solver, hetero, dtype
+
+
+def adaptive_cases():
+    """(shape, dim, tile, solver, isotropic): the adaptive ell schedule (every iteration) across tile and
+    chunk seams, 3-D, isotropic and batched; all well-conditioned (checked against the oracle at 1e-12)."""
+    return [
+        ((11, 19, 70), 3, (8, 6, 3), "j3", False),
+        ((37, 150), 2, (32, 0, 5), "j3", False),
+        ((11, 19, 70), 3, (8, 6, 3), "j1", True),
+        ((21, 70, 2), 2, (32, 0, 5), "j3", False),
+    ]
+
+
+def run_adaptive_pair(da, oracle, shape, dim, tile, solver, iso):
+    img = phantom(tuple(shape), 5)
+    kw = dict(mu=0.1, omega=1.0, ell=1.0, dim=dim, max_num_iter=6, isotropic=iso, adaptive=lambda it: True)
+    ref = oracle.split_bregman_tvd(img, solver=SOLVERS[solver](oracle), **kw)
+    out = da.split_bregman_tvd(img, solver=SOLVERS[solver](da), tile=tile, **kw)
+    return out, ref

@@ -11,7 +11,7 @@ import pytest
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from emu.harness import emulated
-from parity_cases import run_pair, small_grid
+from parity_cases import adaptive_cases, run_adaptive_pair, run_pair, small_grid
 
 import darsia_b200 as da
 
@@ -29,13 +29,19 @@ def test_golden(name):
     out = run_case_with(da, arrays, params)
     ref = arrays["out"]
     assert out.shape == ref.shape and out.dtype == ref.dtype
-    assert rel_l2(out, ref) <= tolerance_for(ref.dtype)
+    assert rel_l2(out, ref) <= tolerance_for(ref.dtype, params)
 
 
 @pytest.mark.parametrize("shape,dim,tile,iso,solver,hetero,dtype", list(small_grid()))
 def test_tile_seams(shape, dim, tile, iso, solver, hetero, dtype):
     out, ref = run_pair(da, oracle, shape, dim, iso, solver, dtype=dtype, hetero=hetero, tile=tile)
     assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("shape,dim,tile,solver,iso", adaptive_cases())
+def test_adaptive_schedule(shape, dim, tile, solver, iso):
+    out, ref = run_adaptive_pair(da, oracle, shape, dim, tile, solver, iso)
+    assert rel_l2(out, ref) <= 1e-12
 
 
 @pytest.mark.parametrize("fused", [True, False])

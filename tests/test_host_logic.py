@@ -80,8 +80,8 @@ def test_errors(img):
         da.split_bregman_tvd(img, mu=np.zeros(img.shape))  # ell = 2*mu = 0 (Q12)
     with pytest.raises(AssertionError):
         da.split_bregman_tvd(img, mu=np.ones((3, 3)))
-    with pytest.raises(NotImplementedError):
-        da.split_bregman_tvd(img, adaptive=lambda it: True)
+    with pytest.raises(TypeError):
+        da.split_bregman_tvd(img, adaptive=True)  # a schedule is a callable iter -> bool
 
 
 def test_dtype_and_precision(img):

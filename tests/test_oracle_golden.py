@@ -20,9 +20,26 @@ def test_oracle_matches_reference(name):
     assert out.shape == ref.shape and out.dtype == ref.dtype
     err = rel_l2(out, ref)
     # tolerance of north_star; the restatement actually agrees to round-off
-    assert err <= tolerance_for(ref.dtype), f"{name}: rel L2 {err:.3e}"
-    if ref.dtype == np.float64:
+    assert err <= tolerance_for(ref.dtype, params), f"{name}: rel L2 {err:.3e}"
+    if ref.dtype == np.float64 and not params.get("parity_tol"):
         assert err <= 1e-13, f"{name}: restatement drifted from the reference ({err:.3e})"
+
+
+@pytest.mark.parametrize("name", ["aniso2d_j1_adaptive", "aniso2d_cg5_adaptive", "aniso2d_j1_adaptive_f32"])
+def test_adaptive_conditioning(name):
+    """Why some adaptive fixtures carry a looser tolerance: perturbing the INPUT by about one ulp
+    moves the reference algorithm's own output by far more than 1e-10 (ell = 1/|grad u| blows
+    round-off up wherever the gradient is tiny), so no implementation can agree more closely than
+    that.  The fixture's parity_tol must cover the measured sensitivity with some margin."""
+    arrays, params = load_golden(name)
+    img = arrays["img"]
+    rng = np.random.default_rng(0)
+    ulp = np.finfo(img.dtype).eps
+    pert = dict(arrays)
+    pert["img"] = (img * (1 + ulp * rng.choice([-1.0, 1.0], img.shape))).astype(img.dtype)
+    moved = rel_l2(run_case_with(oracle, pert, params), run_case_with(oracle, arrays, params))
+    assert moved > tolerance_for(img.dtype)  # ill-conditioned: the default bar is not attainable
+    assert moved < tolerance_for(img.dtype, params)  # ... and the fixture's own bar covers it
 
 
 @pytest.fixture(scope="module")
