@@ -161,6 +161,7 @@ struct Geom {
   int zchunk;          // planes per CTA
   int xtiles, ytiles;  // in-plane tiling (depends on the kernel's halo widths)
   int pf;              // L2 prefetch distance in planes (0 = off)
+  int pfsub;           // 1: one thread per 128-byte line issues the prefetch, 0: every thread
 };
 
 template <typename T>
@@ -210,6 +211,8 @@ enum FinKind {
   FIN_CGINIT,  // totals = {sum rhs^2, sum r^2}
   FIN_CGPQ,    // totals[0] = p.q
   FIN_CGRR,    // totals[0] = r.r
+  FIN_CGFIRST, // totals = {r.q, q.q}, q = A r_0          (single-pass CG route, K7)
+  FIN_CGFUSED, // totals = {r.r, p.q, r.q, q.q}
   FIN_JTOL,    // totals = {sum (x_new - x)^2, sum x_in^2}
   FIN_ENERGY   // totals = {sum (omega (x - f))^2, sum |mu G x|}
 };
@@ -282,6 +285,28 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
       s.cg_iters += 1;
       s.cg_stop = (sqrt(tot[0]) < s.atol) ? 1 : 0;
       break;
+    case FIN_CGFIRST: {  // alpha_0 = rho_0 / (p_0.q_0), p_0 = r_0; beta_1 from the predicted rho_1
+      const double rho = s.rho;
+      const double al = rho / tot[0];
+      const double rho_next = fma(al, fma(al, tot[1], -2.0 * tot[0]), rho);  // ||r - alpha q||^2
+      s.pq = tot[0];
+      s.alpha = al;
+      s.rho_prev = rho;
+      s.beta = rho_next / rho;
+      s.cg_first = 0;
+      s.cg_iters = 1;
+    } break;
+    case FIN_CGFUSED: {  // rho_i summed directly; alpha_i = rho_i / (p_i.q_i); beta_{i+1} predicted
+      const double rho = tot[0];
+      const double al = rho / tot[1];
+      const double rho_next = fma(al, fma(al, tot[3], -2.0 * tot[2]), rho);
+      s.rho_prev = s.rho;
+      s.rho = rho;
+      s.pq = tot[1];
+      s.alpha = al;
+      s.beta = rho_next / rho;
+      s.cg_iters += 1;
+    } break;
     case FIN_JTOL: {  // jacobi.py:118-131 (old iterate kept on convergence, Q7)
       if (f.first_sweep) s.jac_x0nrm2 = tot[1];
       double err = sqrt(tot[0]) / sqrt(s.jac_x0nrm2);
@@ -307,10 +332,13 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
 // around loads); what a thread outside the image loads is never consumed because the boundary
 // rules select the other operand.  Blocks whose whole region (interior + halo) lies strictly
 // inside the image take a fast path without any per-element boundary selects (`edge == false`).
-template <typename T, int D, int LH, int RH>
+// LH / RH: halo rows below / above along y (3-D); LHX / RHX: halo VECTORS left / right along x (a
+// vector already holds >= 2 elements, so one vector covers an element halo of up to 2).
+template <typename T, int D, int LH, int RH, int LHX_ = -1>
 struct Col {
   static constexpr int V = Vec<T>::N;
   static constexpr int RHX = RH > 0 ? 1 : 0;
+  static constexpr int LHX = LHX_ < 0 ? LH : LHX_;
   int X, Y, b;      // global coordinates of the first element of the thread's vector; problem
   int soff;         // shared-memory element offset of the vector inside one row array
   int spitch;       // shared-memory row pitch (elements)
@@ -327,14 +355,14 @@ struct Col {
   bool hl[V], hr[V];  // element has a left / right neighbour along x
   bool hylo, hyhi;    // row has a lower / upper neighbour along y (3-D)
 
-  static TVDK_HD int iw(int ntx) { return (ntx - LH - RHX) * V; }
+  static TVDK_HD int iw(int ntx) { return (ntx - LHX - RHX) * V; }
   static TVDK_HD int ih(int nty) { return D == 3 ? nty - LH - RH : 1; }
   static TVDK_HD int row_elems(int ntx, int nty) { return (nty + 2) * (ntx + 2) * V; }
 
   TVDK_DEV void setup(const Geom& g, const LaunchCtx& lc) {
     const int xt = lc.bx % g.xtiles, yt = lc.bx / g.xtiles;
     const int x0 = xt * iw(lc.ntx);
-    X = x0 + (lc.tx - LH) * V;
+    X = x0 + (lc.tx - LHX) * V;
     bool rowok = true;
     Y = 0;
     bool edge_y = false;
@@ -344,12 +372,12 @@ struct Col {
       rowok = (Y >= 0) && (Y < g.ny);
       edge_y = (y0 - LH < 0) || (y0 + ih(lc.nty) + RH > g.ny);
     }
-    edge = edge_y || (x0 - LH * V < 0) || (x0 + iw(lc.ntx) + RHX * V > g.nx);
+    edge = edge_y || (x0 - LHX * V < 0) || (x0 + iw(lc.ntx) + RHX * V > g.nx);
     b = lc.bz;
     z0 = g.z_begin + lc.by * g.zchunk;
     z1 = z0 + g.zchunk < g.z_end ? z0 + g.zchunk : g.z_end;
     const bool inalloc = rowok && X >= 0 && X < g.pitch;
-    const bool xin = lc.tx >= LH && lc.tx < lc.ntx - RHX;
+    const bool xin = lc.tx >= LHX && lc.tx < lc.ntx - RHX;
     const bool yin = (D == 3) ? (lc.ty >= LH && lc.ty < lc.nty - RH) : true;
     st = inalloc && xin && yin && X < g.nx;
 #pragma unroll
@@ -370,7 +398,7 @@ struct Col {
     base = ((long long)b * g.sb + (long long)Yc * g.pitch + Xc) * W;
     cur = base + (long long)z0 * s0b;
     pfb = (long long)g.pf * s0b;
-    pfz = g.pf > 0 ? g.n0 - g.pf : -1;  // prefetch from plane j iff j < pfz
+    pfz = (g.pf > 0 && (!g.pfsub || (lc.tx & 7) == 0)) ? g.n0 - g.pf : -1;  // prefetch from plane j iff j < pfz
 #if defined(__CUDACC__)
     // keep the per-thread invariants in registers instead of re-deriving them from %tid / the
     // kernel parameters on every plane (the compiler otherwise rematerialises them)
@@ -678,6 +706,7 @@ template <typename T, int D, bool ISO, bool HET>
 struct KFusedJ1 {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 2, NRED = 1, NROWS = 2 * D + 2;
+  static constexpr int PF2D = ISO ? 4 : 2, PF3D = 2;  // L2 prefetch distance (profiles/r1_pf_sweep.txt)
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -877,6 +906,7 @@ template <typename T, int D, bool ISO, int MODE, bool HET>
 struct KRhs {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 2, NROWS = 2 * D;
+  static constexpr int PF2D = 4, PF3D = 4;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -1045,6 +1075,7 @@ template <typename T, int D, bool HET>
 struct KSweep {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 2, NROWS = 2;
+  static constexpr int PF2D = 0, PF3D = 4;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -1128,18 +1159,21 @@ struct KSweep {
 //   UPDATE: x += alpha p ; r -= alpha (A p) ;    reduce r . r      (q = A p is recomputed,
 //           not stored: 8 instead of 10 words per voxel and CG iteration)
 //   MATVEC: y = A x (test-granularity operator)
+//   FIRST:  reduce r.(A r) and (A r).(A r)  -- opens the single-pass route (K7): p_0 = r_0 is
+//           never written, alpha_0 and the predicted rho_1 come from these two sums
 // ==========================================================================================
-enum { CG_PQ = 0, CG_UPDATE = 1, CG_MATVEC = 2 };
+enum { CG_PQ = 0, CG_UPDATE = 1, CG_MATVEC = 2, CG_FIRST = 3 };
 
 template <typename T, int D, int MODE, bool HET>
 struct KCg {
   static constexpr int V = Vec<T>::N;
-  static constexpr int LH = 1, RH = 1, NRED = 1, NROWS = 2;
+  static constexpr int LH = 1, RH = 1, NRED = MODE == CG_FIRST ? 2 : 1, NROWS = 2;
+  static constexpr int PF2D = 0, PF3D = 4;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
     Coefs<T> k;
-    const T* p_in;  // PQ: old p ; UPDATE: p ; MATVEC: x
+    const T* p_in;  // PQ: old p ; UPDATE: p ; MATVEC: x ; FIRST: r
     const T* r_in;  // PQ: r
     T* p_out;       // PQ: new p ; MATVEC: y
     T* x;           // UPDATE (in place)
@@ -1182,8 +1216,9 @@ struct KCg {
     if (a.skip && (a.skip[lc.bz].done || a.skip[lc.bz].cg_stop)) return false;
     c.setup(a.g, lc);
     rowe = C::row_elems(lc.ntx, lc.nty);
-    red[0] = 0.0;
-    coef = (MODE == CG_MATVEC || !a.coef.p) ? (T)0 : (T)a.coef.at(c.b);
+#pragma unroll
+    for (int r = 0; r < NRED; ++r) red[r] = 0.0;
+    coef = (MODE == CG_MATVEC || MODE == CG_FIRST || !a.coef.p) ? (T)0 : (T)a.coef.at(c.b);
     first = (MODE == CG_PQ) && (a.first_all || a.first.at(c.b));
     j = c.z0;
     const long long o = c.at(a.g, j);
@@ -1246,11 +1281,167 @@ struct KCg {
           cr = ldw(a.r, c.cur + c.s0b);
         }
       }
+    } else if (MODE == CG_FIRST) {
+      if (c.st) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (c.template OK<E>(v)) {
+            red[0] += (double)p_c.v[v] * (double)q.v[v];
+            red[NRED - 1] += (double)q.v[v] * (double)q.v[v];
+          }
+      }
     } else {
       sto(c, a.p_out, c.cur, q);
     }
     p_lo = p_c;
     p_c = p_hi;
+    c.cur += c.s0b;
+    ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge || ZEDGE(a))
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
+  }
+  static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
+};
+
+// ==========================================================================================
+// K7  one whole CG iteration in ONE pass (fixed iteration count, tol == 0):
+//         r  = r_old - alpha_old (A p_old)        x += alpha_old p_old
+//         p  = r + beta p_old                     q  = A p
+//         reduce  r.r,  p.q,  r.q,  q.q
+//     Same recurrence as K5/K6 (scipy cg, cg.py:50-56), reordered so that x, r and p stream
+//     through the SM once per iteration (6 instead of 8 words per voxel): the update that closes
+//     iteration i-1 and the direction/matvec that open iteration i share one kernel.  beta needs
+//     rho = r.r BEFORE r exists, so the previous kernel predicts it from its own sums,
+//         rho_next = ||r - alpha q||^2 = rho - 2 alpha (r.q) + alpha^2 (q.q),
+//     while alpha always uses the directly summed rho (finalize_fin: FIN_CGFIRST / FIN_CGFUSED).
+//     p (and r) are needed on a +-1 halo of the new p, hence on +-2 of the old one: two halo rows
+//     each side in y, one halo vector each side in x, two extra planes at both chunk ends.
+//     Shared rows: [slot] = p_old(j), [2 + slot] = p_new(j).
+// ==========================================================================================
+template <typename T, int D, bool HET>
+struct KCgFused {
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = 2, RH = 2, NRED = 4, NROWS = 4;
+  static constexpr int PF2D = 0, PF3D = 4;
+  typedef Col<T, D, LH, RH, 1> C;
+  struct Args {
+    Geom g;
+    Coefs<T> k;
+    const T* p_in;   // p_old (== r_in for the first fused iteration: p_0 = r_0)
+    const T* r_in;   // r_old
+    T* p_out;
+    T* r_out;
+    T* x;            // in place
+    DRef alpha;      // alpha_old
+    DRef beta;
+    const tvdk_stat_t* skip;  // done / cg_stop
+    Fin fin;
+  };
+  C c;
+  int j, rowe;
+  T alpha, beta;
+  bool same, have_a;
+  Vec<T> po_lo, po_c, po_hi, ro_c;  // p_old(j-1), p_old(j), p_old(j+1), r_old(j)
+  Vec<T> pn_lo, pn_c, rn_c;         // p_new(j-2), p_new(j-1), r_new(j-1)
+  Vec<T> nx_p, nx_r, cx;            // p_old(j+1), r_old(j) loaded one step ahead; x(j-1)
+  double red[NRED];
+
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
+    if (a.skip && (a.skip[lc.bz].done || a.skip[lc.bz].cg_stop)) return false;
+    c.setup(a.g, lc);
+    rowe = C::row_elems(lc.ntx, lc.nty);
+#pragma unroll
+    for (int r = 0; r < NRED; ++r) red[r] = 0.0;
+    alpha = (T)a.alpha.at(c.b);
+    beta = (T)a.beta.at(c.b);
+    same = a.p_in == a.r_in;
+    j = c.z0 - 1;
+    const long long o = c.at(a.g, j);
+    c.cur = o;  // the march starts one plane below the chunk
+    if (c.plane_ok(a.g, j)) {
+      nx_r = ldo(a.r_in, o);
+      po_c = same ? nx_r : ldo(a.p_in, o);
+      po_lo = c.has_zlo(a.g, j) ? ldo(a.p_in, o - c.s0b) : po_c;
+      nx_p = ldo(a.p_in, o + c.s0b);  // plane z0 always exists
+    } else {
+      nx_p = ldo(a.p_in, o + c.s0b);
+      po_c = nx_p;
+      po_lo = nx_p;
+      nx_r = nx_p;
+    }
+    pn_lo = pn_c = rn_c = po_c;
+    cx = po_c;
+    if (c.st) cx = ldw(a.x, o + c.s0b);
+    return true;
+  }
+  TVDK_DEV bool more() const { return j <= c.z1; }
+
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    have_a = c.plane_ok(a.g, j);
+    po_hi = c.has_zhi(a.g, j) ? nx_p : po_c;
+    ro_c = nx_r;
+    sst(srow<T>(smem, j & 1, rowe), c, po_c);
+    if (j + 1 <= c.z1 && c.plane_ok(a.g, j + 1)) {
+      // (first fused iteration: p_0 = r_0, the plane loaded as p one step ago is this step's r)
+      nx_r = same ? nx_p : ldo(a.r_in, c.cur + c.s0b);
+      if (c.has_zhi(a.g, j + 1)) nx_p = ldo(a.p_in, c.cur + 2 * c.s0b);
+    }
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      pfo(a.r_in, o);
+      if (!same) pfo(a.p_in, o);
+      if (c.st) pfo(a.x, o);
+    }
+  }
+
+  TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j) || c.zedge(a.g, j - 1); }
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
+    Vec<T> pn_hi = pn_c;
+    Vec<T> rn_hi = rn_c;
+    if (have_a) {  // stage A, plane j: close the previous iteration, open this one
+      const Vec<T> om = ldcoef<HET>(c, a.k.omega, c.cur);
+      const Vec<T> qo = apply_A<T, D, E, HET>(c, a.g, j, c.cur, po_lo, po_c, po_hi, srow<T>(smem, j & 1, rowe), om, a.k.ell);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        rn_hi.v[v] = ro_c.v[v] - alpha * qo.v[v];
+        pn_hi.v[v] = beta * po_c.v[v] + rn_hi.v[v];
+      }
+      sst(srow<T>(smem, 2 + (j & 1), rowe), c, pn_hi);
+    }
+    if (j > c.z0) {  // stage B, plane j-1: q = A p_new, sums, outputs
+      const int zo = j - 1;
+      const long long oo = c.cur - c.s0b;
+      const Vec<T> om = ldcoef<HET>(c, a.k.omega, oo);
+      const Vec<T> q = apply_A<T, D, E, HET>(c, a.g, zo, oo, pn_lo, pn_c, pn_hi, srow<T>(smem, 2 + (zo & 1), rowe), om, a.k.ell);
+      if (c.st) {
+        Vec<T> x = cx;
+#pragma unroll
+        for (int v = 0; v < V; ++v) x.v[v] += alpha * po_lo.v[v];  // po_lo still holds p_old(j-1)
+        stw(a.x, oo, x);
+        stw(a.r_out, oo, rn_c);
+        stw(a.p_out, oo, pn_c);
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (c.template OK<E>(v)) {
+            const double r = (double)rn_c.v[v], pp = (double)pn_c.v[v], qq = (double)q.v[v];
+            red[0] += r * r;
+            red[1] += pp * qq;
+            red[2] += r * qq;
+            red[3] += qq * qq;
+          }
+        if (j < c.z1) cx = ldw(a.x, c.cur);
+      }
+    }
+    po_lo = po_c;
+    po_c = po_hi;
+    pn_lo = pn_c;
+    pn_c = pn_hi;
+    rn_c = rn_hi;
     c.cur += c.s0b;
     ++j;
   }
@@ -1271,12 +1462,15 @@ template <typename T, int D, bool ISO, bool HET>
 struct KShrink {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 0, RH = 1, NRED = 1, NROWS = 2;
+  static constexpr int PF2D = 0, PF3D = 0;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
     Coefs<T> k;
     const T* unew[3];  // candidate buffers holding u+ ; selected by stats[b].jac_sel if use_sel
     int use_sel;
+    const T* axpy_p;   // optional: u+ = unew[0] + alpha * axpy_p (last x-update of the single-pass CG route)
+    DRef axpy_alpha;
     const T* u_old;    // pointwise
     T* u_out;          // may alias u_old (pointwise) or be nullptr
     const T* t_in;     // nullptr: explicit warm-start b in xb
@@ -1290,7 +1484,18 @@ struct KShrink {
   C c;
   int j, rowe;
   const T* un;
+  const T* ap;
+  T aalpha;
   Vec<T> up_c, up_hi, nx_up;
+  TVDK_DEV Vec<T> load_up(long long o) const {
+    Vec<T> x = ldo(un, o);
+    if (ap) {
+      const Vec<T> pv = ldo(ap, o);
+#pragma unroll
+      for (int v = 0; v < V; ++v) x.v[v] += aalpha * pv.v[v];
+    }
+    return x;
+  }
   // t and u may be updated in place (t_out == t_in, u_out == u_old): only the owning (interior)
   // thread touches them, one plane ahead of their use; halo threads merely publish u+ rows
   RawT<T, D> nx;
@@ -1309,10 +1514,12 @@ struct KShrink {
     rowe = C::row_elems(lc.ntx, lc.nty);
     red[0] = 0.0;
     un = a.unew[a.use_sel ? a.skip[lc.bz].jac_sel : 0];
+    ap = (a.axpy_p && !(a.skip && a.skip[lc.bz].cg_stop)) ? a.axpy_p : nullptr;
+    aalpha = ap ? (T)a.axpy_alpha.at(lc.bz) : (T)0;
     j = c.z0;
     const long long o = c.at(a.g, j);
-    up_c = ldo(un, o);
-    if (c.has_zhi(a.g, j)) nx_up = ldo(un, o + c.s0b);
+    up_c = load_up(o);
+    if (c.has_zhi(a.g, j)) nx_up = load_up(o + c.s0b);
     prefetch_own(a, o);
     return true;
   }
@@ -1320,10 +1527,11 @@ struct KShrink {
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
     up_hi = c.has_zhi(a.g, j) ? nx_up : up_c;
     sst(srow<T>(smem, j & 1, rowe), c, up_c);
-    if (j + 1 < c.z1 && c.has_zhi(a.g, j + 1)) nx_up = ldo(un, c.cur + 2 * c.s0b);
+    if (j + 1 < c.z1 && c.has_zhi(a.g, j + 1)) nx_up = load_up(c.cur + 2 * c.s0b);
     if (c.pf_ok(j)) {
       const long long o = c.cur + c.pfb;
       pfo(un, o);
+      if (ap) pfo(ap, o);
       if (c.st) {
         pfo(a.u_old, o);
         if (a.t_in) {

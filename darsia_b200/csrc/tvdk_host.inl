@@ -65,15 +65,29 @@ static int check_geom(const tvdk_geom_t* g) {
   return 0;
 }
 
-// L2 prefetch distance of the march kernels in planes (TVDK_PF overrides; 0 = off)
-static int prefetch_planes() {
-  static const int v = [] {
-    const char* e = getenv("TVDK_PF");
-    const int d = e ? atoi(e) : 4;
-    return d < 0 ? 0 : (d > 64 ? 64 : d);
-  }();
+// L2 prefetch distance of the march kernels in planes: per kernel (K::PF2D / K::PF3D, measured);
+// the environment variables TVDK_PF (planes, 0 = off) and TVDK_PFSUB (1 = one thread per
+// 128-byte line issues the hint) override it for tuning runs.
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+static int prefetch_override() {
+  static const int v = std::min(env_int("TVDK_PF", -1), 64);
   return v;
 }
+static int prefetch_sub() {
+  static const int v = env_int("TVDK_PFSUB", 0) != 0;
+  return v;
+}
+template <class K, typename = void>
+struct KernelPf {
+  static int get(int) { return 0; }
+};
+template <class K>
+struct KernelPf<K, std::void_t<decltype(K::PF2D)>> {
+  static int get(int dim) { return dim == 2 ? K::PF2D : K::PF3D; }
+};
 
 static Geom make_geom(const tvdk_geom_t& g) {
   Geom r;
@@ -90,7 +104,8 @@ static Geom make_geom(const tvdk_geom_t& g) {
   r.z_end = g.z_end;
   r.zchunk = g.z_end - g.z_begin;
   r.xtiles = r.ytiles = 1;
-  r.pf = prefetch_planes();
+  r.pf = 0;
+  r.pfsub = prefetch_sub();
   return r;
 }
 
@@ -159,7 +174,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
   typedef typename K::C C;
   constexpr int V = Vec<T>::N;
   LaunchCfg L;
-  const int halo_x = K::LH + C::RHX;
+  const int halo_x = C::LHX + C::RHX;
   const int need_x = (g.nx + V - 1) / V + halo_x;  // vectors to cover one row incl. halo
   if (D == 2) {
     int ntx = tune.tile_x > 0 ? round_up(tune.tile_x, 32) : 128;
@@ -229,9 +244,11 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   LaunchCfg b = plan_launch<KSweep<T, D, false>, T, D>(g, tune, false);
   LaunchCfg c = plan_launch<KShrink<T, D, false, false>, T, D>(g, tune, false);
   LaunchCfg d = plan_launch<KDot<T, D, 0>, T, D>(g, tune, false);
+  LaunchCfg e = plan_launch<KCgFused<T, D, false>, T, D>(g, tune, true);
   size_t m = 0;
-  for (const LaunchCfg* L : {&a, &b, &c, &d}) m = std::max(m, (size_t)L->gx * L->gy * L->gz);
-  return m * 2 + 64;
+  for (const LaunchCfg* L : {&a, &b, &c, &d}) m = std::max(m, (size_t)L->gx * L->gy * L->gz * 2);
+  m = std::max(m, (size_t)e.gx * e.gy * e.gz * 4);
+  return m + 64;
 }
 
 static size_t scratch_bytes(size_t partial_cap, int nb) {
@@ -257,6 +274,7 @@ static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_ti
                void* stream) {
   LaunchCfg L = plan_launch<K, T, D>(g, tune, big_tile);
   a.g = L.g;
+  a.g.pf = prefetch_override() >= 0 ? prefetch_override() : KernelPf<K>::get(D);
   if ((size_t)L.gx * L.gy * L.gz * (K::NRED > 0 ? K::NRED : 1) > sc.partial_cap)
     return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
   ++g_launches;
@@ -287,7 +305,7 @@ static Fin no_fin() {
 // ---------------------------------------------------------------------------------------
 struct FieldPlan {
   // number of extra fields taken from the workspace
-  bool fusedj1, cg, jac, expl, adapt;
+  bool fusedj1, cg, cgfused, jac, expl, adapt;
   int n_fields;
 };
 
@@ -301,6 +319,9 @@ static FieldPlan field_plan(const tvdk_problem_t* p) {
   // the adaptive schedule runs on the building-block route: Jacobi keeps the diagonal of the
   // initial ell (jacobi.py:101-106 caches it), rhs and shrink use the current one
   fp.fusedj1 = p->fused && !fp.cg && p->solver_maxiter == 1 && p->solver_tol < 0.0 && !fp.adapt;
+  // single-pass CG iterations (K7): fixed iteration count only -- with a tolerance the stopping
+  // test would act on a predicted instead of a summed residual norm
+  fp.cgfused = fp.cg && p->fused && p->solver_tol == 0.0;
   fp.jac = !fp.cg;
   const int D = p->geom.dim;
   int n = 0;
@@ -309,7 +330,7 @@ static FieldPlan field_plan(const tvdk_problem_t* p) {
     n += 1 + D;           // U2, T2
     if (fp.expl) n += 2;  // rhs + xa for the explicit first iteration
   } else if (fp.cg) {
-    n += 4;  // X, R, P0, P1
+    n += fp.cgfused ? 5 : 4;  // X, R, P0, P1 (+ R1: the single-pass route ping-pongs r as well)
   } else {
     n += (p->solver_maxiter >= 2) ? 3 : 2;  // rhs, XA, (XB)
   }
@@ -362,7 +383,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
   T* tbuf[2] = {reinterpret_cast<T*>(p->t), nullptr};
   long long tcs[2] = {p->t_comp_stride, (long long)fe};
   T *RB = nullptr, *XA = nullptr, *XB = nullptr, *X = nullptr, *P[2] = {nullptr, nullptr};
-  T *ELL = nullptr, *XD = nullptr, *XBB = nullptr;
+  T *ELL = nullptr, *XD = nullptr, *XBB = nullptr, *R1 = nullptr;
   if (fp.adapt) {
     ELL = take(1);
     XD = take(D);
@@ -385,6 +406,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
     RB = take(1);
     P[0] = take(1);
     P[1] = take(1);
+    if (fp.cgfused) R1 = take(1);
   } else {
     RB = take(1);
     XA = take(1);
@@ -424,13 +446,16 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
   const bool het0 = het;
 
   // shrink + Bregman update + in-place u update, shared by the unfused routes
-  auto launch_shrink = [&](int it, int cur, const T* u0, const T* u1, const T* u2, int use_sel, bool expl_now) {
+  const int stat_dstride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
+  auto launch_shrink = [&](int it, int cur, const T* u0, const T* u1, const T* u2, int use_sel, bool expl_now,
+                           const T* axpy_p = nullptr) {
     const Fin fn = outer_fin(it, cur);
     return dispatch2(iso, het, [&](auto I, auto H) {
       typedef KShrink<T, D, decltype(I)::value, decltype(H)::value> K;
       typename K::Args a;
       memset(&a, 0, sizeof a);
       a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
+      a.axpy_p = axpy_p; a.axpy_alpha.p = &st[0].alpha; a.axpy_alpha.stride = stat_dstride;
       a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
       a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
       a.xb = xb_cur; a.xcs = xcs_cur;
@@ -510,6 +535,33 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       Fin fn = no_fin();
       fn.kind = FIN_CGINIT; fn.stats = st; fn.tol = p->solver_tol;
       TVDK_TRY(launch_rhs_cginit(cur, expl_now, X, RB, fn));
+      if (fp.cgfused) {
+        // iteration 0: p_0 = r_0 is never written; alpha_0 and beta_1 come from r.(A r), (A r).(A r)
+        TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+          typedef KCg<T, D, CG_FIRST, decltype(H)::value> K;
+          typename K::Args a;
+          memset(&a, 0, sizeof a);
+          a.k = k; a.p_in = RB; a.skip = st; a.fin = no_fin(); a.fin.kind = FIN_CGFIRST; a.fin.stats = st;
+          return run<K, T, D>(a, g, tune, false, sc, stream);
+        }));
+        T* R[2] = {RB, R1};
+        const T* p_last = RB;
+        for (int i = 1; i < p->solver_maxiter; ++i) {
+          TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+            typedef KCgFused<T, D, decltype(H)::value> K;
+            typename K::Args a;
+            memset(&a, 0, sizeof a);
+            a.k = k; a.p_in = p_last; a.r_in = R[(i - 1) & 1]; a.p_out = P[i & 1]; a.r_out = R[i & 1]; a.x = X;
+            a.alpha.p = &st[0].alpha; a.alpha.stride = stat_dstride;
+            a.beta.p = &st[0].beta; a.beta.stride = stat_dstride;
+            a.skip = st; a.fin = no_fin(); a.fin.kind = FIN_CGFUSED; a.fin.stats = st;
+            return run<K, T, D>(a, g, tune, true, sc, stream);
+          }));
+          p_last = P[i & 1];
+        }
+        // x_m = x_{m-1} + alpha_{m-1} p_{m-1} is formed inside the shrink kernel
+        TVDK_TRY(launch_shrink(it, cur, X, nullptr, nullptr, 0, expl_now, p_last));
+      } else {
       for (int i = 0; i < p->solver_maxiter; ++i) {
         TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
           typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
@@ -532,6 +584,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
         }));
       }
       TVDK_TRY(launch_shrink(it, cur, X, nullptr, nullptr, 0, expl_now));
+      }
     } else {
       // Jacobi: sweep 1 fused with the rhs, then ping-pong XA/XB (jacobi.py:109-131)
       Fin fn = no_fin();
@@ -981,6 +1034,39 @@ static int cgupd_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_c
   });
 }
 
+template <typename T, int D>
+static int cgfirst_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* r,
+                        double* sum_out, void* ws, size_t wsb, void* stream) {
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KCg<T, D, CG_FIRST, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = (const T*)r; a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
+}
+
+template <typename T, int D>
+static int cgfused_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* p_in,
+                        const void* r_in, void* p_out, void* r_out, void* x, const double* alpha,
+                        const double* beta, double* sum_out, void* ws, size_t wsb, void* stream) {
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KCgFused<T, D, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = (const T*)p_in; a.r_in = (const T*)r_in; a.p_out = (T*)p_out; a.r_out = (T*)r_out;
+    a.x = (T*)x; a.alpha.p = alpha; a.alpha.stride = 1; a.beta.p = beta; a.beta.stride = 1;
+    a.fin = sum_fin(sum_out);
+    return run<K, T, D>(a, o.g, o.tune, true, o.sc, stream);
+  });
+}
+
 }  // namespace tvdk
 
 #define TVDK_C_ENTRY(g, CALL)        \
@@ -1063,4 +1149,18 @@ int tvdk_cg_update(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_co
                    void* r, const double* alpha, double* sum_out, void* workspace, size_t workspace_bytes,
                    void* stream) {
   TVDK_C_ENTRY(g, (cgupd_impl<T, D>(g, omega, ell, p, x, r, alpha, sum_out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_cg_first(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* r,
+                  double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  TVDK_C_ENTRY(g, (cgfirst_impl<T, D>(g, omega, ell, r, sum_out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* p_in,
+                  const void* r_in, void* p_out, void* r_out, void* x, const double* alpha, const double* beta,
+                  double* sum_out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (p_out == p_in || p_out == r_in || r_out == r_in || r_out == p_in)
+    return fail(TVDK_ERR_INVALID, "cg_fused is out-of-place in p and r");
+  TVDK_C_ENTRY(g, (cgfused_impl<T, D>(g, omega, ell, p_in, r_in, p_out, r_out, x, alpha, beta, sum_out, workspace,
+                                      workspace_bytes, stream)))
 }

@@ -224,6 +224,21 @@ int tvdk_cg_update(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_co
                    const void* p, void* x, void* r, const double* alpha, double* sum_out,
                    void* workspace, size_t workspace_bytes, void* stream);
 
+/* Single-pass CG iterations (what tvdk_solve runs for CG with tol == 0; same scipy recurrence as
+ * above, cg.py:50-56, reordered so that x, r and p stream through the GPU once per iteration):
+ *   tvdk_cg_first:  sum_out[2b..] = { r.(A r), (A r).(A r) }          (p_0 = r_0 is never stored)
+ *   tvdk_cg_fused:  x += alpha[b] p_in;  r_out = r_in - alpha[b] A p_in;  p_out = r_out + beta[b] p_in;
+ *                   sum_out[4b..] = { r_out.r_out, p_out.(A p_out), r_out.(A p_out), (A p_out).(A p_out) }
+ * p_in may equal r_in (first fused iteration); p_out / r_out must not alias p_in / r_in.
+ * The caller derives alpha = rho / (p.q) and beta = rho_next / rho with the PREDICTED
+ * rho_next = rho - 2 alpha (r.q) + alpha^2 (q.q)  (= ||r - alpha q||^2). */
+int tvdk_cg_first(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* r,
+                  double* sum_out, void* workspace, size_t workspace_bytes, void* stream);
+int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell,
+                  const void* p_in, const void* r_in, void* p_out, void* r_out, void* x,
+                  const double* alpha, const double* beta, double* sum_out, void* workspace,
+                  size_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -59,3 +59,34 @@ def run_adaptive_pair(da, oracle, shape, dim, tile, solver, iso):
     ref = oracle.split_bregman_tvd(img, solver=SOLVERS[solver](oracle), **kw)
     out = da.split_bregman_tvd(img, solver=SOLVERS[solver](da), tile=tile, **kw)
     return out, ref
+
+
+def cg_fixed_count_cases():
+    """(shape, dim, tile, cg iterations, isotropic, hetero (mu, omega AND ell maps), dtype, batch): CG with
+    tol == 0 runs the single-pass kernels (K7); thin / tiny extents put every plane of the two-deep
+    pipeline on a boundary, tiny tiles put every halo row and column on a seam."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((37, 150), 2, (32, 0, 5), 4, True, False, f8, ()),
+        ((37, 150), 2, (32, 0, 5), 1, False, False, f8, ()),
+        ((37, 150), 2, (32, 0, 5), 2, False, True, f8, (2,)),
+        ((11, 19, 70), 3, (8, 6, 3), 5, True, False, f8, ()),
+        ((11, 19, 70), 3, (8, 7, 4), 3, False, True, f4, ()),
+        ((9, 5, 6), 3, (0, 0, 0), 6, False, False, f8, ()),
+        ((3, 40), 2, (0, 0, 0), 6, False, False, f8, ()),
+        ((1, 40), 2, (0, 0, 0), 3, False, False, f8, ()),
+        ((2, 1, 7), 3, (0, 0, 0), 3, False, False, f8, ()),
+    ]
+
+
+def run_cg_fixed_pair(da, oracle, shape, dim, tile, m, iso, het, dtype, batch, fused=True):
+    img = phantom(tuple(shape) + tuple(batch), 5, dtype)
+    kw = dict(mu=0.1, omega=1.0, ell=1.0)
+    if het:
+        kw["mu"] = coeff_field(shape, 8, 0.05, 0.1, 0.1).astype(dtype)
+        kw["omega"] = coeff_field(shape, 9, 0.5, 2.0).astype(dtype)
+        kw["ell"] = coeff_field(shape, 10, 0.5, 1.5).astype(dtype)
+    ref = oracle.split_bregman_tvd(img, dim=dim, max_num_iter=6, isotropic=iso, solver=oracle.CG(maxiter=m, tol=0.0), **kw)
+    out = da.split_bregman_tvd(img, dim=dim, max_num_iter=6, isotropic=iso, solver=da.CG(maxiter=m, tol=0.0),
+                               tile=tile, fused=fused, **kw)
+    return out, ref

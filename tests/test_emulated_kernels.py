@@ -11,7 +11,8 @@ import pytest
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from emu.harness import emulated
-from parity_cases import adaptive_cases, run_adaptive_pair, run_pair, small_grid
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, run_adaptive_pair, run_cg_fixed_pair, run_pair,
+                          small_grid)
 
 import darsia_b200 as da
 
@@ -36,6 +37,14 @@ def test_golden(name):
 def test_tile_seams(shape, dim, tile, iso, solver, hetero, dtype):
     out, ref = run_pair(da, oracle, shape, dim, iso, solver, dtype=dtype, hetero=hetero, tile=tile)
     assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 2e-5)
+
+
+@pytest.mark.parametrize("shape,dim,tile,m,iso,het,dtype,batch", cg_fixed_count_cases())
+@pytest.mark.parametrize("fused", [True, False])
+def test_cg_fixed_count_single_pass_and_two_pass(shape, dim, tile, m, iso, het, dtype, batch, fused):
+    """CG(tol=0): the single-pass route (fused=True, K7) and the two-kernel route agree with the oracle."""
+    out, ref = run_cg_fixed_pair(da, oracle, shape, dim, tile, m, iso, het, dtype, batch, fused=fused)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
 
 
 @pytest.mark.parametrize("shape,dim,tile,solver,iso", adaptive_cases())

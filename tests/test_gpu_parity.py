@@ -9,7 +9,8 @@ import pytest
 
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
-from parity_cases import adaptive_cases, run_adaptive_pair, run_pair, small_grid
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, run_adaptive_pair, run_cg_fixed_pair, run_pair,
+                          small_grid)
 
 pytestmark = pytest.mark.gpu
 
@@ -38,6 +39,14 @@ def test_golden(da, name):
     assert err <= tolerance_for(ref.dtype, params), f"{name}: {err:.3e}"
     if ref.dtype == np.float64 and not params.get("parity_tol"):
         assert err <= 1e-12, f"{name}: {err:.3e}"
+
+
+@pytest.mark.parametrize("shape,dim,tile,m,iso,het,dtype,batch", cg_fixed_count_cases())
+@pytest.mark.parametrize("fused", [True, False])
+def test_cg_fixed_count_single_pass_and_two_pass(da, shape, dim, tile, m, iso, het, dtype, batch, fused):
+    """CG(tol=0): the single-pass route (fused=True, K7) and the two-kernel route agree with the oracle."""
+    out, ref = run_cg_fixed_pair(da, oracle, shape, dim, tile, m, iso, het, dtype, batch, fused=fused)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
 
 
 @pytest.mark.parametrize("shape,dim,tile,solver,iso", adaptive_cases())

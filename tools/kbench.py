@@ -57,9 +57,9 @@ def main():
     def rnd(n=1):
         return torch.rand(n * eng.batch_elems, dtype=eng.tdtype, device=dev, generator=gen)
 
-    f, u, u2, x, r, p0, p1 = rnd(), rnd(), rnd(), rnd(), rnd(), rnd(), rnd()
+    f, u, u2, x, r, p0, p1, r2 = rnd(), rnd(), rnd(), rnd(), rnd(), rnd(), rnd(), rnd()
     t, t2 = 0.1 * rnd(dim), rnd(dim)
-    sums = torch.zeros(2 * args.nb, dtype=torch.float64, device=dev)
+    sums = torch.zeros(4 * args.nb, dtype=torch.float64, device=dev)
     coef = torch.full((args.nb,), 1e-3, dtype=torch.float64, device=dev)
     if args.hetero:
         mu_c, _k1 = eng.coef(0.1 * rnd()[: eng.field_elems].contiguous())
@@ -82,6 +82,9 @@ def main():
                                                sums.data_ptr(), *ws(), s)),
         "cg_pq": (3, lambda: lib.cg_pq(bg, bo, be, p0.data_ptr(), r.data_ptr(), p1.data_ptr(), coef.data_ptr(), 0,
                                        sums.data_ptr(), *ws(), s)),
+        "cg_fused": (6, lambda: lib.cg_fused(bg, bo, be, p0.data_ptr(), r.data_ptr(), p1.data_ptr(), r2.data_ptr(),
+                                             x.data_ptr(), coef.data_ptr(), coef.data_ptr(), sums.data_ptr(), *ws(), s)),
+        "cg_first": (1, lambda: lib.cg_first(bg, bo, be, r.data_ptr(), sums.data_ptr(), *ws(), s)),
         "cg_init": (4 + dim, lambda: lib.cg_init(bg, 1, bm, bo, be, f.data_ptr(), t.data_ptr(), eng.batch_elems,
                                                  u.data_ptr(), x.data_ptr(), r.data_ptr(), sums.data_ptr(), *ws(), s)),
         "shrink": (2 + 2 * dim, lambda: lib.shrink(bg, 1, bm, be, u.data_ptr(), u2.data_ptr(), None, t.data_ptr(),
