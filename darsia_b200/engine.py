@@ -110,8 +110,11 @@ class Engine:
         g.nb = nb
         return g
 
-    def to_device(self, arr: np.ndarray) -> torch.Tensor:
-        """Host array -> flat device tensor in host order (a plain H2D copy)."""
+    def to_device(self, arr) -> torch.Tensor:
+        """Host array -> flat device tensor in host order (a plain H2D copy); a tensor that already
+        lives on the device is used as it is (device-resident callers: no copy)."""
+        if isinstance(arr, torch.Tensor):
+            return arr.to(self.device, non_blocking=True).contiguous().reshape(-1)
         t = torch.from_numpy(np.ascontiguousarray(arr).reshape(-1))
         return t.to(self.device, non_blocking=True)
 
@@ -142,9 +145,30 @@ class Engine:
         self.lib.check(rc, "tvdk_unpack")
         return out
 
-    def upload(self, img: np.ndarray) -> torch.Tensor:
-        """Host image ``(*spatial, *batch)`` -> field (H2D copy + layout kernel)."""
+    def upload(self, img) -> torch.Tensor:
+        """Host (or device) image ``(*spatial, *batch)`` -> field (H2D copy + layout kernel)."""
         return self.pack(self.to_device(img))
+
+    def expand_state(self, t: torch.Tensor, mu, ell, isotropic: bool, full_shape=None):
+        """Compressed state ``t`` -> the reference's ``(d, b)`` (``split_bregman_tvd.py:100-101``) as
+        planar fields (``dim`` components each), via ``tvdk_expand_state``."""
+        d = self.empty_fields(self.dim)
+        b = self.empty_fields(self.dim)
+        muc, k1 = self.coef(mu, full_shape, "mu")
+        elc, k2 = self.coef(ell, full_shape, "ell")
+        with device_guard(self.device):
+            rc = self.lib.expand_state(C.byref(self.geom), 1 if isotropic else 0, C.byref(muc), C.byref(elc),
+                                       t.data_ptr(), self.batch_elems, d.data_ptr(), b.data_ptr(), self.batch_elems,
+                                       self.stream())
+        self.lib.check(rc, "tvdk_expand_state")
+        return d, b
+
+    def components_to_host_order(self, planar: torch.Tensor, dst_dtype, shape) -> torch.Tensor:
+        """``dim`` planar component fields -> device tensor ``(*shape, dim)`` (component axis last, as
+        the reference keeps d and b)."""
+        comps = [self.unpack(planar[a * self.batch_elems:(a + 1) * self.batch_elems], dst_dtype).reshape(shape)
+                 for a in range(self.dim)]
+        return torch.stack(comps, dim=-1)
 
     def download(self, field: torch.Tensor, out_dtype=None, shape=None) -> np.ndarray:
         """Field -> host array ``(*spatial, *batch)``."""
@@ -170,21 +194,27 @@ class Engine:
             c.value = 0.0
             c.batch_stride = self.field_elems if (self.nb > 1 and value.numel() == self.batch_elems) else 0
             return c, value
-        arr = np.asarray(value)
+        if isinstance(value, torch.Tensor):  # an N-d map, possibly already on the device
+            arr = value if value.dim() > 0 else np.asarray(float(value))
+        else:
+            arr = np.asarray(value)
         if arr.ndim == 0:
             c.device_ptr = None
             c.value = float(arr)
             c.batch_stride = 0
             return c, None
-        if arr.shape == self.spatial:
+        if tuple(arr.shape) == self.spatial:
             nbc = 1
-        elif full_shape is not None and arr.shape == tuple(full_shape):
+        elif full_shape is not None and tuple(arr.shape) == tuple(full_shape):
             nbc = self.nb
         else:
             raise AssertionError(
                 f"{name} of shape {arr.shape} matches neither the spatial shape {self.spatial} nor the image shape"
             )
-        field = self.pack(self.to_device(arr.astype(self.np_dtype, copy=False)), nb=nbc)
+        if isinstance(arr, torch.Tensor):
+            field = self.pack(self.to_device(arr.to(self.tdtype)), nb=nbc)
+        else:
+            field = self.pack(self.to_device(arr.astype(self.np_dtype, copy=False)), nb=nbc)
         c.device_ptr = field.data_ptr()
         c.value = 0.0
         c.batch_stride = self.field_elems if nbc > 1 else 0

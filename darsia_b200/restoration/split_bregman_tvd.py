@@ -46,9 +46,15 @@ def _solver_spec(solver: Optional[Solver]) -> SolverSpec:
     return SolverSpec(kind=kind, maxiter=maxiter, tol=None if tol is None else float(tol))
 
 
+def _all(pred, c) -> bool:
+    """``pred`` holds for every entry of a scalar, array or (device) tensor coefficient."""
+    if _is_tensor(c):
+        return bool(pred(c).all())
+    return bool(np.all(pred(np.asarray(c))))
+
+
 def _check_positive(name: str, c: Coeff) -> None:
-    a = np.asarray(c)
-    if not np.all(a > 0):
+    if not _all(lambda a: a > 0, c):
         raise ValueError(f"{name} must be positive everywhere (the reference divides by it; SURVEY Q12)")
 
 
@@ -69,6 +75,7 @@ def split_bregman_tvd(
     precision: Optional[str] = None,
     device=None,
     return_info: bool = False,
+    return_state: bool = False,
     fused: bool = True,
     tile=(0, 0, 0),
 ):
@@ -87,15 +94,26 @@ def split_bregman_tvd(
         precision: ``"fp64"`` / ``"fp32"`` compute precision (default: the image's dtype).
         device: CUDA device (default: the current one).
         return_info: also return a ``SolveInfo`` (iterations, increments, history).
+        return_state: return ``(u, d, b)`` instead of ``u`` -- exactly the tuple the reference takes as
+            ``x0`` (``split_bregman_tvd.py:93-97``), so consecutive frames of a series can be warm-started.
+    Device-resident callers: ``img`` (and ``x0``, ``mu``, ``omega``, ``ell``) may be
+    ``torch`` tensors on the CUDA device; the result (and the state) then stays on that device as a
+    tensor and no host<->device copy is made.
         fused: allow the fused one-kernel-per-iteration path (default True).
         tile: (block_x, block_y, planes_per_block) launch-shape override, 0 = default (tuning/tests).
     """
-    if not isinstance(img, np.ndarray):
+    on_device = _is_tensor(img)
+    if not isinstance(img, np.ndarray) and not on_device:
         raise TypeError(f"Input type {type(img)} not supported.")
-    if not np.issubdtype(img.dtype, np.floating) or img.dtype not in (np.float32, np.float64):
+    img_dtype = _np_dtype(img)
+    if img_dtype not in (np.float32, np.float64):
         raise TypeError(
             f"float32/float64 images only, got {img.dtype} (the reference mixes rescaled and raw integers, SURVEY Q10)"
         )
+    if on_device:
+        if device is None and img.is_cuda:
+            device = img.device
+        mu, omega, ell = (_coef_to_host_or_field(c) for c in (mu, omega, ell))
     adaptive_mask = None
     if adaptive is not None:
         if not callable(adaptive):
@@ -109,11 +127,11 @@ def split_bregman_tvd(
     if ell is None:  # split_bregman_tvd.py:62-63
         ell = 2 * mu
     _check_positive("ell", ell)
-    if not np.all(np.asarray(mu) >= 0):
+    if not _all(lambda a: a >= 0, mu):
         raise ValueError("mu (the TV weight) must be non-negative")
 
     if precision is None:
-        cdtype = img.dtype
+        cdtype = img_dtype
     elif precision in ("fp64", "float64"):
         cdtype = np.dtype(np.float64)
     elif precision in ("fp32", "float32"):
@@ -121,10 +139,14 @@ def split_bregman_tvd(
     else:
         raise ValueError(f"precision must be 'fp64' or 'fp32', got {precision!r}")
 
-    spatial = img.shape[:dim]
-    nb = int(np.prod(img.shape[dim:], dtype=np.int64))
-    if img.size == 0:
-        return (img.copy(), None) if return_info else img.copy()
+    shape = tuple(img.shape)
+    spatial = shape[:dim]
+    nb = int(np.prod(shape[dim:], dtype=np.int64))
+    if int(np.prod(shape, dtype=np.int64)) == 0:
+        empty = img.clone() if on_device else img.copy()
+        return (empty, None) if return_info else empty
+    if return_state and adaptive is not None:
+        raise NotImplementedError("return_state with an adaptive ell schedule (the state would need the final ell map)")
     timing = os.environ.get("DARSIA_B200_TIMING") == "1"
     t_start = time.perf_counter()
     eng = Engine(spatial, nb=nb, dtype=cdtype, device=device, tile=tile)
@@ -132,17 +154,16 @@ def split_bregman_tvd(
     f = eng.upload(img)
     x0_db = None
     if x0 is not None:  # split_bregman_tvd.py:93-97
-        u0, d0, b0 = x0
-        u0, d0, b0 = np.asarray(u0), np.asarray(d0), np.asarray(b0)
-        assert u0.shape == img.shape and d0.shape == (*img.shape, dim) and b0.shape == (*img.shape, dim)
-        u = eng.upload(u0.astype(img.dtype, copy=False))
+        u0, d0, b0 = (v if _is_tensor(v) else np.asarray(v) for v in x0)
+        assert tuple(u0.shape) == shape and tuple(d0.shape) == (*shape, dim) and tuple(b0.shape) == (*shape, dim)
+        u = eng.upload(_cast(u0, img_dtype))
         # component axis last in the reference; planar components on the device
         d_pl = eng.empty_fields(dim)
         b_pl = eng.empty_fields(dim)
         for a in range(dim):
             sl = slice(a * eng.batch_elems, (a + 1) * eng.batch_elems)
-            d_pl[sl] = eng.upload(np.ascontiguousarray(d0[..., a]).astype(img.dtype, copy=False))
-            b_pl[sl] = eng.upload(np.ascontiguousarray(b0[..., a]).astype(img.dtype, copy=False))
+            d_pl[sl] = eng.upload(_cast(d0[..., a], img_dtype))
+            b_pl[sl] = eng.upload(_cast(b0[..., a], img_dtype))
         x0_db = (d_pl, b_pl)
     else:  # split_bregman_tvd.py:99-101
         u = f.clone()
@@ -159,17 +180,58 @@ def split_bregman_tvd(
     info: SolveInfo = eng.solve(
         f, u, t, mu, omega, ell, isotropic, spec, max_num_iter, eps,
         x0_db=x0_db, verbose_every=verbose_every, record_history=return_info, fused=fused,
-        full_shape=img.shape, adaptive_mask=adaptive_mask,
+        full_shape=shape, adaptive_mask=adaptive_mask,
     )
     if verbose_every:
         _print_verbose(info, verbose_every)
     if timing:
         t_solve = time.perf_counter()
-    out = eng.download(u, img.dtype, img.shape)  # convert_dtype, split_bregman_tvd.py:177
+    # convert_dtype, split_bregman_tvd.py:177
+    if on_device:
+        out = eng.unpack(u, img_dtype).reshape(shape)
+    else:
+        out = eng.download(u, img_dtype, shape)
+    if return_state:
+        d_pl, b_pl = eng.expand_state(t, mu, ell, isotropic, full_shape=shape)
+        d_out = eng.components_to_host_order(d_pl, img_dtype, shape)
+        b_out = eng.components_to_host_order(b_pl, img_dtype, shape)
+        if not on_device:
+            d_out, b_out = d_out.cpu().numpy(), b_out.cpu().numpy()
+        out = (out, d_out, b_out)
     if timing:
         LAST_TIMINGS.clear()
         LAST_TIMINGS.update(upload=t_up - t_start, solve=t_solve - t_up, download=time.perf_counter() - t_solve)
     return (out, info) if return_info else out
+
+
+def _is_tensor(x) -> bool:
+    import torch
+
+    return isinstance(x, torch.Tensor)
+
+
+def _np_dtype(x) -> np.dtype:
+    if _is_tensor(x):
+        import torch
+
+        return {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64)}.get(x.dtype, np.dtype(object))
+    return np.dtype(x.dtype)
+
+
+def _cast(x, np_dtype):
+    """``x`` (array or tensor) in the image's dtype, contiguous."""
+    if _is_tensor(x):
+        import torch
+
+        return x.to({np.dtype(np.float32): torch.float32, np.dtype(np.float64): torch.float64}[np.dtype(np_dtype)]).contiguous()
+    return np.ascontiguousarray(x).astype(np_dtype, copy=False)
+
+
+def _coef_to_host_or_field(c):
+    """Coefficients of a device-resident call: 0-d tensors become floats, maps stay on the device."""
+    if _is_tensor(c) and c.dim() == 0:
+        return float(c)
+    return c
 
 
 def _sync(eng: Engine) -> None:

@@ -83,3 +83,26 @@ def test_h1_regularization_golden(name):
 
     out, ref = h1_cases.run(da, h1_cases.load(), name)
     assert out.shape == ref.shape and rel_l2(out, ref) <= 1e-12
+
+
+def test_state_round_trip_and_device_resident_io():
+    """``return_state`` hands back the reference's ``x0`` tuple (u, d, b): 4 iterations + a warm start of 3
+    more == 7 iterations straight.  Tensors in -> tensors out (no host copies), same numbers."""
+    import torch
+    from golden.generate_golden import coeff_field, phantom
+
+    img = phantom((24, 31, 2), 3)
+    mu = coeff_field((24, 31), 8, 0.05, 0.1, 0.1)
+    kw = dict(omega=1.0, ell=1.0, dim=2, isotropic=True)
+    ref7 = oracle.split_bregman_tvd(img, mu=mu, max_num_iter=7, solver=oracle.CG(maxiter=4, tol=0.0), **kw)
+    u4, d4, b4 = da.split_bregman_tvd(img, mu=mu, max_num_iter=4, solver=da.CG(maxiter=4, tol=0.0), return_state=True, **kw)
+    assert d4.shape == (*img.shape, 2) and b4.shape == (*img.shape, 2)
+    out = da.split_bregman_tvd(img, mu=mu, max_num_iter=3, solver=da.CG(maxiter=4, tol=0.0), x0=(u4, d4, b4), **kw)
+    assert rel_l2(out, ref7) <= 1e-13
+    ti, tmu = torch.from_numpy(img), torch.from_numpy(mu)
+    st = da.split_bregman_tvd(ti, mu=tmu, max_num_iter=4, solver=da.CG(maxiter=4, tol=0.0), return_state=True, **kw)
+    assert all(isinstance(a, torch.Tensor) for a in st)
+    tout = da.split_bregman_tvd(ti, mu=tmu, max_num_iter=3, solver=da.CG(maxiter=4, tol=0.0), x0=st, **kw)
+    assert isinstance(tout, torch.Tensor) and np.array_equal(tout.numpy(), out)
+    tv = da.tvd(ti, method="heterogeneous bregman", weight=0.1, max_num_iter=3, eps=None, dim=2)
+    assert isinstance(tv, torch.Tensor) and tv.shape == ti.shape

@@ -154,3 +154,24 @@ def test_h1_regularization_golden(da, name):
 
     out, ref = h1_cases.run(da, h1_cases.load(), name)
     assert out.shape == ref.shape and rel_l2(out, ref) <= 1e-12
+
+
+def test_state_round_trip_and_device_resident_io(da):
+    """Device-resident callers: CUDA tensors in -> CUDA tensors out, and the (u, d, b) state of
+    one call warm-starts the next: 4 + 3 iterations == 7 iterations straight (oracle)."""
+    import torch
+    from golden.generate_golden import coeff_field, phantom
+
+    img = phantom((120, 131, 2), 3)
+    mu = coeff_field((120, 131), 8, 0.05, 0.1, 0.1)
+    kw = dict(omega=1.0, ell=1.0, dim=2, isotropic=True)
+    ref7 = oracle.split_bregman_tvd(img, mu=mu, max_num_iter=7, solver=oracle.CG(maxiter=4, tol=0.0), **kw)
+    st = da.split_bregman_tvd(img, mu=mu, max_num_iter=4, solver=da.CG(maxiter=4, tol=0.0), return_state=True, **kw)
+    out = da.split_bregman_tvd(img, mu=mu, max_num_iter=3, solver=da.CG(maxiter=4, tol=0.0), x0=st, **kw)
+    assert rel_l2(out, ref7) <= 1e-12
+    dev = torch.device("cuda", 0)
+    ti, tmu = torch.from_numpy(img).to(dev), torch.from_numpy(mu).to(dev)
+    tst = da.split_bregman_tvd(ti, mu=tmu, max_num_iter=4, solver=da.CG(maxiter=4, tol=0.0), return_state=True, **kw)
+    assert all(isinstance(a, torch.Tensor) and a.is_cuda for a in tst)
+    tout = da.split_bregman_tvd(ti, mu=tmu, max_num_iter=3, solver=da.CG(maxiter=4, tol=0.0), x0=tst, **kw)
+    assert tout.is_cuda and np.array_equal(tout.cpu().numpy(), out)
