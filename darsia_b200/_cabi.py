@@ -13,7 +13,8 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libtvdk.so")
+# (TVDK_LIB: tuning runs compare alternative builds of the same CUDA library; there is still no CPU path)
+LIB_PATH = os.environ.get("TVDK_LIB") or os.path.join(HERE, "csrc", "libtvdk.so")
 
 TVDK_F64, TVDK_F32 = 0, 1
 TVDK_SOLVER_JACOBI, TVDK_SOLVER_CG = 0, 1

@@ -6,6 +6,8 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <type_traits>
+
 #include "tvdk_core.h"
 
 namespace tvdk {
@@ -38,6 +40,11 @@ __device__ __forceinline__ void block_sum(double (&val)[NRED], double (*wsum)[NR
   __syncthreads();
 }
 
+template <class K, typename = void>
+struct has_unroll2 : std::false_type {};
+template <class K>
+struct has_unroll2<K, std::void_t<decltype(K::UNROLL2)>> : std::bool_constant<K::UNROLL2> {};
+
 template <class K>
 __global__ void __launch_bounds__(kMaxThreads) tvdk_kernel(const typename K::Args a, double* partials,
                                                             unsigned* counters) {
@@ -47,10 +54,23 @@ __global__ void __launch_bounds__(kMaxThreads) tvdk_kernel(const typename K::Arg
   lc.bx = blockIdx.x; lc.by = blockIdx.y; lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
   K k;
   if (!k.init(a, lc, smem)) return;  // block-uniform (whole problems are skipped)
-  while (k.more()) {
-    k.pre(a, smem);
-    __syncthreads();
-    k.post(a, smem);
+  if constexpr (has_unroll2<K>::value) {
+    // march loop unrolled by two with a compile-time phase (see KFusedJ1)
+    while (k.more()) {
+      k.template pre_p<0>(a, smem);
+      __syncthreads();
+      k.template post_p<0>(a, smem);
+      if (!k.more()) break;
+      k.template pre_p<1>(a, smem);
+      __syncthreads();
+      k.template post_p<1>(a, smem);
+    }
+  } else {
+    while (k.more()) {
+      k.pre(a, smem);
+      __syncthreads();
+      k.post(a, smem);
+    }
   }
   if constexpr (K::NRED > 0) {
     constexpr int NR = K::NRED;

@@ -706,7 +706,7 @@ template <typename T, int D, bool ISO, bool HET>
 struct KFusedJ1 {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 2, NRED = 1, NROWS = 2 * D + 2;
-  static constexpr int PF2D = ISO ? 4 : 2, PF3D = 2;  // L2 prefetch distance (profiles/r1_pf_sweep.txt)
+  static constexpr int PF2D = ISO ? 3 : 2, PF3D = 3;  // L2 prefetch distance (profiles/r1_pf_sweep.txt)
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -769,10 +769,23 @@ struct KFusedJ1 {
 
   // phase 1: consume the prefetched plane j (form b/w from t), publish u(j) and w_a(j) (a >= 1),
   //          then issue the loads of plane j+1
+  // The march loop is unrolled by two in the sm_100a runner (UNROLL2): the phase PH = (j - z0) & 1
+  // is then a compile-time constant, so the double-buffer slot of every shared row is an immediate
+  // and the pipeline-register roll at the end of a step is renamed away across the two copies.
+  // (measured, profiles/r1_ab_unroll2.txt: +1 % with scalar coefficients, -2 % with per-voxel maps,
+  //  where the second copy of the loop body pushes the kernel over 128 registers)
+  static constexpr bool UNROLL2 = !HET;
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if ((j - c.z0) & 1) pre_p<1>(a, smem); else pre_p<0>(a, smem);
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if ((j - c.z0) & 1) post_p<1>(a, smem); else post_p<0>(a, smem);
+  }
+  template <int PH>
+  TVDK_DEV void pre_p(const Args& a, unsigned char* smem) {
     have_row = (j < c.z1) || c.plane_ok(a.g, j);
     if (!have_row) return;
-    const int slot = j & 1;
+    constexpr int slot = PH;
     u_hi = c.has_zhi(a.g, j) ? nx_u : u_c;
     Vec<T> ww[D];
     bw_plane<T, D, ISO, HET>(nx, a.k.sc, false, b_cur, ww);
@@ -806,9 +819,9 @@ struct KFusedJ1 {
   }
 
   TVDK_DEV bool ZEDGE(const Args& a) const { return c.zedge(a.g, j) || c.zedge(a.g, j - 1); }
-  template <bool E>
+  template <bool E, int PH>
   TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
-    const int slot = j & 1;
+    constexpr int slot = PH;
     Vec<T> up = vsplat<T>((T)0);
     if (have_row) {
       const T* urow = srow<T>(smem, slot * D + 0, rowe);
@@ -842,7 +855,7 @@ struct KFusedJ1 {
       // outputs of plane j-1: t_new = G u+ + b, u_out = u+, increment (:136-146, :161)
       const int zo = j - 1;
       const long long oo = c.cur - c.s0b;
-      const T* prow = srow<T>(smem, 2 * D + (zo & 1), rowe);
+      const T* prow = srow<T>(smem, 2 * D + (1 - PH), rowe);
       Vec<T> tn[D];
       const bool zhi = c.template ZHI<E>(a.g, zo);
 #pragma unroll
@@ -884,11 +897,12 @@ struct KFusedJ1 {
     c.cur += c.s0b;
     ++j;
   }
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+  template <int PH>
+  TVDK_DEV void post_p(const Args& a, unsigned char* smem) {
     if (c.edge || ZEDGE(a))
-      post_t<true>(a, smem);
+      post_t<true, PH>(a, smem);
     else
-      post_t<false>(a, smem);
+      post_t<false, PH>(a, smem);
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };
@@ -906,7 +920,7 @@ template <typename T, int D, bool ISO, int MODE, bool HET>
 struct KRhs {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 2, NROWS = 2 * D;
-  static constexpr int PF2D = 4, PF3D = 4;
+  static constexpr int PF2D = 3, PF3D = 3;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -1075,7 +1089,7 @@ template <typename T, int D, bool HET>
 struct KSweep {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = 2, NROWS = 2;
-  static constexpr int PF2D = 0, PF3D = 4;
+  static constexpr int PF2D = 2, PF3D = 4;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -1168,7 +1182,8 @@ template <typename T, int D, int MODE, bool HET>
 struct KCg {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 1, NRED = MODE == CG_FIRST ? 2 : 1, NROWS = 2;
-  static constexpr int PF2D = 0, PF3D = 4;
+  static constexpr int PF2D = MODE == CG_UPDATE ? 1 : (MODE == CG_FIRST ? 4 : 3);
+  static constexpr int PF3D = MODE == CG_UPDATE ? 3 : 4;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;
@@ -1326,7 +1341,7 @@ template <typename T, int D, bool HET>
 struct KCgFused {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 2, RH = 2, NRED = 4, NROWS = 4;
-  static constexpr int PF2D = 0, PF3D = 4;
+  static constexpr int PF2D = 3, PF3D = 2;
   typedef Col<T, D, LH, RH, 1> C;
   struct Args {
     Geom g;
@@ -1462,7 +1477,7 @@ template <typename T, int D, bool ISO, bool HET>
 struct KShrink {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 0, RH = 1, NRED = 1, NROWS = 2;
-  static constexpr int PF2D = 0, PF3D = 0;
+  static constexpr int PF2D = 1, PF3D = 3;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;

@@ -321,7 +321,9 @@ static FieldPlan field_plan(const tvdk_problem_t* p) {
   fp.fusedj1 = p->fused && !fp.cg && p->solver_maxiter == 1 && p->solver_tol < 0.0 && !fp.adapt;
   // single-pass CG iterations (K7): fixed iteration count only -- with a tolerance the stopping
   // test would act on a predicted instead of a summed residual norm
-  fp.cgfused = fp.cg && p->fused && p->solver_tol == 0.0;
+  // ... and 2-D only: in 3-D its two halo rows on each side of y cost more (0.5 of the HBM peak
+  // measured, profiles/r1_pf_sweep2.txt) than the 2 words per iteration it saves
+  fp.cgfused = fp.cg && p->fused && p->solver_tol == 0.0 && (p->geom.dim == 2 || p->fused >= 2);
   fp.jac = !fp.cg;
   const int D = p->geom.dim;
   int n = 0;

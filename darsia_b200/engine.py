@@ -273,7 +273,7 @@ class Engine:
             p.x0_comp_stride = self.batch_elems
         p.verbose_every = int(verbose_every)
         p.check_every = int(check_every)
-        p.fused = 1 if fused else 0
+        p.fused = int(fused)  # False/True, or 2: single-pass CG iterations in 3-D as well
         p.tile_x, p.tile_y, p.zchunk = self.tile
         if adaptive_mask is not None:
             adaptive_mask = np.ascontiguousarray(adaptive_mask, dtype=np.uint8)

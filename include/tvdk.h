@@ -118,7 +118,8 @@ typedef struct tvdk_problem {
   double* energy_history;  /* device or NULL: energies (verbose), max_num_iter * nb */
   int32_t verbose_every;   /* 0 = never compute the energy functional */
   int32_t check_every;     /* host polls the device "all done" flag every N outer iterations */
-  int32_t fused;           /* 1 = allow the fused per-iteration kernels (default), 0 = building blocks only */
+  int32_t fused;           /* 1 = allow the fused per-iteration kernels (default), 0 = building blocks only,
+                            * 2 = also take the single-pass CG iterations in 3-D (default: 2-D only) */
   int32_t tile_x, tile_y, zchunk; /* 0 = library default; thread-block shape / planes per CTA */
   /* `adaptive` schedule (split_bregman_tvd.py:26, :149-158): HOST array of max_num_iter flags,
    * adaptive_mask[it] != 0 <=> adaptive(it) is true: after the shrinkage of iteration `it`

@@ -88,5 +88,5 @@ def run_cg_fixed_pair(da, oracle, shape, dim, tile, m, iso, het, dtype, batch, f
         kw["ell"] = coeff_field(shape, 10, 0.5, 1.5).astype(dtype)
     ref = oracle.split_bregman_tvd(img, dim=dim, max_num_iter=6, isotropic=iso, solver=oracle.CG(maxiter=m, tol=0.0), **kw)
     out = da.split_bregman_tvd(img, dim=dim, max_num_iter=6, isotropic=iso, solver=da.CG(maxiter=m, tol=0.0),
-                               tile=tile, fused=fused, **kw)
+                               tile=tile, fused=(2 if fused else False), **kw)  # 2: single-pass also in 3-D
     return out, ref
