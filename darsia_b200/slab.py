@@ -76,12 +76,15 @@ class SlabEngine(Engine):
         return field[base + z0 * self.plane_elems: base + z1 * self.plane_elems]
 
     # -- communication ----------------------------------------------------------------------
-    def exchange(self, views: List[Tuple[torch.Tensor, int, int, int]]) -> None:
+    def exchange(self, views: List[Tuple[torch.Tensor, int, int, int]], wait: bool = True):
         """Halo exchange.  ``views``: (field, component, n_up, n_down) -- the last ``n_up`` owned
         planes go to the upper neighbour's ghost planes below its range, the first ``n_down``
-        owned planes go to the lower neighbour's ghost planes above its range."""
+        owned planes go to the lower neighbour's ghost planes above its range.
+        With ``wait=False`` the transfers are only enqueued (they start once everything enqueued on the
+        current stream so far has finished) and the request list is returned: kernels launched
+        afterwards overlap with them; ``finish`` makes the current stream wait for the data."""
         if self.world == 1:
-            return
+            return []
         ops = []
         for field, comp, n_up, n_down in views:
             assert n_up <= GL and n_down <= GH
@@ -95,9 +98,22 @@ class SlabEngine(Engine):
                     ops.append(dist.P2POp(dist.isend, self.planes(field, self.zb, self.zb + n_down, comp), self.lo, self.group))
                 if self.hi is not None:
                     ops.append(dist.P2POp(dist.irecv, self.planes(field, self.ze, self.ze + n_down, comp), self.hi, self.group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+        reqs = dist.batch_isend_irecv(ops) if ops else []
+        if wait:
+            self.finish(reqs)
+            return []
+        return reqs
+
+    @staticmethod
+    def finish(reqs) -> None:
+        for req in reqs:
+            req.wait()
+
+    def sub_geom(self, z0: int, z1: int) -> "_cabi.Geom":
+        """The slab's geometry restricted to the owned planes [z0, z1) (local indices)."""
+        g = _cabi.Geom.from_buffer_copy(self.geom)
+        g.z_begin, g.z_end = int(z0), int(z1)
+        return g
 
     def allreduce(self, t: torch.Tensor) -> torch.Tensor:
         if self.world > 1:
@@ -113,6 +129,8 @@ class SlabSolver:
     synchronisation unless ``eps`` or a positive CG tolerance asks for one; ``result`` downloads
     the owned planes.  ``bench.py`` times ``iterate``.
     """
+
+    HB = 4  # planes per boundary launch of the overlapped fused route (>= the 2 planes sent down)
 
     def __init__(self, global_shape, dim, dtype, mu, omega, ell, isotropic, solver, eps=None, group=None,
                  device=None):
@@ -135,6 +153,7 @@ class SlabSolver:
         self.incs: List[torch.Tensor] = []
         self.done = False
         self.iters = 0
+        self._pending = None  # halo transfers of the current iterate still in flight (fused route)
 
     def _coef(self, value, name):
         eng = self.eng
@@ -152,7 +171,7 @@ class SlabSolver:
         self.u = self.f.clone()
         self.t = eng.zero_fields(D)
         ws = eng.op_workspace()
-        self.sums = torch.zeros(2, dtype=torch.float64, device=eng.device)
+        self.sums = torch.zeros(8, dtype=torch.float64, device=eng.device)  # 3 launches x up to 2 sums
         with device_guard(eng.device):  # ||img|| over all ranks (split_bregman_tvd.py:58)
             lib.check(lib.dot(C.byref(g), self.f.data_ptr(), self.f.data_ptr(), self.sums.data_ptr(), ws.data_ptr(),
                               ws.numel(), eng.stream()), "tvdk_dot")
@@ -166,6 +185,36 @@ class SlabSolver:
             self.p = [eng.zero_fields(1), eng.zero_fields(1)]
             self.rho, self.rho_prev, self.pq, self.alpha, self.beta = (
                 torch.zeros(1, dtype=torch.float64, device=eng.device) for _ in range(5))
+
+    def _split(self, launch, halo, nsum: int = 1, lo_planes: int = 0, hi_planes: int = 0):
+        """Boundary-first overlap of one kernel with the halo exchange of what it produces.
+
+        ``launch(geom_ptr, sum_ptr)`` enqueues the kernel on the owned planes of ``geom``; it is called for
+        the few planes at either end of the slab that the neighbours need, then the transfers ``halo``
+        are enqueued (NCCL starts them once those small launches are done) and the interior launch
+        runs meanwhile.  The partial sums of the launches are added into ``self.sums[:nsum]``.
+        Returns the pending requests (``SlabEngine.finish`` before the ghosts are read)."""
+        eng, sums = self.eng, self.sums
+        nlo = max(self.HB, lo_planes) if eng.lo is not None else 0
+        nhi = max(self.HB, hi_planes) if eng.hi is not None else 0
+        sums.zero_()
+
+        def run(z0, z1, slot):
+            gg = eng.sub_geom(z0, z1)
+            launch(C.byref(gg), sums[slot * nsum:(slot + 1) * nsum].data_ptr())
+
+        if eng.world > 1 and eng.nown >= nlo + nhi + 1:
+            if nlo:
+                run(eng.zb, eng.zb + nlo, 1)
+            if nhi:
+                run(eng.ze - nhi, eng.ze, 2)
+            reqs = eng.exchange(halo, wait=False)
+            run(eng.zb + nlo, eng.ze - nhi, 0)
+            sums[0:nsum].add_(sums[nsum:2 * nsum]).add_(sums[2 * nsum:3 * nsum])
+        else:
+            run(eng.zb, eng.ze, 0)
+            reqs = eng.exchange(halo, wait=False)
+        return reqs
 
     def iterate(self, n: int) -> int:
         """Enqueue up to ``n`` outer iterations; returns how many were run (eps may stop early)."""
@@ -182,11 +231,18 @@ class SlabSolver:
             with device_guard(eng.device):
                 s_ = eng.stream()
                 if self.fused:
+                    # Boundary-first overlap (``_split``): the planes the neighbours need (2 at the lower, 1 at
+                    # the upper end) come from two small launches, the interior launch hides their transfer.
                     (ui, ti), (uo, to) = self.bufs[self.cur], self.bufs[1 - self.cur]
-                    eng.exchange([(ui, 0, 1, 2)] + [(ti, d, 1, 1) for d in range(D)])
-                    call(lib.fused_jacobi1(bg, iso, bm, bo, be, self.f.data_ptr(), ui.data_ptr(), uo.data_ptr(),
-                                           ti.data_ptr(), to.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, s_),
-                         "tvdk_fused_jacobi1")
+                    if self._pending is None:  # first iteration (or after reset): ghosts of the input
+                        eng.exchange([(ui, 0, 1, 2)] + [(ti, d, 1, 1) for d in range(D)])
+                    else:
+                        eng.finish(self._pending)
+                    self._pending = self._split(
+                        lambda gp, sp: call(lib.fused_jacobi1(gp, iso, bm, bo, be, self.f.data_ptr(), ui.data_ptr(),
+                                                              uo.data_ptr(), ti.data_ptr(), to.data_ptr(), tcs, sp, wsp,
+                                                              wsn, s_), "tvdk_fused_jacobi1"),
+                        [(uo, 0, 1, 2)] + [(to, d, 1, 1) for d in range(D)])
                     self.cur = 1 - self.cur
                 elif spec.kind == _cabi.TVDK_SOLVER_JACOBI:
                     u, t = self.u, self.t
@@ -206,36 +262,58 @@ class SlabSolver:
                 else:
                     u, t, x, r, p = self.u, self.t, self.x, self.r, self.p
                     rho, rho_prev, pq, alpha, beta = self.rho, self.rho_prev, self.pq, self.alpha, self.beta
-                    eng.exchange([(u, 0, 1, 1)] + [(t, d, 1, 1) for d in range(D)])
-                    call(lib.cg_init(bg, iso, bm, bo, be, self.f.data_ptr(), t.data_ptr(), tcs, u.data_ptr(), x.data_ptr(),
-                                     r.data_ptr(), sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_init")
-                    eng.allreduce(sums)
+                    # every kernel is split boundary-first (``_split``) so that the halo exchange of what it
+                    # produces overlaps its interior launch; the all-reduce that follows each kernel also
+                    # orders the transfers before the next kernel's ghost reads
+                    if self._pending is None:
+                        eng.exchange([(u, 0, 1, 1)] + [(t, d, 1, 1) for d in range(D)])
+                    else:
+                        eng.finish(self._pending)
+                    reqs = self._split(
+                        lambda gp, sp: call(lib.cg_init(gp, iso, bm, bo, be, self.f.data_ptr(), t.data_ptr(), tcs,
+                                                        u.data_ptr(), x.data_ptr(), r.data_ptr(), sp, wsp, wsn, s_),
+                                            "tvdk_cg_init"),
+                        [(r, 0, 1, 1)], nsum=2)
+                    eng.allreduce(sums[0:2])
                     bnrm = torch.sqrt(sums[0:1])
                     atol = float(spec.tol) * bnrm
                     rho.copy_(sums[1:2])
                     stop = False
                     if spec.tol > 0.0 or self.iters == 0:  # host check only when a tolerance can fire
                         stop = bool((bnrm == 0).item()) or bool((torch.sqrt(rho) < atol).item())
+                    updated = False
                     for i in range(spec.maxiter):
                         if stop:
                             break
-                        eng.exchange([(r, 0, 1, 1)])
+                        eng.finish(reqs)  # ghosts of r
                         if i > 0:
                             torch.div(rho, rho_prev, out=beta)
-                        call(lib.cg_pq(bg, bo, be, p[(i & 1) ^ 1].data_ptr(), r.data_ptr(), p[i & 1].data_ptr(),
-                                       beta.data_ptr(), 1 if i == 0 else 0, sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_pq")
+                        pin, pout = p[(i & 1) ^ 1], p[i & 1]
+                        reqs = self._split(
+                            lambda gp, sp: call(lib.cg_pq(gp, bo, be, pin.data_ptr(), r.data_ptr(), pout.data_ptr(),
+                                                          beta.data_ptr(), 1 if i == 0 else 0, sp, wsp, wsn, s_),
+                                                "tvdk_cg_pq"),
+                            [(pout, 0, 1, 1)])
                         pq.copy_(eng.allreduce(sums[0:1]))
                         torch.div(rho, pq, out=alpha)
-                        eng.exchange([(p[i & 1], 0, 1, 1)])
-                        call(lib.cg_update(bg, bo, be, p[i & 1].data_ptr(), x.data_ptr(), r.data_ptr(), alpha.data_ptr(),
-                                           sums.data_ptr(), wsp, wsn, s_), "tvdk_cg_update")
+                        eng.finish(reqs)  # ghosts of p
+                        last = i == spec.maxiter - 1
+                        reqs = self._split(
+                            lambda gp, sp: call(lib.cg_update(gp, bo, be, pout.data_ptr(), x.data_ptr(), r.data_ptr(),
+                                                              alpha.data_ptr(), sp, wsp, wsn, s_), "tvdk_cg_update"),
+                            [(r, 0, 1, 1)] + ([(x, 0, 0, 1)] if (last or spec.tol > 0.0) else []))
+                        updated = True
                         rho_prev.copy_(rho)
                         rho.copy_(eng.allreduce(sums[0:1]))
                         if spec.tol > 0.0:
                             stop = bool((torch.sqrt(rho) < atol).item())
-                    eng.exchange([(x, 0, 0, 1)])
-                    call(lib.shrink(bg, iso, bm, be, x.data_ptr(), u.data_ptr(), u.data_ptr(), t.data_ptr(), t.data_ptr(),
-                                    tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_shrink")
+                    eng.finish(reqs)
+                    if not updated:
+                        eng.exchange([(x, 0, 0, 1)])  # stopped before any update: x = u still needs its upper ghost
+                    self._pending = self._split(
+                        lambda gp, sp: call(lib.shrink(gp, iso, bm, be, x.data_ptr(), u.data_ptr(), u.data_ptr(),
+                                                       t.data_ptr(), t.data_ptr(), tcs, sp, wsp, wsn, s_), "tvdk_shrink"),
+                        [(u, 0, 1, 1)] + [(t, d, 1, 1) for d in range(D)], lo_planes=1)
             inc2 = eng.allreduce(sums[0:1].clone())
             self.incs.append(torch.sqrt(inc2 / self.nrm2))
             ran += 1
@@ -247,6 +325,9 @@ class SlabSolver:
 
     def reset(self) -> None:
         """Back to the initial state (u = img, t = 0) without re-uploading."""
+        if self._pending is not None:
+            self.eng.finish(self._pending)
+            self._pending = None
         if self.fused:
             self.cur = 0
         self.u.copy_(self.f)
@@ -254,6 +335,9 @@ class SlabSolver:
         self.incs, self.done, self.iters = [], False, 0
 
     def result_field(self) -> torch.Tensor:
+        if self._pending is not None:  # the last iterate's halo transfers: nothing reads them, but let them land
+            self.eng.finish(self._pending)
+            self._pending = None
         return self.bufs[self.cur][0] if self.fused else self.u
 
     def result(self, out_dtype=None) -> np.ndarray:
