@@ -450,9 +450,12 @@ def run_ours(args, w, wname):
     os.environ["DARSIA_B200_TIMING"] = "1"
     t0 = time.perf_counter()
     out = None
+    e2e_each = []
     for _ in range(e2e_steps):
         del out  # a streaming caller consumes one result before asking for the next (the pinned block is reused)
+        t1 = time.perf_counter()
         out = da.tvd(pinned_np, **kw)
+        e2e_each.append(round(time.perf_counter() - t1, 4))
     torch.cuda.synchronize(dev)
     e2e_s = (time.perf_counter() - t0) / e2e_steps
     os.environ.pop("DARSIA_B200_TIMING", None)
@@ -460,6 +463,8 @@ def run_ours(args, w, wname):
 
     _sbt = importlib.import_module("darsia_b200.restoration.split_bregman_tvd")
     e2e_breakdown = {k: round(v, 4) for k, v in _sbt.LAST_TIMINGS.items()}
+    e2e_breakdown["each_call_s"] = e2e_each
+    e2e_breakdown["input_is_pinned"] = bool(torch.from_numpy(pinned_np).is_pinned())
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)

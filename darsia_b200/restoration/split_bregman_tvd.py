@@ -151,7 +151,20 @@ def split_bregman_tvd(
     t_start = time.perf_counter()
     eng = Engine(spatial, nb=nb, dtype=cdtype, device=device, tile=tile)
 
-    f = eng.upload(img)
+    if timing:  # finer split of the upload: H2D copy vs layout kernel vs state allocation
+        _sync(eng)
+        t_e = time.perf_counter()
+        inter = eng.to_device(img)
+        _sync(eng)
+        t_h = time.perf_counter()
+        f = eng.pack(inter)
+        del inter
+        _sync(eng)
+        LAST_TIMINGS["_engine"] = t_e - t_start
+        LAST_TIMINGS["_h2d"] = t_h - t_e
+        LAST_TIMINGS["_pack"] = time.perf_counter() - t_h
+    else:
+        f = eng.upload(img)
     x0_db = None
     if x0 is not None:  # split_bregman_tvd.py:93-97
         u0, d0, b0 = (v if _is_tensor(v) else np.asarray(v) for v in x0)
@@ -199,7 +212,6 @@ def split_bregman_tvd(
             d_out, b_out = d_out.cpu().numpy(), b_out.cpu().numpy()
         out = (out, d_out, b_out)
     if timing:
-        LAST_TIMINGS.clear()
         LAST_TIMINGS.update(upload=t_up - t_start, solve=t_solve - t_up, download=time.perf_counter() - t_solve)
     return (out, info) if return_info else out
 
