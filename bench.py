@@ -441,9 +441,9 @@ def run_ours(args, w, wname):
               omega=(om_host if w["hetero"] else OMEGA), regularization=ELL, dim=dim, isotropic=w["iso"],
               max_num_iter=outer, eps=None, solver=solver_obj)
     e2e_steps = max(1, min(args.steps, 3))
-    # steady state of a caller that processes image after image: two warm-up calls fill torch's
+    # steady state of a caller that processes image after image: three warm-up calls fill torch's
     # device and pinned-host allocator caches (a fresh 672 MB cudaHostAlloc alone costs ~0.2 s)
-    for _ in range(2):
+    for _ in range(3):
         out = da.tvd(pinned_np, **kw)
         del out
     barrier()

@@ -85,9 +85,11 @@ __global__ void __launch_bounds__(kMaxThreads) tvdk_kernel(const typename K::Arg
 #pragma unroll
     for (int r = 0; r < NR; ++r) v[r] = k.red[r];
     block_sum<NR>(v, wsum, tid, nthreads);
+    // partials: [problem][sum][block] -- the second stage reads them coalesced
+    double* pb = partials + (size_t)b * nblk * NR;
     if (tid == 0) {
 #pragma unroll
-      for (int r = 0; r < NR; ++r) partials[((size_t)b * nblk + blk) * NR + r] = v[r];
+      for (int r = 0; r < NR; ++r) pb[(size_t)r * nblk + blk] = v[r];
       __threadfence();
       const unsigned prev = atomicAdd(&counters[b], 1u);
       is_last = (prev == nblk - 1);
@@ -98,9 +100,22 @@ __global__ void __launch_bounds__(kMaxThreads) tvdk_kernel(const typename K::Arg
       double s[NR];
 #pragma unroll
       for (int r = 0; r < NR; ++r) s[r] = 0.0;
-      for (unsigned i = tid; i < nblk; i += nthreads) {
+      // fixed order per thread (i = tid, tid + nthreads, ...), four independent loads in flight per sum
+      unsigned i = tid;
+      for (; i + 3u * nthreads < nblk; i += 4u * nthreads) {
 #pragma unroll
-        for (int r = 0; r < NR; ++r) s[r] += __ldcg(&partials[((size_t)b * nblk + i) * NR + r]);
+        for (int r = 0; r < NR; ++r) {
+          const double* q = pb + (size_t)r * nblk + i;
+          const double x0 = __ldcg(q), x1 = __ldcg(q + nthreads), x2 = __ldcg(q + 2 * nthreads), x3 = __ldcg(q + 3 * nthreads);
+          s[r] += x0;
+          s[r] += x1;
+          s[r] += x2;
+          s[r] += x3;
+        }
+      }
+      for (; i < nblk; i += nthreads) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) s[r] += __ldcg(pb + (size_t)r * nblk + i);
       }
       block_sum<NR>(s, wsum, tid, nthreads);
       if (tid == 0) {

@@ -18,12 +18,15 @@ from .tvd_oracle import (  # noqa: F401
     CG,
     H1_regularization,
     Jacobi,
+    MG,
     Solver,
     backward_diff,
     cg_matvec,
     forward_diff,
     jacobi_sweep,
     laplace,
+    mg_prolongation,
+    mg_restriction,
     neighbor_accumulation,
     shrink_anisotropic,
     shrink_isotropic,

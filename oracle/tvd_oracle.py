@@ -250,6 +250,98 @@ class CG(Solver):
 
 
 # --------------------------------------------------------------------------- #
+# MG (utils/linear_solvers/mg.py) -- V-cycle with Jacobi smoothing, scalar coefficients
+# --------------------------------------------------------------------------- #
+def mg_restriction(x: np.ndarray, dim: int) -> np.ndarray:
+    """Pairwise averages along each spatial axis in turn, last entry dropped if odd (mg.py:107-132)."""
+    for ax in range(dim):
+        n = x.shape[ax]
+        x = (np.take(x, np.arange(0, n - 1, 2), axis=ax) + np.take(x, np.arange(1, n, 2), axis=ax)) / 2
+    return x
+
+
+def mg_prolongation(x: np.ndarray, dim: int) -> np.ndarray:
+    """Every value repeated twice along each spatial axis (mg.py:151-168)."""
+    for ax in range(dim):
+        x = np.repeat(x, 2, axis=ax)
+    return x
+
+
+class MG(Solver):
+    """V-cycle multigrid for ``omega x - ell Lap x = rhs`` (mg.py:13-270), scalar ``omega`` / ``ell``.
+
+    Restated quirks of the reference: (i) ONE Jacobi smoother object serves every level, and it caches
+    ``diag`` / ``diag/ell`` on its first call, which is at ``h = 1`` (mg.py:60-66, jacobi.py:101-106) --
+    so the smoother never sees the coarse spacing, only the residual operator does (mg.py:94-105 via
+    ``laplace(..., h=h)``: every difference is divided by ``h``); (ii) the coarsest problem is "solved"
+    by the same smoother from a zero guess (mg.py:218-219); (iii) odd extents lose their last entry in
+    the restriction and get it back by edge padding (mg.py:229-238); (iv) with ``tol`` the PREVIOUS
+    iterate is returned on convergence and the increment is normalised by ``||x0||`` (mg.py:257-270).
+    Per-voxel coefficients are not restated: the reference overwrites them with their restricted /
+    prolongated (block-averaged) versions during the first V-cycle (mg.py:134-149, 170-192).
+    """
+
+    def __init__(self, depth: int = 2, smoother_iterations: int = 5, maxiter: int = 100, tol: Optional[float] = None,
+                 dim: int = 2, mass_coeff: Optional[Coeff] = None, diffusion_coeff: Optional[Coeff] = None,
+                 verbose: bool = False) -> None:
+        super().__init__(maxiter=maxiter, tol=tol, dim=dim, mass_coeff=mass_coeff, diffusion_coeff=diffusion_coeff,
+                         verbose=verbose)
+        self.depth = depth
+        self.smoother_iterations = smoother_iterations
+
+    def _check_scalar(self) -> None:
+        if np.ndim(self.mass_coeff) != 0 or np.ndim(self.diffusion_coeff) != 0:
+            raise NotImplementedError("MG: scalar mass / diffusion coefficients only (see the class docstring)")
+
+    def smooth(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+        omega, ell, dim = self.mass_coeff, self.diffusion_coeff, self.dim
+        diag = omega + ell * 2 * dim / 1.0**2  # cached at h = 1 (quirk i)
+        diag_scaled = np.divide(diag, ell / 1.0**2)
+        rhs_scaled = np.divide(rhs, diag)
+        x = x0
+        for _ in range(self.smoother_iterations):
+            x = rhs_scaled + np.divide(neighbor_accumulation(x), diag_scaled)
+        return x
+
+    def operator(self, x: np.ndarray, h: float) -> np.ndarray:
+        """mg.py:94-105: ``omega x - ell * laplace(x, dim, h=h)`` (unit coefficient inside the Laplacian)."""
+        lap = np.zeros_like(x)
+        for ax in range(self.dim):
+            lap += 0.5 * (backward_diff(1 * (forward_diff(x, ax, self.dim) / h), ax, self.dim) / h
+                          + forward_diff(1 * (backward_diff(x, ax, self.dim) / h), ax, self.dim) / h)
+        return self.mass_coeff * x - self.diffusion_coeff * lap
+
+    def v_cycle(self, x0: np.ndarray, rhs: np.ndarray, depth: int, h: float = 1) -> np.ndarray:
+        x = self.smooth(x0, rhs)  # mg.py:209
+        r = rhs - self.operator(x, h)  # :212
+        r = mg_restriction(r, self.dim)  # :215
+        if depth == 0:  # :218-223
+            eps = self.smooth(np.zeros_like(r), r)
+        else:
+            eps = self.v_cycle(np.zeros_like(r), r, depth - 1, 2 * h)
+        eps = mg_prolongation(eps, self.dim)  # :226
+        pad = tuple((0, x.shape[i] - eps.shape[i]) for i in range(self.dim))  # :229-238
+        eps = np.pad(eps, pad, "edge")
+        x = x + eps  # :239
+        return self.smooth(x, rhs)  # :242
+
+    def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+        self._check_scalar()
+        x = x0
+        if self.tol is None:  # mg.py:257-259
+            for _ in range(self.maxiter):
+                x = self.v_cycle(x, rhs, self.depth)
+        else:  # :260-269
+            for _ in range(self.maxiter):
+                x_new = self.v_cycle(x, rhs, self.depth)
+                nrm = np.linalg.norm(x_new - x) / np.linalg.norm(x0)
+                if nrm < self.tol:
+                    break
+                x = x_new
+        return x
+
+
+# --------------------------------------------------------------------------- #
 # Shrinkage (restoration/split_bregman_tvd.py:80-81, 107-126)
 # --------------------------------------------------------------------------- #
 def shrink_anisotropic(t: np.ndarray, kappa: Coeff) -> np.ndarray:

@@ -49,7 +49,7 @@ def run_case_with(api, arrays, params):
     has_x0 = p.pop("x0")
     spec = dict(p.pop("solver"))
     kind = spec.pop("kind")
-    solver = {"jacobi": api.Jacobi, "cg": api.CG}[kind](**spec)
+    solver = {"jacobi": api.Jacobi, "cg": api.CG, "mg": getattr(api, "MG", None)}[kind](**spec)
     kwargs = dict(p)
     kwargs.pop("parity_tol", None)
     kwargs["solver"] = solver

@@ -8,8 +8,9 @@ Run in the build container (where ``/root/reference`` exists)::
 eight hot-path source files are executed VERBATIM, from where they lie under
 ``/root/reference/src/darsia``, inside a stub ``darsia`` namespace plus a stub
 ``skimage`` exposing the ``img_as_*`` identities the path uses on float arrays.
-The only shim is ``scipy.sparse.linalg.cg(tol=...)`` -> ``rtol=...`` (SciPy >= 1.14
-renamed the argument; same meaning, SURVEY.md Q4).  Nothing is copied into the repo;
+The only shims are ``scipy.sparse.linalg.cg(tol=...)`` -> ``rtol=...`` (SciPy >= 1.14
+renamed the argument; same meaning) and ``np.lib.pad = np.pad`` (NumPy 2
+removed the alias that ``utils/linear_solvers/mg.py:233`` still uses).  Nothing is copied into the repo;
 only the inputs/outputs are stored, as ``tests/golden/<case>.npz``.
 
 Each case stores its inputs (``img`` and any coefficient arrays), a JSON ``params``
@@ -76,6 +77,9 @@ def load_reference():
         cg._tol_shim = True
         spla.cg = cg
 
+    if not hasattr(np.lib, "pad"):  # NumPy >= 2 removed the alias mg.py:233 uses
+        np.lib.pad = np.pad
+
     order = [
         "utils/array_slice.py",
         "utils/derivatives.py",
@@ -83,6 +87,7 @@ def load_reference():
         "utils/linear_solvers/solver.py",
         "utils/linear_solvers/jacobi.py",
         "utils/linear_solvers/cg.py",
+        "utils/linear_solvers/mg.py",
         "restoration/tvd.py",
         "restoration/split_bregman_tvd.py",
         "restoration/h1_regularization.py",
@@ -120,7 +125,7 @@ def coeff_field(shape, seed, lo, hi, zero_frac=0.0):
 def make_solver(da, spec):
     kind = spec["kind"]
     kw = {k: v for k, v in spec.items() if k != "kind"}
-    return {"jacobi": da.Jacobi, "cg": da.CG}[kind](**kw)
+    return {"jacobi": da.Jacobi, "cg": da.CG, "mg": da.MG}[kind](**kw)
 
 
 CASES = []
@@ -194,6 +199,15 @@ case("tvd_entry_iso_cg", (37, 52), 36, entry="tvd", method="heterogeneous bregma
      omega=0.8, dim=2, isotropic=True, max_num_iter=15, eps=None,
      solver={"kind": "cg", "maxiter": 4, "tol": 0.0})
 
+# --- MG V-cycle as the inner solver (utils/linear_solvers/mg.py) ------------------
+case("aniso2d_mg", (37, 52), 45, mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=8, isotropic=False,
+     solver={"kind": "mg", "depth": 2, "smoother_iterations": 3, "maxiter": 2})
+case("iso2d_mg_tol", (40, 33), 46, mu=0.1, omega=0.5, ell=2.0, dim=2, max_num_iter=6, isotropic=True,
+     solver={"kind": "mg", "depth": 1, "smoother_iterations": 5, "maxiter": 20, "tol": 1e-3})
+case("aniso3d_mg", (13, 18, 11), 47, mu=0.1, omega=1.0, ell=1.0, dim=3, max_num_iter=5, isotropic=False,
+     solver={"kind": "mg", "depth": 1, "smoother_iterations": 2, "maxiter": 1})
+case("aniso2d_mg_f32", (37, 52), 48, dtype="float32", mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=6,
+     isotropic=False, solver={"kind": "mg", "depth": 2, "smoother_iterations": 3, "maxiter": 1})
 # --- adaptive ell schedule (split_bregman_tvd.py:149-158) -------------------------------
 # parity_tol: ell = 1/|grad u| amplifies round-off wherever the gradient is tiny -- the reference's
 # own output moves by 2e-7 (Jacobi) / 1e-5 (CG) / 2e-3 (fp32) rel. L2 when its input is perturbed by
@@ -273,6 +287,12 @@ def operator_cases(da):
         store[f"{tag}_cg4"] = cg(x0=x, rhs=rhs)
         cgh = da.CG(maxiter=4, tol=0.0, dim=dim, mass_coeff=1.3, diffusion_coeff=ell)
         store[f"{tag}_cg4_hetero"] = cgh(x0=x, rhs=rhs)
+        if tag != "thin":
+            mg = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
+            store[f"{tag}_mg_restrict"] = mg.restriction(x)
+            store[f"{tag}_mg_prolong"] = mg.prolongation(mg.restriction(x))
+            store[f"{tag}_mg_operator_h2"] = mg.operator(x, h=2)
+            store[f"{tag}_mg2"] = mg(x0=x.copy(), rhs=rhs)
     return store
 
 
@@ -301,10 +321,12 @@ def main():
         store = run_case(da, c)
         np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), **store)
         print(f"{c['name']:28s} shape={c['shape']} out_norm={np.linalg.norm(store['out']):.12g}")
-    if only:
+    if only and "operators" not in only:
         return
     np.savez_compressed(os.path.join(OUT, "operators.npz"), **operator_cases(da))
     print("operators.npz written")
+    if only:
+        return
     np.savez_compressed(os.path.join(OUT, "h1.npz"), **h1_cases(da))
     print("h1.npz written")
 
