@@ -7,7 +7,7 @@ used for device memory, streams and ``torch.distributed`` only.  There is no CPU
 """
 
 from .image import Image, is_image_like  # noqa: F401
-from .utils.linear_solvers import CG, Jacobi, Solver  # noqa: F401
+from .utils.linear_solvers import CG, MG, Jacobi, Solver  # noqa: F401
 from .restoration.split_bregman_tvd import split_bregman_tvd  # noqa: F401
 from .restoration.tvd import TVD, tvd  # noqa: F401
 from .restoration.h1_regularization import H1_regularization  # noqa: F401

@@ -1173,10 +1173,11 @@ struct KSweep {
 //   UPDATE: x += alpha p ; r -= alpha (A p) ;    reduce r . r      (q = A p is recomputed,
 //           not stored: 8 instead of 10 words per voxel and CG iteration)
 //   MATVEC: y = A x (test-granularity operator)
+//   RESID:  y = rhs - A x  (multigrid residual, mg.py:212; rhs in r_in)
 //   FIRST:  reduce r.(A r) and (A r).(A r)  -- opens the single-pass route (K7): p_0 = r_0 is
 //           never written, alpha_0 and the predicted rho_1 come from these two sums
 // ==========================================================================================
-enum { CG_PQ = 0, CG_UPDATE = 1, CG_MATVEC = 2, CG_FIRST = 3 };
+enum { CG_PQ = 0, CG_UPDATE = 1, CG_MATVEC = 2, CG_FIRST = 3, CG_RESID = 4 };
 
 template <typename T, int D, int MODE, bool HET>
 struct KCg {
@@ -1233,7 +1234,7 @@ struct KCg {
     rowe = C::row_elems(lc.ntx, lc.nty);
 #pragma unroll
     for (int r = 0; r < NRED; ++r) red[r] = 0.0;
-    coef = (MODE == CG_MATVEC || MODE == CG_FIRST || !a.coef.p) ? (T)0 : (T)a.coef.at(c.b);
+    coef = (MODE == CG_MATVEC || MODE == CG_FIRST || MODE == CG_RESID || !a.coef.p) ? (T)0 : (T)a.coef.at(c.b);
     first = (MODE == CG_PQ) && (a.first_all || a.first.at(c.b));
     j = c.z0;
     const long long o = c.at(a.g, j);
@@ -1296,6 +1297,12 @@ struct KCg {
           cr = ldw(a.r, c.cur + c.s0b);
         }
       }
+    } else if (MODE == CG_RESID) {
+      const Vec<T> b = ldo(a.r_in, c.cur);
+      Vec<T> y;
+#pragma unroll
+      for (int v = 0; v < V; ++v) y.v[v] = b.v[v] - q.v[v];
+      sto(c, a.p_out, c.cur, y);
     } else if (MODE == CG_FIRST) {
       if (c.st) {
 #pragma unroll
@@ -1841,6 +1848,59 @@ struct KSelectCopy {
     if (c.st) {
       long long o = c.cur;
       for (int z = c.z0; z < c.z1; ++z, o += c.s0b) stw(a.dst, o, ldo(a.src, o));
+    }
+    return true;
+  }
+  TVDK_DEV bool more() const { return false; }
+  TVDK_DEV void pre(const Args&, unsigned char*) {}
+  TVDK_DEV void post(const Args&, unsigned char*) {}
+  static TVDK_DEV void finalize(const Args&, int, const double*) {}
+};
+
+// Multigrid grid transfer (utils/linear_solvers/mg.py).  One thread per element of the TARGET grid.
+//   MODE 0  restriction (mg.py:107-132): pairwise averages along axis 0, then 1 (, then 2); the last
+//           entry of an odd extent is dropped (coarse extent = fine extent / 2)
+//   MODE 1  prolongation + edge padding + correction (mg.py:226-239): every coarse value is repeated
+//           twice along each axis, an odd fine extent re-uses the last coarse value; fine += that
+template <typename T, int D, int MODE>
+struct KMgXfer {
+  static constexpr int NRED = 0, NROWS = 0;
+  struct Args {
+    Geom g;   // target grid (coarse for MODE 0, fine for MODE 1)
+    Geom go;  // the other grid
+    const T* src;
+    T* dst;
+    Fin fin;
+  };
+  double red[1];
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
+    // grid: x = rows (z * ny + y) of the target, y = row segments, z = problem
+    const long long row = lc.bx;
+    const int z = (int)(row / a.g.ny), y = (int)(row % a.g.ny);
+    const T* sb = a.src + (long long)lc.bz * a.go.sb;
+    T* db = a.dst + (long long)lc.bz * a.g.sb;
+    for (int x = lc.by * lc.ntx + lc.tx; x < a.g.nx; x += lc.nby * lc.ntx) {
+      const long long ti = (long long)z * a.g.s0 + (long long)y * a.g.pitch + x;
+      if (MODE == 0) {
+        T acc[2];
+#pragma unroll
+        for (int dx = 0; dx < 2; ++dx) {
+          T ay[2];
+#pragma unroll
+          for (int dy = 0; dy < (D == 3 ? 2 : 1); ++dy) {
+            const long long o = (long long)(2 * z) * a.go.s0 + (long long)(D == 3 ? 2 * y + dy : 0) * a.go.pitch + 2 * x + dx;
+            ay[dy] = (sb[o] + sb[o + a.go.s0]) / (T)2;  // axis 0 first
+          }
+          acc[dx] = D == 3 ? (ay[0] + ay[1]) / (T)2 : ay[0];  // then axis 1 (3-D)
+        }
+        db[ti] = (acc[0] + acc[1]) / (T)2;  // last axis
+      } else {
+        int zc = z >> 1, yc = y >> 1, xc = x >> 1;
+        zc = zc < a.go.n0 ? zc : a.go.n0 - 1;
+        yc = D == 3 ? (yc < a.go.ny ? yc : a.go.ny - 1) : 0;
+        xc = xc < a.go.nx ? xc : a.go.nx - 1;
+        db[ti] += sb[(long long)zc * a.go.s0 + (long long)yc * a.go.pitch + xc];
+      }
     }
     return true;
   }

@@ -1069,6 +1069,48 @@ static int cgfused_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk
   });
 }
 
+template <typename T, int D>
+static int resid_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* x,
+                      const void* rhs, void* r, void* ws, size_t wsb, void* stream) {
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
+    typedef KCg<T, D, CG_RESID, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = (const T*)x; a.r_in = (const T*)rhs; a.p_out = (T*)r; a.fin = no_fin();
+    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
+  });
+}
+
+template <typename T, int D, int MODE>
+static int mgxfer_impl(const tvdk_geom_t* target, const tvdk_geom_t* other, const void* src, void* dst,
+                       void* stream) {
+  typedef KMgXfer<T, D, MODE> K;
+  typename K::Args a;
+  memset(&a, 0, sizeof a);
+  a.g = make_geom(*target);
+  a.go = make_geom(*other);
+  a.src = (const T*)src; a.dst = (T*)dst; a.fin = no_fin();
+  const int ntx = 128;
+  const int gy = std::max(1, std::min((a.g.nx + ntx - 1) / ntx, 64));
+  const long long rows = (long long)a.g.n0 * a.g.ny;
+  ++g_launches;
+  return backend::launch<K>(a, (int)rows, gy, a.g.nb, ntx, 1, 0, stream, nullptr, nullptr);
+}
+
+static int check_mg_pair(const tvdk_geom_t* f, const tvdk_geom_t* c) {
+  TVDK_TRY(check_geom(f));
+  TVDK_TRY(check_geom(c));
+  if (f->dim != c->dim || f->dtype != c->dtype || f->nb != c->nb)
+    return fail(TVDK_ERR_INVALID, "fine and coarse grids must agree in dim, dtype and nb");
+  for (int a = 0; a < f->dim; ++a)
+    if (c->n[a] != f->n[a] / 2 || c->n[a] < 1)
+      return fail(TVDK_ERR_INVALID, "coarse extent n[%d] = %d must be fine / 2 = %d (>= 1)", a, c->n[a], f->n[a] / 2);
+  return 0;
+}
+
 }  // namespace tvdk
 
 #define TVDK_C_ENTRY(g, CALL)        \
@@ -1165,4 +1207,28 @@ int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coe
     return fail(TVDK_ERR_INVALID, "cg_fused is out-of-place in p and r");
   TVDK_C_ENTRY(g, (cgfused_impl<T, D>(g, omega, ell, p_in, r_in, p_out, r_out, x, alpha, beta, sum_out, workspace,
                                       workspace_bytes, stream)))
+}
+
+int tvdk_residual(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x,
+                  const void* rhs, void* r, void* workspace, size_t workspace_bytes, void* stream) {
+  if (r == x) return fail(TVDK_ERR_INVALID, "residual is out-of-place in x");
+  TVDK_C_ENTRY(g, (resid_impl<T, D>(g, omega, ell, x, rhs, r, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_mg_restrict(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, const void* x_fine, void* x_coarse,
+                     void* stream) {
+  TVDK_TRY(check_mg_pair(fine, coarse));
+  if (!x_fine || !x_coarse) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  int rc = 0;
+  TVDK_DISPATCH(*fine, rc = (mgxfer_impl<T, D, 0>(coarse, fine, x_fine, x_coarse, stream)));
+  return rc;
+}
+
+int tvdk_mg_prolong_add(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, const void* e_coarse, void* x_fine,
+                        void* stream) {
+  TVDK_TRY(check_mg_pair(fine, coarse));
+  if (!e_coarse || !x_fine) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  int rc = 0;
+  TVDK_DISPATCH(*fine, rc = (mgxfer_impl<T, D, 1>(fine, coarse, e_coarse, x_fine, stream)));
+  return rc;
 }

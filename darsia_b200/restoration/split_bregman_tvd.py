@@ -20,7 +20,7 @@ import numpy as np
 
 from .. import _cabi
 from ..engine import Engine, SolveInfo, SolverSpec
-from ..utils.linear_solvers import CG, Jacobi, Solver
+from ..utils.linear_solvers import CG, MG, TVDK_SOLVER_MG, Jacobi, Solver
 
 Coeff = Union[float, int, np.ndarray]
 
@@ -32,9 +32,9 @@ def _solver_spec(solver: Optional[Solver]) -> SolverSpec:
     if solver is None:
         solver = Jacobi()
     kind = getattr(solver, "kind", None)
-    if kind not in (_cabi.TVDK_SOLVER_JACOBI, _cabi.TVDK_SOLVER_CG):
+    if kind not in (_cabi.TVDK_SOLVER_JACOBI, _cabi.TVDK_SOLVER_CG, TVDK_SOLVER_MG):
         raise NotImplementedError(
-            f"inner solver {type(solver).__name__} is not implemented on the GPU (Jacobi and CG are); "
+            f"inner solver {type(solver).__name__} is not implemented on the GPU (Jacobi, CG and MG are); "
             "darsia_b200 has no CPU fallback"
         )
     maxiter = int(solver.maxiter)
@@ -147,6 +147,13 @@ def split_bregman_tvd(
         return (empty, None) if return_info else empty
     if return_state and adaptive is not None:
         raise NotImplementedError("return_state with an adaptive ell schedule (the state would need the final ell map)")
+    if spec.kind == TVDK_SOLVER_MG:
+        if isinstance(verbose, bool):
+            vevery = 1 if verbose else 0
+        else:
+            vevery = int(verbose) if verbose and verbose > 0 else 0
+        return _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic, solver, adaptive_mask,
+                                 cdtype, device, return_info, return_state, vevery)
     timing = os.environ.get("DARSIA_B200_TIMING") == "1"
     t_start = time.perf_counter()
     eng = Engine(spatial, nb=nb, dtype=cdtype, device=device, tile=tile)
@@ -214,6 +221,91 @@ def split_bregman_tvd(
     if timing:
         LAST_TIMINGS.update(upload=t_up - t_start, solve=t_solve - t_up, download=time.perf_counter() - t_solve)
     return (out, info) if return_info else out
+
+
+def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic, solver, adaptive_mask, cdtype,
+                      device, return_info, return_state, verbose_every):
+    """The outer loop with ``darsia.MG`` as the inner solver (``split_bregman_tvd.py:129-175`` around
+    ``mg.py:245-270``): host-driven, every step a libtvdk kernel on resident fields -- rhs
+    (``tvdk_rhs``), V-cycles (``darsia_b200/mg.py``), shrink + Bregman update + increment (``tvdk_shrink``)."""
+    import ctypes as C
+
+    import torch
+
+    from .._runtime import device_guard
+    from ..mg import MGHierarchy
+
+    if x0 is not None or adaptive_mask is not None or return_state:
+        raise NotImplementedError("MG as the inner solver: x0, adaptive and return_state are not implemented")
+    on_device = _is_tensor(img)
+    img_dtype = _np_dtype(img)
+    shape = tuple(img.shape)
+    nb = int(np.prod(shape[dim:], dtype=np.int64))
+    if nb > 1 and (eps is not None or solver.tol is not None):
+        # per-problem stopping (outer eps, MG tol): one problem at a time
+        outs, infos = [], []
+        flat = img.reshape(shape[:dim] + (nb,))
+        for b in range(nb):
+            sl = flat[..., b].contiguous() if on_device else np.ascontiguousarray(flat[..., b])
+            mu_b = mu
+            if not np.isscalar(mu) and tuple(getattr(mu, "shape", ())) == shape:
+                mu_b = mu.reshape(shape[:dim] + (nb,))[..., b]
+            o, inf = _split_bregman_mg(sl, mu_b, omega, ell, dim, max_num_iter, eps, None, isotropic, solver, None, cdtype,
+                                       device, True, False, verbose_every)
+            outs.append(o)
+            infos.append(inf)
+        out = (torch.stack(outs, dim=-1) if on_device else np.stack(outs, axis=-1)).reshape(shape)
+        info = SolveInfo(iters=np.concatenate([i.iters for i in infos]), inc=np.concatenate([i.inc for i in infos]),
+                         done=np.concatenate([i.done for i in infos]), history=None, energy=None,
+                         launched=max(i.launched for i in infos))
+        return (out, info) if return_info else out
+
+    eng = Engine(shape[:dim], nb=nb, dtype=cdtype, device=device)
+    lib, g = eng.lib, eng.geom
+    hier = MGHierarchy(eng, solver.depth, solver.smoother_iterations, omega, ell)
+    f = eng.upload(img)
+    u = f.clone()
+    t = eng.zero_fields(dim)
+    rhs = eng.empty_fields(1)
+    ws = eng.op_workspace()
+    wsp, wsn, tcs = ws.data_ptr(), ws.numel(), eng.batch_elems
+    (muc, k1), (omc, k2), (elc, k3) = eng.coef(mu, shape, "mu"), eng.coef(omega, shape, "omega"), eng.coef(ell, shape, "ell")
+    sums = torch.zeros(2 * nb, dtype=torch.float64, device=eng.device)
+    with device_guard(eng.device):
+        lib.check(lib.dot(C.byref(g), f.data_ptr(), f.data_ptr(), sums.data_ptr(), wsp, wsn, eng.stream()), "tvdk_dot")
+    nrm_f = torch.sqrt(sums[:nb].clone())  # split_bregman_tvd.py:58
+    hist, iters, inc = [], 0, None
+    for it in range(int(max_num_iter)):
+        with device_guard(eng.device):
+            if verbose_every and it % verbose_every == 0:
+                lib.check(lib.energy(C.byref(g), C.byref(muc), C.byref(omc), u.data_ptr(), f.data_ptr(), sums.data_ptr(),
+                                     wsp, wsn, eng.stream()), "tvdk_energy")
+                en = sums[: 2 * nb].cpu().numpy().reshape(nb, 2)
+                energy = 0.5 * en[:, 0] + en[:, 1]
+            lib.check(lib.rhs(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(omc), C.byref(elc), f.data_ptr(),
+                              t.data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, eng.stream()), "tvdk_rhs")  # :84-89
+        x = hier.solve(u, rhs, solver.maxiter, solver.tol)  # :133
+        with device_guard(eng.device):
+            lib.check(lib.shrink(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(elc), x.data_ptr(), u.data_ptr(),
+                                 u.data_ptr(), t.data_ptr(), t.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, eng.stream()),
+                      "tvdk_shrink")  # :136-146, :161, :170
+        inc_t = torch.sqrt(sums[:nb]) / nrm_f
+        iters += 1
+        if eps is not None or return_info or verbose_every:
+            inc = inc_t.cpu().numpy().copy()
+            hist.append(inc)
+            if verbose_every and it % verbose_every == 0:
+                for b in range(nb):
+                    print(f"Split Bregman iteration {it} - relative increment: {inc[b]}, energy functional: {energy[b]}")
+            if eps is not None and float(inc[0]) < eps:  # :173-175 (nb == 1 whenever eps is given)
+                break
+    out = eng.unpack(u, img_dtype).reshape(shape) if on_device else eng.download(u, img_dtype, shape)
+    if not return_info:
+        return out
+    inc = inc_t.cpu().numpy().copy() if iters else np.full(nb, np.nan)
+    info = SolveInfo(iters=np.full(nb, iters), inc=inc, done=np.array([eps is not None and bool(v < eps) for v in inc]),
+                     history=np.array(hist).reshape(-1, nb) if hist else None, energy=None, launched=iters)
+    return out, info
 
 
 def _is_tensor(x) -> bool:

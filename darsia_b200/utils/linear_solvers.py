@@ -1,6 +1,6 @@
-"""``darsia.Solver`` / ``darsia.Jacobi`` / ``darsia.CG`` with the reference's signatures.
+"""``darsia.Solver`` / ``darsia.Jacobi`` / ``darsia.CG`` / ``darsia.MG`` with the reference's signatures.
 
-Reference: ``utils/linear_solvers/solver.py:12-72``, ``jacobi.py:14-133``, ``cg.py:10-59``.
+Reference: ``utils/linear_solvers/solver.py:12-72``, ``jacobi.py:14-133``, ``cg.py:10-59``, ``mg.py:13-270``.
 Inside ``split_bregman_tvd`` the objects are *descriptors* (kind, ``maxiter``, ``tol``): the
 inner solves run inside ``libtvdk``'s kernels, never through ``__call__``.  ``__call__`` is
 still provided -- it solves ``mass_coeff * x - diffusion_coeff * laplace(x) = rhs`` on the GPU
@@ -172,3 +172,55 @@ class CG(Solver):
                       "tvdk_cg_update")
             rho_prev, rho = rho, float(dev_sum().sum())
         return eng.download(x, x0.dtype, x0.shape)
+
+
+TVDK_SOLVER_MG = 2  # host-composed (darsia_b200/mg.py); not a tvdk_solve kind
+
+
+class MG(Solver):
+    """V-cycle multigrid with Jacobi smoothing (``mg.py:13-270``), scalar coefficients.
+
+    Same constructor as the reference (``mg.py:25-35``).  The cycle runs on the GPU (``darsia_b200/mg.py``:
+    sweeps, residual, restriction, prolongation are libtvdk kernels; the recursion is host logic).
+    """
+
+    kind = TVDK_SOLVER_MG
+
+    def __init__(
+        self,
+        depth: int = 2,
+        smoother_iterations: int = 5,
+        maxiter: int = 100,
+        tol: Optional[float] = None,
+        dim: int = 2,
+        mass_coeff: Optional[Coeff] = None,
+        diffusion_coeff: Optional[Coeff] = None,
+        verbose=False,
+    ) -> None:
+        super().__init__(maxiter=maxiter, tol=tol, dim=dim, mass_coeff=mass_coeff, diffusion_coeff=diffusion_coeff,
+                         verbose=verbose)
+        self.depth = depth
+        self.smoother_iterations = smoother_iterations
+
+    def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
+        from ..engine import Engine
+        from ..mg import MGHierarchy
+
+        assert x0.shape == rhs.shape
+        if not np.issubdtype(x0.dtype, np.floating):
+            raise TypeError("float arrays only")
+        if x0.ndim > self.dim and self.tol is not None:
+            # with a tolerance every trailing-axis slice has its own stopping cycle
+            out = np.empty_like(x0)
+            for idx in np.ndindex(x0.shape[self.dim:]):
+                sel = (slice(None),) * self.dim + idx
+                out[sel] = self(np.ascontiguousarray(x0[sel]), np.ascontiguousarray(rhs[sel]))
+            return out
+        dtype = np.float32 if x0.dtype == np.float32 else np.float64
+        nb = int(np.prod(x0.shape[self.dim:], dtype=np.int64))
+        eng = Engine(x0.shape[: self.dim], nb=nb, dtype=dtype)
+        hier = MGHierarchy(eng, self.depth, self.smoother_iterations, self.mass_coeff, self.diffusion_coeff)
+        x = eng.upload(x0.astype(dtype, copy=False))
+        b = eng.upload(rhs.astype(dtype, copy=False))
+        res = hier.solve(x, b, self.maxiter, self.tol)
+        return eng.download(res, x0.dtype, x0.shape)

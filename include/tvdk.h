@@ -240,6 +240,19 @@ int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coe
                   const double* alpha, const double* beta, double* sum_out, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* Multigrid building blocks (darsia.MG, utils/linear_solvers/mg.py:94-242; the V-cycle itself is
+ * host logic over these and tvdk_jacobi_sweep):
+ *   tvdk_residual:        r = rhs - (omega x - ell Lap x)        (mg.py:212; pass ell / h^2 for spacing h)
+ *   tvdk_mg_restrict:     coarse = pairwise averages of fine     (mg.py:107-132; coarse extents = fine / 2)
+ *   tvdk_mg_prolong_add:  fine += repeat-twice(coarse), edge-padded for odd extents (mg.py:226-239)
+ * `fine` and `coarse` describe two grids of the same dim / dtype / nb. */
+int tvdk_residual(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x,
+                  const void* rhs, void* r, void* workspace, size_t workspace_bytes, void* stream);
+int tvdk_mg_restrict(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, const void* x_fine, void* x_coarse,
+                     void* stream);
+int tvdk_mg_prolong_add(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, const void* e_coarse, void* x_fine,
+                        void* stream);
+
 #ifdef __cplusplus
 }
 #endif

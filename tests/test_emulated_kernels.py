@@ -106,3 +106,37 @@ def test_state_round_trip_and_device_resident_io():
     assert isinstance(tout, torch.Tensor) and np.array_equal(tout.numpy(), out)
     tv = da.tvd(ti, method="heterogeneous bregman", weight=0.1, max_num_iter=3, eps=None, dim=2)
     assert isinstance(tv, torch.Tensor) and tv.shape == ti.shape
+
+from conftest import GOLDEN_DIR  # noqa: E402
+
+
+@pytest.mark.parametrize("tag,dim", [("2d", 2), ("3d", 3)])
+def test_mg_standalone_and_errors(tag, dim):
+    """darsia_b200.MG standalone (as H1_regularization would use it) against the reference's MG output; the
+    cases the GPU path refuses."""
+    with np.load(f"{GOLDEN_DIR}/operators.npz") as z:
+        x, rhs, ref = z[f"{tag}_x"], z[f"{tag}_rhs"], z[f"{tag}_mg2"]
+    mg = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
+    assert rel_l2(mg(x.copy(), rhs), ref) <= 1e-13
+    with pytest.raises(NotImplementedError):  # per-voxel coefficients (the reference block-averages them)
+        da.MG(dim=dim, mass_coeff=np.ones_like(x), diffusion_coeff=1.0)(x, rhs)
+    with pytest.raises(ValueError):  # a coarse grid would be empty (the reference crashes there)
+        da.MG(depth=3, dim=dim, mass_coeff=1.0, diffusion_coeff=1.0)(x, rhs)
+
+
+def test_mg_inner_solver_batched_and_stopping():
+    """MG inside split_bregman_tvd: channels are independent problems (batched without tol/eps, one at a time
+    with them) and the outer eps / MG tol stop each problem where the oracle stops it."""
+    from golden.generate_golden import phantom
+
+    img = phantom((24, 40, 2), 3)
+    kw = dict(mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=5)
+    mk = lambda m, **k: m.MG(depth=1, smoother_iterations=2, maxiter=3, **k)  # noqa: E731
+    ref = oracle.split_bregman_tvd(img, solver=mk(oracle), **kw)
+    assert rel_l2(da.split_bregman_tvd(img, solver=mk(da), **kw), ref) <= 1e-13
+    hist = []
+    kw2 = dict(kw, max_num_iter=40, eps=1e-2)
+    ref = oracle.split_bregman_tvd(img, solver=mk(oracle, tol=1e-2), history=hist, **kw2)
+    out, info = da.split_bregman_tvd(img, solver=mk(da, tol=1e-2), return_info=True, **kw2)
+    assert [len(h) for h in hist] == list(info.iters)
+    assert rel_l2(out, ref) <= 1e-13

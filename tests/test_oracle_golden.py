@@ -64,6 +64,20 @@ def test_operator_level(ops, tag, dim):
     assert rel_l2(cgh(x0=x, rhs=rhs), ops[f"{tag}_cg4_hetero"]) < 1e-13
 
 
+@pytest.mark.parametrize("tag,dim", [("2d", 2), ("3d", 3)])
+def test_mg_operator_level(ops, tag, dim):
+    """oracle.MG against the reference's MG (mg.py, run with the np.lib.pad shim): grid transfer, the
+    h-scaled operator and two V-cycles."""
+    x, rhs = ops[f"{tag}_x"], ops[f"{tag}_rhs"]
+    np.testing.assert_array_equal(oracle.mg_restriction(x, dim), ops[f"{tag}_mg_restrict"])
+    np.testing.assert_array_equal(oracle.mg_prolongation(oracle.mg_restriction(x, dim), dim), ops[f"{tag}_mg_prolong"])
+    mg = oracle.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
+    np.testing.assert_allclose(mg.operator(x, 2), ops[f"{tag}_mg_operator_h2"], rtol=0, atol=1e-15)
+    assert rel_l2(mg(x.copy(), rhs), ops[f"{tag}_mg2"]) < 1e-14
+    with pytest.raises(NotImplementedError):
+        oracle.MG(dim=dim, mass_coeff=np.ones_like(x), diffusion_coeff=1.0)(x, rhs)
+
+
 def test_oracle_cg_is_scipy_recurrence():
     """The written-out recurrence == scipy.sparse.linalg.cg (third party on this path)."""
     import scipy.sparse.linalg as spla
