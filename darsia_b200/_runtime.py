@@ -12,6 +12,9 @@ import torch
 from ._cabi import Library, get_library
 
 
+_CHECKED: set = set()  # device indices that passed tvdk_device_ok
+
+
 def resolve_device(device: Optional[Union[str, int, torch.device]] = None) -> torch.device:
     """Return the CUDA device to run on; raise if there is none (no CPU fallback).
 
@@ -35,9 +38,11 @@ def resolve_device(device: Optional[Union[str, int, torch.device]] = None) -> to
             raise ValueError(f"device must be a CUDA device, got {dev}")
         if dev.index is None:
             dev = torch.device("cuda", torch.cuda.current_device())
-    with torch.cuda.device(dev):
-        if not lib.device_ok():
-            raise RuntimeError(lib.last_error().decode())
+    if dev.index not in _CHECKED:  # once per device and process
+        with torch.cuda.device(dev):
+            if not lib.device_ok():
+                raise RuntimeError(lib.last_error().decode())
+        _CHECKED.add(dev.index)
     return dev
 
 

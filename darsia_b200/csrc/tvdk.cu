@@ -194,14 +194,16 @@ static int device_ok(char* msg, size_t n) {
     snprintf(msg, n, "no CUDA device: %s", cudaGetErrorString(e));
     return 0;
   }
-  cudaDeviceProp prop;
-  e = cudaGetDeviceProperties(&prop, dev);
+  // (cudaDeviceGetAttribute, not cudaGetDeviceProperties: the latter takes milliseconds per call)
+  int major = 0, minor = 0;
+  e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+  if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
   if (e != cudaSuccess) {
-    snprintf(msg, n, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    snprintf(msg, n, "cudaDeviceGetAttribute: %s", cudaGetErrorString(e));
     return 0;
   }
-  if (prop.major != 10) {
-    snprintf(msg, n, "libtvdk is built for sm_100a only; device %d is sm_%d%d", dev, prop.major, prop.minor);
+  if (major != 10) {
+    snprintf(msg, n, "libtvdk is built for sm_100a only; device %d is sm_%d%d", dev, major, minor);
     return 0;
   }
   return 1;

@@ -304,6 +304,8 @@ def h1_cases(da):
     store["vol_jac_tol"] = da.H1_regularization(vol.copy(), mu=1, omega=1, dim=3,
                                                 solver=da.Jacobi(maxiter=30, tol=1e-6))  # examples/regularization.py:33-40
     store["vol_cg"] = da.H1_regularization(vol.copy(), mu=0.5, omega=2.0, dim=3, solver=da.CG(maxiter=8, tol=0.0))
+    store["vol_mg"] = da.H1_regularization(vol.copy(), mu=1.0, omega=1.0, dim=3,
+                                           solver=da.MG(depth=1, smoother_iterations=3, maxiter=4))  # examples/regularization.py:39
     rgb = phantom((23, 31, 3), 52)
     store["rgb"] = rgb
     store["rgb_jac5"] = da.H1_regularization(rgb.copy(), mu=0.7, omega=1.0, dim=2, solver=da.Jacobi(maxiter=5))
@@ -321,11 +323,10 @@ def main():
         store = run_case(da, c)
         np.savez_compressed(os.path.join(OUT, c["name"] + ".npz"), **store)
         print(f"{c['name']:28s} shape={c['shape']} out_norm={np.linalg.norm(store['out']):.12g}")
-    if only and "operators" not in only:
-        return
-    np.savez_compressed(os.path.join(OUT, "operators.npz"), **operator_cases(da))
-    print("operators.npz written")
-    if only:
+    if not only or "operators" in only:
+        np.savez_compressed(os.path.join(OUT, "operators.npz"), **operator_cases(da))
+        print("operators.npz written")
+    if only and "h1" not in only:
         return
     np.savez_compressed(os.path.join(OUT, "h1.npz"), **h1_cases(da))
     print("h1.npz written")

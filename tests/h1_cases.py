@@ -10,6 +10,7 @@ CASES = {
     "vol_cg": ("vol", dict(mu=0.5, omega=2.0, dim=3), ("cg", dict(maxiter=8, tol=0.0))),
     "rgb_jac5": ("rgb", dict(mu=0.7, omega=1.0, dim=2), ("jacobi", dict(maxiter=5))),
     "rgb_jac_tol": ("rgb", dict(mu=0.7, omega=1.0, dim=2), ("jacobi", dict(maxiter=40, tol=1e-3))),
+    "vol_mg": ("vol", dict(mu=1.0, omega=1.0, dim=3), ("mg", dict(depth=1, smoother_iterations=3, maxiter=4))),
 }
 
 
@@ -20,5 +21,5 @@ def load():
 
 def run(api, data, name):
     src, kw, (kind, skw) = CASES[name]
-    solver = {"jacobi": api.Jacobi, "cg": api.CG}[kind](**skw)
+    solver = {"jacobi": api.Jacobi, "cg": api.CG, "mg": api.MG}[kind](**skw)
     return api.H1_regularization(data[src].copy(), solver=solver, **kw), data[name]
