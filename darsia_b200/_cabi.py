@@ -138,6 +138,7 @@ SIGNATURES = {
     "tvdk_cg_init": (C.c_int, [_PG, _I, _PC, _PC, _PC, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_pq": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _I, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_update": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "tvdk_jacobi_sweeps": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _I, C.POINTER(C.c_int), _VP, _SZ, _VP]),
     "tvdk_residual": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_mg_restrict": (C.c_int, [_PG, _PG, _VP, _VP, _VP]),
     "tvdk_mg_prolong_add": (C.c_int, [_PG, _PG, _VP, _VP, _VP]),

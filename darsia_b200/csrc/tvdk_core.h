@@ -334,10 +334,10 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
 // inside the image take a fast path without any per-element boundary selects (`edge == false`).
 // LH / RH: halo rows below / above along y (3-D); LHX / RHX: halo VECTORS left / right along x (a
 // vector already holds >= 2 elements, so one vector covers an element halo of up to 2).
-template <typename T, int D, int LH, int RH, int LHX_ = -1>
+template <typename T, int D, int LH, int RH, int LHX_ = -1, int RHX_ = -1>
 struct Col {
   static constexpr int V = Vec<T>::N;
-  static constexpr int RHX = RH > 0 ? 1 : 0;
+  static constexpr int RHX = RHX_ < 0 ? (RH > 0 ? 1 : 0) : RHX_;
   static constexpr int LHX = LHX_ < 0 ? LH : LHX_;
   int X, Y, b;      // global coordinates of the first element of the thread's vector; problem
   int soff;         // shared-memory element offset of the vector inside one row array
@@ -1168,6 +1168,126 @@ struct KSweep {
 };
 
 // ==========================================================================================
+// K4xS  S Jacobi sweeps in ONE pass (temporal blocking; scalar coefficients, no tol branch):
+//         x^(s) = rhs/diag + N(x^(s-1))/(diag/ell),  s = 1..S          (jacobi.py:109-114)
+//     Stage s runs one plane behind stage s-1: at march step j it forms x^(s) of plane j-s+1 from
+//     the three planes of x^(s-1) it keeps in registers and the in-plane neighbours that stage s-1
+//     published one step earlier (one barrier per plane for all stages).  x and rhs are read once
+//     and x written once per S sweeps: 3/S instead of 3 words per voxel and sweep.  The price is a
+//     halo of S cells (rows / elements) around every tile and 2(S-1) extra planes per chunk.
+//     Shared rows: [2 s + slot] = x^(s) of the plane stage s wrote last (s = 0: the input).
+// ==========================================================================================
+template <typename T, int D, int S>
+struct KSweepN {
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = S, RH = S, NRED = 0, NROWS = 2 * S;
+  static constexpr int HX = (S + V - 1) / V;  // halo vectors left / right
+  static constexpr int PF2D = 3, PF3D = 3;
+  static constexpr int ZC2D = 64;
+  typedef Col<T, D, LH, RH, HX, HX> C;
+  struct Args {
+    Geom g;
+    Coefs<T> k;
+    const T* x_in;
+    const T* rhs;
+    T* x_out;
+    const tvdk_stat_t* skip;  // done
+    Fin fin;
+  };
+  C c;
+  int j, rowe, zlast;
+  Vec<T> xs[S][2];    // xs[s][0], xs[s][1] = x^(s) at planes (j-s-1), (j-s): the two older planes stage s+1 needs
+  Vec<T> rh[S];       // rhs at planes j, j-1, .., j-S+1
+  Vec<T> nx_x, nx_r;  // x^(0)(j+1) and rhs(j+1) loaded one step ahead
+  double red[1];
+
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
+    if (a.skip && a.skip[lc.bz].done) return false;
+    c.setup(a.g, lc);
+    rowe = C::row_elems(lc.ntx, lc.nty);
+    // first plane any stage touches / last march step (clamped to the planes that exist)
+    int zs = c.z0 - (S - 1);
+    if (zs < 0) zs = 0;
+    zlast = c.z1 - 1 + (S - 1);
+    j = zs;
+    const long long o = c.at(a.g, j);
+    c.cur = o;
+    const Vec<T> x0 = ldo(a.x_in, o);
+#pragma unroll
+    for (int s = 0; s < S; ++s) {
+      xs[s][0] = x0;
+      xs[s][1] = x0;
+      rh[s] = x0;
+    }
+    xs[0][0] = c.has_zlo(a.g, j) ? ldo(a.x_in, o - c.s0b) : x0;
+    nx_r = ldo(a.rhs, o);
+    nx_x = c.has_zhi(a.g, j) ? ldo(a.x_in, o + c.s0b) : x0;
+    return true;
+  }
+  TVDK_DEV bool more() const { return j <= zlast; }
+
+  // pre: plane j of the input becomes current (x^(0)(j) = xs[0][1]); publish its row; prefetch
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if (!c.plane_ok(a.g, j)) return;  // past the last plane: only the later stages still run
+    sst(srow<T>(smem, 0 + (j & 1), rowe), c, xs[0][1]);
+  }
+
+  // (the axis-0 boundary is resolved explicitly per stage below, so only the in-plane position of the
+  //  block decides between the select-free and the general path)
+  template <bool E>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
+    // roll rhs history: rh[0] = rhs(j)
+#pragma unroll
+    for (int s = S - 1; s > 0; --s) rh[s] = rh[s - 1];
+    rh[0] = nx_r;
+    const bool have0 = c.plane_ok(a.g, j);
+    Vec<T> hi = have0 && c.has_zhi(a.g, j) ? nx_x : xs[0][1];  // x^(0)(j+1)
+    if (have0 && j + 1 <= zlast && c.plane_ok(a.g, j + 1)) {      // loads for the next step
+      nx_r = ldo(a.rhs, c.cur + c.s0b);
+      if (c.has_zhi(a.g, j + 1)) nx_x = ldo(a.x_in, c.cur + 2 * c.s0b);
+    }
+    if (c.pf_ok(j)) {
+      pfo(a.rhs, c.cur + c.pfb);
+      pfo(a.x_in, c.cur + c.pfb);
+    }
+    // stage s (1-based) forms x^(s) of plane p = j - (s - 1) from x^(s-1) at p-1, p, p+1
+#pragma unroll
+    for (int s = 1; s <= S; ++s) {
+      const int p = j - (s - 1);
+      // x^(s-1): lo = xs[s-1][0] (plane p-1), cen = xs[s-1][1] (plane p), hi (plane p+1, just formed / loaded)
+      const bool ok = p >= 0 && p < a.g.n0;  // whole volumes only (tvdk_solve)
+      Vec<T> y = xs[s - 1][1];
+      if (ok) {
+        const Vec<T> lo = xs[s - 1][0], cen = xs[s - 1][1];
+        const Vec<T> up = (p + 1 < a.g.n0) ? hi : cen;
+        const Vec<T> dn = (p > 0) ? lo : cen;
+        const Vec<T> nb = nsum<T, D, E>(c, dn, up, cen, srow<T>(smem, 2 * (s - 1) + (p & 1), rowe));
+#pragma unroll
+        for (int v = 0; v < V; ++v) y.v[v] = rh[s - 1].v[v] * a.k.sc.inv_diag + nb.v[v] * a.k.sc.c_nb;
+        if (s < S) {
+          sst(srow<T>(smem, 2 * s + (p & 1), rowe), c, y);
+        } else if (p >= c.z0 && p < c.z1) {
+          sto(c, a.x_out, c.at(a.g, p), y);
+        }
+      }
+      // roll stage s-1's window, hand the new plane to the next stage
+      xs[s - 1][0] = xs[s - 1][1];
+      xs[s - 1][1] = hi;
+      hi = y;
+    }
+    c.cur += c.s0b;
+    ++j;
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (c.edge)
+      post_t<true>(a, smem);
+    else
+      post_t<false>(a, smem);
+  }
+  static TVDK_DEV void finalize(const Args&, int, const double*) {}
+};
+
+// ==========================================================================================
 // K5/K6  CG iteration (scipy.sparse.linalg.cg recurrence, called from cg.py:50-56)
 //   PQ:     p_out = first ? r : beta p_in + r ;  reduce p_out . (A p_out)
 //   UPDATE: x += alpha p ; r -= alpha (A p) ;    reduce r . r      (q = A p is recomputed,
@@ -1349,6 +1469,7 @@ struct KCgFused {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 2, RH = 2, NRED = 4, NROWS = 4;
   static constexpr int PF2D = 3, PF3D = 2;
+  static constexpr int ZC2D = 48;  // planes per CTA: 6 extra planes are read per chunk (0.92 vs 0.90 at 32)
   typedef Col<T, D, LH, RH, 1> C;
   struct Args {
     Geom g;

@@ -81,6 +81,14 @@ static int prefetch_sub() {
   return v;
 }
 template <class K, typename = void>
+struct KernelZc {
+  static int get(int) { return 32; }
+};
+template <class K>
+struct KernelZc<K, std::void_t<decltype(K::ZC2D)>> {
+  static int get(int dim) { return dim == 2 ? K::ZC2D : 32; }
+};
+template <class K, typename = void>
 struct KernelPf {
   static int get(int) { return 0; }
 };
@@ -214,6 +222,10 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     zc = (int)((nz + want - 1) / want);
     zc = std::max(zc, 8);
     zc = std::min(zc, 32);
+    // kernels with a deep chunk prologue (K7 re-reads 6 planes per chunk) prefer longer chunks as long
+    // as a problem alone still fills the GPU several times over
+    const int pref = KernelZc<K>::get(D);
+    if (pref > zc && tiles * ((nz + pref - 1) / pref) >= 148LL * 8) zc = pref;
   }
   zc = std::min(zc, nz);
   g.zchunk = zc;
@@ -275,7 +287,7 @@ static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_ti
   LaunchCfg L = plan_launch<K, T, D>(g, tune, big_tile);
   a.g = L.g;
   a.g.pf = prefetch_override() >= 0 ? prefetch_override() : KernelPf<K>::get(D);
-  if ((size_t)L.gx * L.gy * L.gz * (K::NRED > 0 ? K::NRED : 1) > sc.partial_cap)
+  if (K::NRED > 0 && (size_t)L.gx * L.gy * L.gz * K::NRED > sc.partial_cap)
     return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
   ++g_launches;
   return backend::launch<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
@@ -607,6 +619,29 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
         TVDK_TRY(launch_rhs_sweep(cur, expl_now, RB, XA, fn));
       }
       for (int s = s_first; s <= p->solver_maxiter; ++s) {
+        // temporal blocking: S sweeps per pass wherever the plain recurrence allows it (scalar
+        // coefficients, no tol branch): 4 at a time in 2-D, 2 at a time in 3-D
+        if (!tolmode && !het0 && p->fused && s > 1) {
+          const int rem = p->solver_maxiter - s + 1;
+          const int S = (D == 2 && rem >= 4) ? 4 : (rem >= 2 ? 2 : 1);
+          if (S > 1) {
+            auto go = [&](auto SS) {
+              typedef KSweepN<T, D, decltype(SS)::value> K;
+              typename K::Args a;
+              memset(&a, 0, sizeof a);
+              a.k = k0; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
+              return run<K, T, D>(a, g, tune, true, sc, stream);
+            };
+            if (S == 4)
+              TVDK_TRY(go(std::integral_constant<int, 4>{}));
+            else
+              TVDK_TRY(go(std::integral_constant<int, 2>{}));
+            std::swap(xin, xout);  // (s > 1: both are XA / XB here)
+            out_id = 3 - out_id;
+            s += S - 1;
+            continue;
+          }
+        }
         TVDK_TRY(dispatch2(het0, false, [&](auto H, auto) {
           typedef KSweep<T, D, decltype(H)::value> K;
           typename K::Args a;
@@ -616,7 +651,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
             a.fin.kind = FIN_JTOL; a.fin.stats = st; a.fin.tol = p->solver_tol; a.fin.buf_id = out_id;
             a.fin.first_sweep = (s == 1);
           }
-          return run<K, T, D>(a, g, tune, false, sc, stream);
+          return run<K, T, D>(a, g, tune, true, sc, stream);  // 3-D: 16-row tiles (profiles/r1_tile3d.txt)
         }));
         if (s == 1) {
           xin = XA;
@@ -1070,6 +1105,45 @@ static int cgfused_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk
 }
 
 template <typename T, int D>
+static int sweeps_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, void* xa, const void* rhs,
+                       void* xb, int n, int* result_in_b, void* ws, size_t wsb, void* stream) {
+  OpCtx<T, D> o;
+  TVDK_TRY(o.init(gg, ws, wsb, stream));
+  const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
+  const bool het = k.sc.hetero != 0;
+  T* src = (T*)xa;
+  T* dst = (T*)xb;
+  for (int rem = n; rem > 0;) {
+    const int S = het ? 1 : ((D == 2 && rem >= 4) ? 4 : (rem >= 2 ? 2 : 1));
+    if (S == 1) {
+      TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
+        typedef KSweep<T, D, decltype(H)::value> K;
+        typename K::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.x_in = src; a.rhs = (const T*)rhs; a.x_out = dst; a.fin = no_fin();
+        return run<K, T, D>(a, o.g, o.tune, true, o.sc, stream);
+      }));
+    } else {
+      auto go = [&](auto SS) {
+        typedef KSweepN<T, D, decltype(SS)::value> K;
+        typename K::Args a;
+        memset(&a, 0, sizeof a);
+        a.k = k; a.x_in = src; a.rhs = (const T*)rhs; a.x_out = dst; a.fin = no_fin();
+        return run<K, T, D>(a, o.g, o.tune, true, o.sc, stream);
+      };
+      if (S == 4)
+        TVDK_TRY(go(std::integral_constant<int, 4>{}));
+      else
+        TVDK_TRY(go(std::integral_constant<int, 2>{}));
+    }
+    std::swap(src, dst);
+    rem -= S;
+  }
+  if (result_in_b) *result_in_b = (src == (T*)xb) ? 1 : 0;
+  return 0;
+}
+
+template <typename T, int D>
 static int resid_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, const void* x,
                       const void* rhs, void* r, void* ws, size_t wsb, void* stream) {
   OpCtx<T, D> o;
@@ -1231,4 +1305,15 @@ int tvdk_mg_prolong_add(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, cons
   int rc = 0;
   TVDK_DISPATCH(*fine, rc = (mgxfer_impl<T, D, 1>(fine, coarse, e_coarse, x_fine, stream)));
   return rc;
+}
+
+int tvdk_jacobi_sweeps(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, void* xa,
+                       const void* rhs, void* xb, int nsweeps, int* result_in_b, void* workspace,
+                       size_t workspace_bytes, void* stream) {
+  if (!xa || !xb || !rhs || xa == xb) return fail(TVDK_ERR_INVALID, "jacobi_sweeps needs two distinct iterate buffers");
+  if (nsweeps < 0) return fail(TVDK_ERR_INVALID, "nsweeps must be >= 0");
+  if (g && (g->z_begin != 0 || g->z_end != g->n[0] || g->g0_off != 0 || g->g0_n != g->n[0]))
+    return fail(TVDK_ERR_INVALID, "jacobi_sweeps works on whole volumes (slabs sweep one at a time)");
+  TVDK_C_ENTRY(g, (sweeps_impl<T, D>(g, omega, ell, xa, rhs, xb, nsweeps, result_in_b, workspace, workspace_bytes,
+                                     stream)))
 }

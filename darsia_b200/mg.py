@@ -61,19 +61,23 @@ class MGHierarchy:
 
     # -- building blocks ---------------------------------------------------------------------
     def _smooth(self, lv: int, x: torch.Tensor, rhs: torch.Tensor) -> torch.Tensor:
-        """``smoother_iterations`` Jacobi sweeps starting from ``x`` (not modified); returns the buffer
-        holding the result (``xa[lv]`` or ``xb[lv]``)."""
+        """``smoother_iterations`` Jacobi sweeps starting from ``x`` (an external ``x`` is not modified);
+        returns the buffer holding the result (``xa[lv]`` or ``xb[lv]``).  ``tvdk_jacobi_sweeps`` blocks
+        the sweeps temporally (4 per pass in 2-D, 2 in 3-D)."""
         e, lib = self.levels[lv], self.lib
         ws = e.op_workspace()
-        src = x
-        for k in range(self.nsmooth):
-            dst = self.xa[lv] if (src is not self.xa[lv]) else self.xb[lv]
-            with device_guard(e.device):
-                rc = lib.jacobi_sweep(C.byref(e.geom), C.byref(self.om[lv]), C.byref(self.el[lv]), src.data_ptr(),
-                                      rhs.data_ptr(), dst.data_ptr(), ws.data_ptr(), ws.numel(), e.stream())
-            lib.check(rc, "tvdk_jacobi_sweep")
-            src = dst
-        return src
+        a, b = self.xa[lv], self.xb[lv]
+        if x is b:
+            a, b = b, a
+        elif x is not a:
+            a.copy_(x)
+        in_b = C.c_int(0)
+        with device_guard(e.device):
+            rc = lib.jacobi_sweeps(C.byref(e.geom), C.byref(self.om[lv]), C.byref(self.el[lv]), a.data_ptr(),
+                                   rhs.data_ptr(), b.data_ptr(), self.nsmooth, C.byref(in_b), ws.data_ptr(), ws.numel(),
+                                   e.stream())
+        lib.check(rc, "tvdk_jacobi_sweeps")
+        return b if in_b.value else a
 
     def _vcycle(self, lv: int, x0: torch.Tensor, rhs: torch.Tensor, depth: int) -> torch.Tensor:
         """``base_V_Cycle`` (mg.py:194-243) on level ``lv``; returns the buffer holding the result."""

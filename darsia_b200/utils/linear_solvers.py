@@ -96,6 +96,12 @@ class Jacobi(Solver):
         x0n = None
         if self.tol is not None:
             x0n = float(np.linalg.norm(x0))
+        if self.tol is None:  # fixed count: one call, temporally blocked sweeps
+            in_b = C.c_int(0)
+            rc = lib.jacobi_sweeps(C.byref(eng.geom), C.byref(om), C.byref(el), x.data_ptr(), b.data_ptr(), y.data_ptr(),
+                                   int(self.maxiter), C.byref(in_b), ws.data_ptr(), ws.numel(), eng.stream())
+            lib.check(rc, "tvdk_jacobi_sweeps")
+            return eng.download(y if in_b.value else x, x0.dtype, x0.shape)
         dsum = torch.zeros(eng.nb, dtype=torch.float64, device=eng.device)
         for _ in range(self.maxiter):
             rc = lib.jacobi_sweep(C.byref(eng.geom), C.byref(om), C.byref(el), x.data_ptr(), b.data_ptr(),

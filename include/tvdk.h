@@ -240,6 +240,13 @@ int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coe
                   const double* alpha, const double* beta, double* sum_out, void* workspace,
                   size_t workspace_bytes, void* stream);
 
+/* n Jacobi sweeps (jacobi.py:109-114, no tol branch) ping-ponging between xa (in: the start iterate) and
+ * xb; with scalar coefficients they are temporally blocked (4 per pass in 2-D, 2 per pass in 3-D).
+ * *result_in_b tells which buffer holds the result; the other one is scratch afterwards. */
+int tvdk_jacobi_sweeps(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, void* xa,
+                       const void* rhs, void* xb, int nsweeps, int* result_in_b, void* workspace,
+                       size_t workspace_bytes, void* stream);
+
 /* Multigrid building blocks (darsia.MG, utils/linear_solvers/mg.py:94-242; the V-cycle itself is
  * host logic over these and tvdk_jacobi_sweep):
  *   tvdk_residual:        r = rhs - (omega x - ell Lap x)        (mg.py:212; pass ell / h^2 for spacing h)

@@ -90,3 +90,32 @@ def run_cg_fixed_pair(da, oracle, shape, dim, tile, m, iso, het, dtype, batch, f
     out = da.split_bregman_tvd(img, dim=dim, max_num_iter=6, isotropic=iso, solver=da.CG(maxiter=m, tol=0.0),
                                tile=tile, fused=(2 if fused else False), **kw)  # 2: single-pass also in 3-D
     return out, ref
+
+
+def jacobi_blocked_cases():
+    """(shape, dim, tile, sweeps, isotropic, dtype, batch): Jacobi(maxiter=K >= 2) with scalar coefficients
+    runs temporally blocked passes (4 / 2 sweeps per pass); thin extents and tiny tiles put every stage of the
+    pipeline on a boundary or a seam."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((37, 150), 2, (32, 0, 5), 20, False, f8, ()),
+        ((37, 150), 2, (32, 0, 7), 6, True, f8, (2,)),
+        ((37, 150), 2, (32, 0, 5), 3, False, f8, ()),
+        ((37, 150), 2, (32, 0, 5), 5, False, f4, ()),
+        ((11, 19, 70), 3, (8, 8, 3), 5, False, f8, ()),
+        ((11, 19, 70), 3, (8, 10, 4), 4, True, f4, ()),
+        ((9, 5, 6), 3, (0, 0, 0), 7, False, f8, ()),
+        ((3, 40), 2, (0, 0, 0), 9, False, f8, ()),
+        ((1, 40), 2, (0, 0, 0), 6, False, f8, ()),
+        ((2, 1, 7), 3, (0, 0, 0), 3, False, f8, ()),
+        ((70, 300), 2, (0, 0, 0), 20, False, f8, ()),
+    ]
+
+
+def run_jacobi_blocked_pair(da, oracle, shape, dim, tile, K, iso, dtype, batch):
+    img = phantom(tuple(shape) + tuple(batch), 5, dtype)
+    kw = dict(mu=0.1, omega=0.5, ell=1.0, dim=dim, max_num_iter=4, isotropic=iso)
+    ref = oracle.split_bregman_tvd(img, solver=oracle.Jacobi(maxiter=K), **kw)
+    out = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, **kw)
+    one = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, fused=False, **kw)
+    return out, one, ref

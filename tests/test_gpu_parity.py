@@ -9,8 +9,8 @@ import pytest
 
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
-from parity_cases import (adaptive_cases, cg_fixed_count_cases, run_adaptive_pair, run_cg_fixed_pair, run_pair,
-                          small_grid)
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, jacobi_blocked_cases, run_adaptive_pair,
+                          run_cg_fixed_pair, run_jacobi_blocked_pair, run_pair, small_grid)
 
 pytestmark = pytest.mark.gpu
 
@@ -46,6 +46,15 @@ def test_golden(da, name):
 def test_cg_fixed_count_single_pass_and_two_pass(da, shape, dim, tile, m, iso, het, dtype, batch, fused):
     """CG(tol=0): the single-pass route (fused=True, K7) and the two-kernel route agree with the oracle."""
     out, ref = run_cg_fixed_pair(da, oracle, shape, dim, tile, m, iso, het, dtype, batch, fused=fused)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+
+
+@pytest.mark.parametrize("shape,dim,tile,K,iso,dtype,batch", jacobi_blocked_cases())
+def test_jacobi_sweeps_temporally_blocked(da, shape, dim, tile, K, iso, dtype, batch):
+    """Jacobi(K): S sweeps per pass (K4xS) == one sweep per pass, bitwise (same arithmetic per voxel), and
+    both agree with the oracle."""
+    out, one, ref = run_jacobi_blocked_pair(da, oracle, shape, dim, tile, K, iso, dtype, batch)
+    np.testing.assert_array_equal(out, one)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
 
 

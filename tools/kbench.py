@@ -90,6 +90,8 @@ def main():
         "shrink": (2 + 2 * dim, lambda: lib.shrink(bg, 1, bm, be, u.data_ptr(), u2.data_ptr(), None, t.data_ptr(),
                                                    t2.data_ptr(), eng.batch_elems, sums.data_ptr(), *ws(), s)),
         "sweep": (3, lambda: lib.jacobi_sweep(bg, bo, be, u.data_ptr(), f.data_ptr(), u2.data_ptr(), *ws(), s)),
+        "sweep_x4": (3 / 4, lambda: lib.jacobi_sweeps(bg, bo, be, u.data_ptr(), f.data_ptr(), u2.data_ptr(), 4, None, *ws(), s)),
+        "sweep_x2": (3 / 2, lambda: lib.jacobi_sweeps(bg, bo, be, u.data_ptr(), f.data_ptr(), u2.data_ptr(), 2, None, *ws(), s)),
         "matvec": (2, lambda: lib.cg_matvec(bg, bo, be, u.data_ptr(), u2.data_ptr(), *ws(), s)),
         "dot": (2, lambda: lib.dot(bg, u.data_ptr(), f.data_ptr(), sums.data_ptr(), *ws(), s)),
         "fj1_iso": (3 + 2 * dim + nh, lambda: lib.fused_jacobi1(bg, 1, bm, bo, be, f.data_ptr(), u.data_ptr(),
@@ -116,8 +118,9 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.reps
-            gbs = words * W * N / (ms * 1e-3) / 1e9
-            print(f"{name:10s} shape={shape} nb={args.nb} {dt.name} tile=({tx},{ty},{zc}) {ms:8.4f} ms  "
+            nsw = {"sweep_x4": 4, "sweep_x2": 2}.get(name, 1)  # per SWEEP for the blocked passes
+            gbs = words * nsw * W * N / (ms * 1e-3) / 1e9
+            print(f"{name:10s} shape={shape} nb={args.nb} {dt.name} tile=({tx},{ty},{zc}) {ms / nsw:8.4f} ms  "
                   f"{gbs:7.1f} GB/s algo ({words} words)  {gbs / peak:5.3f} of measured peak", flush=True)
     lib.set_tune(0, 0, 0)
 
