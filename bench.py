@@ -61,7 +61,7 @@ DEFAULT_WORKLOAD = "cfg2_2d_iso_cg10"
 MU, OMEGA, ELL = 0.1, 1.0, 1.0
 
 
-def algo_words_per_voxel_iter(dim: int, solver, hetero_arrays: int = 0, single_pass: bool = True) -> float:
+def algo_words_per_voxel_iter(dim: int, solver, hetero_arrays: int = 0, single_pass: bool = True, big: bool = True) -> float:
     """Algorithmic words per voxel and outer iteration of the IMPLEMENTED formulation
     (compressed state t, q = A p recomputed)."""
     kind, m, _ = solver
@@ -74,7 +74,7 @@ def algo_words_per_voxel_iter(dim: int, solver, hetero_arrays: int = 0, single_p
         # shrink: read u+ u t(D), write u t(D)
         rem, passes = m - 1, 0
         while rem > 0:
-            s_ = 1 if (hetero_arrays or not single_pass) else (4 if (D == 2 and rem >= 4) else (2 if rem >= 2 else 1))
+            s_ = 1 if (hetero_arrays or not single_pass or D != 2 or rem < 2) else (4 if (rem >= 4 and big) else 2)
             rem -= s_
             passes += 1
         return (2 + D + 2) + 3 * passes + (2 + D + 1 + D)
@@ -410,7 +410,7 @@ def run_ours(args, w, wname):
             return lib.cg_update(C.byref(g), C.byref(omc), C.byref(elc), p_.data_ptr(), x_.data_ptr(), r_.data_ptr(),
                                  coef.data_ptr(), sums.data_ptr(), ws.data_ptr(), ws.numel(), eng.stream())
     elif kind == "jacobi" and m >= 2:
-        nsw = 1 if n_het else (4 if (dim == 2 and m >= 5) else 2)
+        nsw = 1 if (n_het or dim != 2) else (4 if (m >= 5 and int(np.prod(w["shape"])) >= (1 << 23)) else 2)
         dom_name, dom_words, dom_key = f"jacobi sweeps, {nsw} per pass (x = rhs/diag + N(x)/(diag/ell))", 3, "jacobi_sweeps"
         xa_, xb_ = eng.upload(pinned_np), eng.empty_fields(1)
 
@@ -440,7 +440,7 @@ def run_ours(args, w, wname):
     peak, peak_src = measured_peak()
     dom_bytes = dom_words * W * nvox_step
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
-    words_iter = algo_words_per_voxel_iter(dim, w["solver"], n_het)
+    words_iter = algo_words_per_voxel_iter(dim, w["solver"], n_het, big=int(np.prod(w["shape"])) >= (1 << 23))
     step_bytes = words_iter * W * nvox_step * outer
     step_gbs = step_bytes / (ms_per_step * 1e-3) / 1e9
     survey_words = {"cg": 8 + 5 * dim + 10 * m, "jacobi": (3 + 4 * dim) if m == 1 else (3 * m + 2 + 5 * dim)}[kind] + n_het

@@ -357,7 +357,8 @@ struct Col {
 
   static TVDK_HD int iw(int ntx) { return (ntx - LHX - RHX) * V; }
   static TVDK_HD int ih(int nty) { return D == 3 ? nty - LH - RH : 1; }
-  static TVDK_HD int row_elems(int ntx, int nty) { return (nty + 2) * (ntx + 2) * V; }
+  // (2-D: a single row with one vector of padding left and right -- no y neighbours to serve)
+  static TVDK_HD int row_elems(int ntx, int nty) { return D == 3 ? (nty + 2) * (ntx + 2) * V : (ntx + 2) * V; }
 
   TVDK_DEV void setup(const Geom& g, const LaunchCtx& lc) {
     const int xt = lc.bx % g.xtiles, yt = lc.bx / g.xtiles;
@@ -389,7 +390,7 @@ struct Col {
     hylo = Y > 0;
     hyhi = Y < g.ny - 1;
     spitch = (lc.ntx + 2) * V;
-    soff = (lc.ty + 1) * spitch + (lc.tx + 1) * V;
+    soff = (D == 3 ? (lc.ty + 1) * spitch : 0) + (lc.tx + 1) * V;
     const int Xc = X < 0 ? 0 : (X > g.pitch - V ? g.pitch - V : X);
     const int Yc = Y < 0 ? 0 : (Y > g.ny - 1 ? g.ny - 1 : Y);
     constexpr long long W = (long long)sizeof(T);
@@ -1210,6 +1211,7 @@ struct KSweepN {
     if (zs < 0) zs = 0;
     zlast = c.z1 - 1 + (S - 1);
     j = zs;
+    zs0 = zs;
     const long long o = c.at(a.g, j);
     c.cur = o;
     const Vec<T> x0 = ldo(a.x_in, o);
@@ -1226,25 +1228,37 @@ struct KSweepN {
   }
   TVDK_DEV bool more() const { return j <= zlast; }
 
-  // pre: plane j of the input becomes current (x^(0)(j) = xs[0][1]); publish its row; prefetch
+  // The sm_100a runner unrolls the march loop by two (UNROLL2): the phase PH = (j - zs) & 1 is a
+  // compile-time constant there, so every double-buffer slot below is an immediate and the window
+  // rolls are renamed away across the two copies of the body.
+  static constexpr bool UNROLL2 = true;
+  int zs0;  // first march step (slot parity is counted from it)
   TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if ((j - zs0) & 1) pre_p<1>(a, smem); else pre_p<0>(a, smem);
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if ((j - zs0) & 1) post_p<1>(a, smem); else post_p<0>(a, smem);
+  }
+  // pre: plane j of the input becomes current (x^(0)(j) = xs[0][1]); publish its row
+  template <int PH>
+  TVDK_DEV void pre_p(const Args& a, unsigned char* smem) {
     if (!c.plane_ok(a.g, j)) return;  // past the last plane: only the later stages still run
-    sst(srow<T>(smem, 0 + (j & 1), rowe), c, xs[0][1]);
+    sst(srow<T>(smem, 0 + PH, rowe), c, xs[0][1]);
   }
 
-  // (the axis-0 boundary is resolved explicitly per stage below, so only the in-plane position of the
-  //  block decides between the select-free and the general path)
-  template <bool E>
+  // E: the block touches the in-plane boundary; ZE: some plane a stage touches in this step is missing or
+  // lies on the axis-0 boundary (block-uniform), otherwise every stage runs select-free
+  template <bool E, bool ZE, int PH>
   TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
     // roll rhs history: rh[0] = rhs(j)
 #pragma unroll
     for (int s = S - 1; s > 0; --s) rh[s] = rh[s - 1];
     rh[0] = nx_r;
-    const bool have0 = c.plane_ok(a.g, j);
-    Vec<T> hi = have0 && c.has_zhi(a.g, j) ? nx_x : xs[0][1];  // x^(0)(j+1)
-    if (have0 && j + 1 <= zlast && c.plane_ok(a.g, j + 1)) {      // loads for the next step
+    const bool have0 = ZE ? c.plane_ok(a.g, j) : true;
+    Vec<T> hi = (!ZE || (have0 && c.has_zhi(a.g, j))) ? nx_x : xs[0][1];  // x^(0)(j+1)
+    if (have0 && j + 1 <= zlast && (!ZE || c.plane_ok(a.g, j + 1))) {    // loads for the next step
       nx_r = ldo(a.rhs, c.cur + c.s0b);
-      if (c.has_zhi(a.g, j + 1)) nx_x = ldo(a.x_in, c.cur + 2 * c.s0b);
+      if (j + 2 < a.g.n0) nx_x = ldo(a.x_in, c.cur + 2 * c.s0b);
     }
     if (c.pf_ok(j)) {
       pfo(a.rhs, c.cur + c.pfb);
@@ -1254,20 +1268,20 @@ struct KSweepN {
 #pragma unroll
     for (int s = 1; s <= S; ++s) {
       const int p = j - (s - 1);
-      // x^(s-1): lo = xs[s-1][0] (plane p-1), cen = xs[s-1][1] (plane p), hi (plane p+1, just formed / loaded)
-      const bool ok = p >= 0 && p < a.g.n0;  // whole volumes only (tvdk_solve)
+      const int slot_in = PH ^ ((s - 1) & 1);  // slot of plane p in the rows of x^(s-1) (and of x^(s))
+      const bool ok = ZE ? (p >= 0 && p < a.g.n0) : true;  // whole volumes only (tvdk_solve)
       Vec<T> y = xs[s - 1][1];
       if (ok) {
         const Vec<T> lo = xs[s - 1][0], cen = xs[s - 1][1];
-        const Vec<T> up = (p + 1 < a.g.n0) ? hi : cen;
-        const Vec<T> dn = (p > 0) ? lo : cen;
-        const Vec<T> nb = nsum<T, D, E>(c, dn, up, cen, srow<T>(smem, 2 * (s - 1) + (p & 1), rowe));
+        const Vec<T> up = (!ZE || p + 1 < a.g.n0) ? hi : cen;
+        const Vec<T> dn = (!ZE || p > 0) ? lo : cen;
+        const Vec<T> nb = nsum<T, D, E>(c, dn, up, cen, srow<T>(smem, 2 * (s - 1) + slot_in, rowe));
 #pragma unroll
         for (int v = 0; v < V; ++v) y.v[v] = rh[s - 1].v[v] * a.k.sc.inv_diag + nb.v[v] * a.k.sc.c_nb;
         if (s < S) {
-          sst(srow<T>(smem, 2 * s + (p & 1), rowe), c, y);
+          sst(srow<T>(smem, 2 * s + slot_in, rowe), c, y);
         } else if (p >= c.z0 && p < c.z1) {
-          sto(c, a.x_out, c.at(a.g, p), y);
+          sto(c, a.x_out, c.cur - (long long)(S - 1) * c.s0b, y);
         }
       }
       // roll stage s-1's window, hand the new plane to the next stage
@@ -1278,11 +1292,16 @@ struct KSweepN {
     c.cur += c.s0b;
     ++j;
   }
-  TVDK_DEV void post(const Args& a, unsigned char* smem) {
-    if (c.edge)
-      post_t<true>(a, smem);
-    else
-      post_t<false>(a, smem);
+  template <int PH>
+  TVDK_DEV void post_p(const Args& a, unsigned char* smem) {
+    const bool ze = j - S < 0 || j + 1 >= a.g.n0;
+    if (ze) {
+      post_t<true, true, PH>(a, smem);
+    } else if (c.edge) {
+      post_t<true, false, PH>(a, smem);
+    } else {
+      post_t<false, false, PH>(a, smem);
+    }
   }
   static TVDK_DEV void finalize(const Args&, int, const double*) {}
 };

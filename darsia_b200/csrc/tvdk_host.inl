@@ -80,6 +80,15 @@ static int prefetch_sub() {
   static const int v = env_int("TVDK_PFSUB", 0) != 0;
   return v;
 }
+// Jacobi sweeps per pass (K4xS), measured in profiles/r1_sweepn.txt: 2-D 4000x7000x3 fp64: 0.332 ms per
+// sweep alone, 0.171 two per pass, 0.153 four per pass; 1788x3180: 0.033 / 0.0185 / 0.0192; 3-D 512^3:
+// 0.56 alone vs 0.62 two per pass (two halo rows on each side of y cost more than the bytes saved).
+static int sweeps_per_pass(int dim, long long voxels, int remaining, bool hetero, bool force3d = false) {
+  if (hetero || remaining < 2) return 1;
+  if (dim != 2) return force3d ? 2 : 1;
+  return (remaining >= 4 && voxels >= (1LL << 23)) ? 4 : 2;
+}
+
 template <class K, typename = void>
 struct KernelZc {
   static int get(int) { return 32; }
@@ -623,7 +632,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
         // coefficients, no tol branch): 4 at a time in 2-D, 2 at a time in 3-D
         if (!tolmode && !het0 && p->fused && s > 1) {
           const int rem = p->solver_maxiter - s + 1;
-          const int S = (D == 2 && rem >= 4) ? 4 : (rem >= 2 ? 2 : 1);
+          const int S = sweeps_per_pass(D, (long long)g.n0 * g.ny * g.nx, rem, false, p->fused >= 2);
           if (S > 1) {
             auto go = [&](auto SS) {
               typedef KSweepN<T, D, decltype(SS)::value> K;
@@ -1114,7 +1123,7 @@ static int sweeps_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_
   T* src = (T*)xa;
   T* dst = (T*)xb;
   for (int rem = n; rem > 0;) {
-    const int S = het ? 1 : ((D == 2 && rem >= 4) ? 4 : (rem >= 2 ? 2 : 1));
+    const int S = sweeps_per_pass(D, (long long)o.g.n0 * o.g.ny * o.g.nx, rem, het);
     if (S == 1) {
       TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
         typedef KSweep<T, D, decltype(H)::value> K;

@@ -119,7 +119,8 @@ typedef struct tvdk_problem {
   int32_t verbose_every;   /* 0 = never compute the energy functional */
   int32_t check_every;     /* host polls the device "all done" flag every N outer iterations */
   int32_t fused;           /* 1 = allow the fused per-iteration kernels (default), 0 = building blocks only,
-                            * 2 = also take the single-pass CG iterations in 3-D (default: 2-D only) */
+                            * 2 = also take the single-pass CG iterations and the blocked Jacobi sweeps in
+                            *     3-D (default: 2-D only -- in 3-D their halo rows cost more than they save) */
   int32_t tile_x, tile_y, zchunk; /* 0 = library default; thread-block shape / planes per CTA */
   /* `adaptive` schedule (split_bregman_tvd.py:26, :149-158): HOST array of max_num_iter flags,
    * adaptive_mask[it] != 0 <=> adaptive(it) is true: after the shrinkage of iteration `it`
@@ -241,7 +242,7 @@ int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coe
                   size_t workspace_bytes, void* stream);
 
 /* n Jacobi sweeps (jacobi.py:109-114, no tol branch) ping-ponging between xa (in: the start iterate) and
- * xb; with scalar coefficients they are temporally blocked (4 per pass in 2-D, 2 per pass in 3-D).
+ * xb; in 2-D with scalar coefficients they are temporally blocked (2 or 4 sweeps per pass).
  * *result_in_b tells which buffer holds the result; the other one is scratch afterwards. */
 int tvdk_jacobi_sweeps(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, void* xa,
                        const void* rhs, void* xb, int nsweeps, int* result_in_b, void* workspace,

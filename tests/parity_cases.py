@@ -116,6 +116,6 @@ def run_jacobi_blocked_pair(da, oracle, shape, dim, tile, K, iso, dtype, batch):
     img = phantom(tuple(shape) + tuple(batch), 5, dtype)
     kw = dict(mu=0.1, omega=0.5, ell=1.0, dim=dim, max_num_iter=4, isotropic=iso)
     ref = oracle.split_bregman_tvd(img, solver=oracle.Jacobi(maxiter=K), **kw)
-    out = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, **kw)
+    out = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, fused=2, **kw)  # 2: blocked in 3-D too
     one = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, fused=False, **kw)
     return out, one, ref
