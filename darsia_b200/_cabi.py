@@ -135,6 +135,7 @@ SIGNATURES = {
     "tvdk_norm_diff2": (C.c_int, [_PG, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_energy": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_fused_jacobi1": (C.c_int, [_PG, _I, _PC, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
+    "tvdk_fused_jacobi1_x2": (C.c_int, [_PG, _I, _PC, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_init": (C.c_int, [_PG, _I, _PC, _PC, _PC, _VP, _VP, _I64, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_pq": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _I, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_update": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),

@@ -45,8 +45,19 @@ struct has_unroll2 : std::false_type {};
 template <class K>
 struct has_unroll2<K, std::void_t<decltype(K::UNROLL2)>> : std::bool_constant<K::UNROLL2> {};
 
+// kernels may cap their block size (K::MAXT) to get more than 128 registers per thread
+template <class K, typename = void>
+struct max_threads : std::integral_constant<int, kMaxThreads> {};
 template <class K>
-__global__ void __launch_bounds__(kMaxThreads) tvdk_kernel(const typename K::Args a, double* partials,
+struct max_threads<K, std::void_t<decltype(K::MAXT)>> : std::integral_constant<int, K::MAXT> {};
+
+template <class K, typename = void>
+struct min_blocks : std::integral_constant<int, 1> {};
+template <class K>
+struct min_blocks<K, std::void_t<decltype(K::MINB)>> : std::integral_constant<int, K::MINB> {};
+
+template <class K>
+__global__ void __launch_bounds__(max_threads<K>::value, min_blocks<K>::value) tvdk_kernel(const typename K::Args a, double* partials,
                                                             unsigned* counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   LaunchCtx lc;

@@ -208,6 +208,7 @@ enum FinKind {
   FIN_NONE = 0,
   FIN_NRMF,    // totals[0] = sum f^2
   FIN_OUTER,   // totals[0] = sum (u+ - u)^2
+  FIN_OUTER2,  // totals = {sum (u' - u)^2, sum (u'' - u')^2}: two outer iterations in one launch (K1x2)
   FIN_CGINIT,  // totals = {sum rhs^2, sum r^2}
   FIN_CGPQ,    // totals[0] = p.q
   FIN_CGRR,    // totals[0] = r.r
@@ -260,6 +261,16 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
       if (f.eps >= 0.0 && inc < f.eps) {
         s.done = 1;
         if (f.ndone) atomic_inc(f.ndone);
+      }
+    } break;
+    case FIN_OUTER2: {  // two iterations of :161 (no eps: the host only fuses pairs when eps is None)
+      const double i1 = sqrt(tot[0]) / s.nrm_f, i2 = sqrt(tot[1]) / s.nrm_f;
+      s.inc = i2;
+      s.iters += 2;
+      s.cur_buf = f.buf_id;
+      if (f.history) {
+        f.history[(long long)f.iter * f.nb + b] = i1;
+        f.history[(long long)(f.iter + 1) * f.nb + b] = i2;
       }
     } break;
     case FIN_CGINIT: {  // scipy cg: bnrm2, atol, early return, r = b - A x
@@ -904,6 +915,300 @@ struct KFusedJ1 {
       post_t<true, PH>(a, smem);
     else
       post_t<false, PH>(a, smem);
+  }
+  static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
+};
+
+// ==========================================================================================
+// K1x2  TWO fused outer iterations for Jacobi(maxiter=1) in one pass (2-D, temporal blocking):
+//     (u, t) -> (u', t') -> (u'', t'') with only u, f, t read and u'', t'' written: (3 + 2D)/2
+//     words per voxel and outer iteration.  Four stages share the plane's single barrier, each one
+//     plane behind the previous:   A1 plane j: u' ;  A2 plane j-1: t' (and its b', w') ;
+//     B1 plane j-2: u'' ;  B2 plane j-3: t'' + stores.   Same arithmetic per voxel as K1
+//     (split_bregman_tvd.py:84-89, jacobi.py:112-114, :136-146, :161 twice).
+//     Shared rows (two slots each): 0 u(j) | 1 w1(j) | 2 u'(ring) | 3 u'(copy for B1) | 4 w1'(j-1) | 5 u''(ring).
+// ==========================================================================================
+template <typename T, bool ISO, bool HET>
+struct KFusedJ1x2 {
+  static constexpr int D = 2;
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = 0, RH = 0, NRED = 2, NROWS = 12;
+  static constexpr int RHXV = (3 + V - 1) / V;  // u'' at x+1 needs u' at x+2 needs u at x+3
+  static constexpr int PF2D = 3, PF3D = 3;
+  static constexpr int ZC2D = 64;  // 4 extra march steps per chunk
+  static constexpr int MAXT = 128;  // block size cap: the four-stage pipeline needs > 128 registers per thread
+#if defined(TVDK_X2_MINB)
+  static constexpr int MINB = TVDK_X2_MINB;  // tuning builds: resident blocks per SM asked of ptxas
+#endif
+  typedef Col<T, D, LH, RH, 1, RHXV> C;
+  struct Args {
+    Geom g;
+    Coefs<T> k;
+    const T* f;
+    const T* u_in;
+    T* u_out;
+    const T* t_in;
+    T* t_out;
+    long long tcs_in, tcs_out;
+    const tvdk_stat_t* skip;
+    Fin fin;
+  };
+  C c;
+  int j, rowe, js, jend;
+  // stage A (iteration 1)
+  Vec<T> u_lo, u_c, u_hi;          // u(j-1), u(j), u(j+1)
+  Vec<T> wA0_prev, wA0_cur, wA1;   // w_0(j-1), w_0(j), w_1(j)
+  Vec<T> bA_prev[D], bA_cur[D];    // b(j-1), b(j)
+  Vec<T> upA1, upA2, upA3;         // u'(j-1), u'(j-2), u'(j-3)
+  Vec<T> omfA, invdA, cnbA;        // per-voxel scalars of plane j
+  Vec<T> mu0, el0, mu1, el1;       // mu, ell of planes j and j-1 (per-voxel maps only)
+  // stage B (iteration 2)
+  Vec<T> wB0_p2, wB0_p3, wB1_p2;   // w'_0(j-2), w'_0(j-3), w'_1(j-2)
+  Vec<T> bB_p2[D], bB_p3[D];       // b'(j-2), b'(j-3)
+  Vec<T> upB_p3;                   // u''(j-3)
+  Vec<T> lf, lom, lel;             // f, omega, ell of plane j-2 (re-read: L1/L2 hits)
+  // prefetched raw data of plane j+1 (u of plane j+2)
+  RawT<T, D> nx;
+  Vec<T> nx_u, nx_f, nx_om;
+  double red[NRED];
+
+  TVDK_DEV void prefetch(const Args& a, long long o, bool zhi) {
+    load_rawt<true, HET, false>(nx, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o);
+    nx_f = ldo(a.f, o);
+    nx_om = ldcoef<HET>(c, a.k.omega, o);
+    if (zhi) nx_u = ldo(a.u_in, o + c.s0b);
+  }
+
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
+    if (a.skip && a.skip[lc.bz].done) return false;
+    c.setup(a.g, lc);
+    rowe = C::row_elems(lc.ntx, lc.nty);
+    red[0] = red[1] = 0.0;
+    js = c.z0 - 1 > 0 ? c.z0 - 1 : 0;  // first plane of stage A1
+    jend = c.z1 + 2;                   // stage B2 writes plane j - 3
+    j = js;
+    const long long o = c.at(a.g, j);
+    c.cur = o;
+    u_c = ldo(a.u_in, o);
+    u_lo = u_c;
+    const Vec<T> z = vsplat<T>((T)0);
+    wA0_prev = z;
+    if (j > 0) {
+      u_lo = ldo(a.u_in, o - c.s0b);
+      RawT<T, D> r;
+      load_rawt<true, HET, false>(r, c, a.k, a.t_in, a.tcs_in, (const T*)nullptr, (const T*)nullptr, 0, o - c.s0b);
+      Vec<T> bb[D], ww[D];
+      bw_plane<T, D, ISO, HET>(r, a.k.sc, false, bb, ww);
+      wA0_prev = ww[0];
+    }
+    upA1 = upA2 = upA3 = upB_p3 = z;
+    wB0_p2 = wB0_p3 = wB1_p2 = z;
+    mu0 = el0 = mu1 = el1 = lf = lom = lel = vsplat<T>((T)1);
+#pragma unroll
+    for (int d = 0; d < D; ++d) bA_prev[d] = bB_p2[d] = bB_p3[d] = z;
+    prefetch(a, o, j + 1 < a.g.n0);
+    return true;
+  }
+  TVDK_DEV bool more() const { return j <= jend; }
+
+  static constexpr bool UNROLL2 = !HET;
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if ((j - js) & 1) pre_p<1>(a, smem); else pre_p<0>(a, smem);
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if ((j - js) & 1) post_p<1>(a, smem); else post_p<0>(a, smem);
+  }
+
+  // rows: index = 2 * kind + slot
+  template <int KIND>
+  TVDK_DEV T* row(unsigned char* smem, int slot) const { return srow<T>(smem, 2 * KIND + slot, rowe); }
+
+  // pre: consume the prefetched plane j (b, w from t; per-voxel scalars), publish u(j) and w_1(j),
+  //      issue the loads of plane j+1 and the re-reads of plane j-2
+  template <int PH>
+  TVDK_DEV void pre_p(const Args& a, unsigned char* smem) {
+    if (j < a.g.n0) {
+      u_hi = (j + 1 < a.g.n0) ? nx_u : u_c;
+      Vec<T> ww[D];
+      bw_plane<T, D, ISO, HET>(nx, a.k.sc, false, bA_cur, ww);
+      wA0_cur = ww[0];
+      wA1 = ww[1];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const VoxCoef<T> vc = voxcoef<HET>(a.k.sc, (T)0, nx_om.v[v], nx.el.v[v]);
+        invdA.v[v] = vc.inv_diag;
+        cnbA.v[v] = vc.c_nb;
+        omfA.v[v] = vc.omega * nx_f.v[v];
+      }
+      sst(row<0>(smem, PH), c, u_c);
+      sst(row<1>(smem, PH), c, wA1);
+      mu0 = nx.mu;  // stage A2 of the NEXT step shrinks t'(j) with plane j's kappa
+      el0 = nx.el;
+      // loads of plane j+1 (u' is needed up to plane z1 + 1 only), issued before the barrier so that
+      // the four stages after it hide their latency
+      if (j + 1 < a.g.n0 && j + 1 <= c.z1 + 1) prefetch(a, c.cur + c.s0b, j + 2 < a.g.n0);
+    }
+    if (j - 2 >= 0 && j - 2 < a.g.n0) {
+      const long long o2 = c.cur - 2 * c.s0b;
+      lf = ldo(a.f, o2);
+      lom = ldcoef<HET>(c, a.k.omega, o2);
+      lel = ldcoef<HET>(c, a.k.ell, o2);
+    }
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      pfo(a.u_in, o);
+      pfo(a.f, o);
+#pragma unroll
+      for (int d = 0; d < D; ++d) pfo(a.t_in + d * a.tcs_in, o);
+      if (HET) {
+        if (a.k.mu.p) pfo(a.k.mu.p + (long long)c.b * a.k.mu.sb, o + c.cdel);
+        if (a.k.omega.p) pfo(a.k.omega.p + (long long)c.b * a.k.omega.sb, o + c.cdel);
+        if (a.k.ell.p) pfo(a.k.ell.p + (long long)c.b * a.k.ell.sb, o + c.cdel);
+      }
+    }
+  }
+
+  // u+ of one plane: rhs (:84-89) then the sweep (jacobi.py:112-114)
+  template <bool E>
+  TVDK_DEV Vec<T> ustep(bool zlo, const Vec<T>& lo, const Vec<T>& cen, const Vec<T>& hi, const T* urow, const Vec<T>& w0c,
+                        const Vec<T>& w0p, const Vec<T>& w1c, const T* w1row, const Vec<T>& omf, const Vec<T>& invd,
+                        const Vec<T>& cnb) const {
+    Vec<T> rhs = omf;
+    if (zlo) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) rhs.v[v] += w0c.v[v] - w0p.v[v];
+    }
+    const T wl = sxm(w1row, c);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const T left = v > 0 ? w1c.v[v > 0 ? v - 1 : 0] : wl;
+      if (c.template HL<E>(v)) rhs.v[v] += w1c.v[v] - left;
+    }
+    const Vec<T> nb = nsum<T, D, E>(c, lo, hi, cen, urow);
+    Vec<T> up;
+#pragma unroll
+    for (int v = 0; v < V; ++v) up.v[v] = rhs.v[v] * invd.v[v] + nb.v[v] * cnb.v[v];
+    return up;
+  }
+  // t+ of one plane: G u+ + b (:136-146 on the compressed state)
+  template <bool E>
+  TVDK_DEV void tstep(bool zhi, const Vec<T>& up_hi, const Vec<T>& up_c, const T* uprow, const Vec<T> (&b)[D],
+                      Vec<T> (&tn)[D]) const {
+#pragma unroll
+    for (int v = 0; v < V; ++v) tn[0].v[v] = (zhi ? up_hi.v[v] - up_c.v[v] : (T)0) + b[0].v[v];
+    const T xr = sxp(uprow, c);
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+      const T right = v < V - 1 ? up_c.v[v < V - 1 ? v + 1 : 0] : xr;
+      tn[1].v[v] = (c.template HR<E>(v) ? right - up_c.v[v] : (T)0) + b[1].v[v];
+    }
+  }
+
+  template <bool E, bool ZE, int PH>
+  TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
+    const int n0 = a.g.n0;
+    // ---- A1, plane j: u'(j)
+    const bool exA1 = ZE ? (j < n0) : true;
+    Vec<T> upA0 = upA1;
+    if (exA1) {
+      upA0 = ustep<E>(ZE ? j > 0 : true, ZE && j == 0 ? u_c : u_lo, u_c, u_hi, row<0>(smem, PH), wA0_cur, wA0_prev, wA1,
+                      row<1>(smem, PH), omfA, invdA, cnbA);
+      sst(row<2>(smem, PH), c, upA0);
+    }
+    // ---- A2, plane j-1: t'(j-1), its b', w'; increment of iteration 1
+    const int p1 = j - 1;
+    const bool exA2 = ZE ? (p1 >= js && p1 < n0) : true;
+    Vec<T> bB_new[D], wB_new[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) bB_new[d] = wB_new[d] = upA1;
+    if (exA2) {
+      Vec<T> tB[D];
+      tstep<E>(ZE ? p1 + 1 < n0 : true, upA0, upA1, row<2>(smem, PH ^ 1), bA_prev, tB);
+      RawT<T, D> r;
+#pragma unroll
+      for (int d = 0; d < D; ++d) r.t[d] = tB[d];
+      r.mu = mu1;
+      r.el = el1;
+      bw_plane<T, D, ISO, HET>(r, a.k.sc, false, bB_new, wB_new);
+      sst(row<4>(smem, PH ^ 1), c, wB_new[1]);
+      sst(row<3>(smem, PH ^ 1), c, upA1);
+      if (c.st && p1 >= c.z0 && p1 < c.z1) {  // u_lo still holds u(j-1)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (c.template OK<E>(v)) {
+            const double df = (double)upA1.v[v] - (double)u_lo.v[v];
+            red[0] += df * df;
+          }
+      }
+    }
+    // ---- B1, plane j-2: u''(j-2)
+    const int p2 = j - 2;
+    const bool exB1 = ZE ? (p2 >= js && p2 < n0) : true;
+    Vec<T> upB_new = upB_p3;
+    if (exB1) {
+      Vec<T> omf, invd, cnb;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const VoxCoef<T> vc = voxcoef<HET>(a.k.sc, (T)0, lom.v[v], lel.v[v]);
+        invd.v[v] = vc.inv_diag;
+        cnb.v[v] = vc.c_nb;
+        omf.v[v] = vc.omega * lf.v[v];
+      }
+      const bool zlo = ZE ? p2 > 0 : true, zhi = ZE ? p2 + 1 < n0 : true;
+      upB_new = ustep<E>(zlo, zlo ? upA3 : upA2, upA2, zhi ? upA1 : upA2, row<3>(smem, PH), wB0_p2, wB0_p3, wB1_p2,
+                         row<4>(smem, PH), omf, invd, cnb);
+      sst(row<5>(smem, PH), c, upB_new);
+    }
+    // ---- B2, plane j-3: t''(j-3), stores, increment of iteration 2
+    const int p3 = j - 3;
+    if (p3 >= c.z0 && p3 < c.z1) {
+      Vec<T> tC[D];
+      tstep<E>(ZE ? p3 + 1 < n0 : true, upB_new, upB_p3, row<5>(smem, PH ^ 1), bB_p3, tC);
+      const long long oo = c.cur - 3 * c.s0b;
+      sto(c, a.u_out, oo, upB_p3);
+#pragma unroll
+      for (int d = 0; d < D; ++d) sto(c, a.t_out + d * a.tcs_out, oo, tC[d]);
+      if (c.st) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (c.template OK<E>(v)) {
+            const double df = (double)upB_p3.v[v] - (double)upA3.v[v];
+            red[1] += df * df;
+          }
+      }
+    }
+    // ---- roll, then the loads of plane j+1
+    u_lo = u_c;
+    u_c = u_hi;
+    wA0_prev = wA0_cur;
+    mu1 = mu0;
+    el1 = el0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      bA_prev[d] = bA_cur[d];
+      bB_p3[d] = bB_p2[d];
+      bB_p2[d] = bB_new[d];
+    }
+    upA3 = upA2;
+    upA2 = upA1;
+    upA1 = upA0;
+    wB0_p3 = wB0_p2;
+    wB0_p2 = wB_new[0];
+    wB1_p2 = wB_new[1];
+    upB_p3 = upB_new;
+    c.cur += c.s0b;
+    ++j;
+  }
+  template <int PH>
+  TVDK_DEV void post_p(const Args& a, unsigned char* smem) {
+    const bool ze = j - 3 <= js || j + 1 >= a.g.n0;  // some stage's plane is missing, first, or on the axis-0 boundary
+    if (ze) {
+      post_t<true, true, PH>(a, smem);
+    } else if (c.edge) {
+      post_t<true, false, PH>(a, smem);
+    } else {
+      post_t<false, false, PH>(a, smem);
+    }
   }
   static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
 };

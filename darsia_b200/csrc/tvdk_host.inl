@@ -90,6 +90,14 @@ static int sweeps_per_pass(int dim, long long voxels, int remaining, bool hetero
 }
 
 template <class K, typename = void>
+struct KernelMaxT {
+  static constexpr int value = 512;
+};
+template <class K>
+struct KernelMaxT<K, std::void_t<decltype(K::MAXT)>> {
+  static constexpr int value = K::MAXT;
+};
+template <class K, typename = void>
 struct KernelZc {
   static int get(int) { return 32; }
 };
@@ -196,6 +204,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
   if (D == 2) {
     int ntx = tune.tile_x > 0 ? round_up(tune.tile_x, 32) : 128;
     ntx = std::min(ntx, round_up(need_x, 32));
+    ntx = std::min(ntx, KernelMaxT<K>::value);
     ntx = std::max(ntx, 32);
     L.ntx = ntx;
     L.nty = 1;
@@ -267,6 +276,10 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   LaunchCfg d = plan_launch<KDot<T, D, 0>, T, D>(g, tune, false);
   LaunchCfg e = plan_launch<KCgFused<T, D, false>, T, D>(g, tune, true);
   size_t m = 0;
+  if constexpr (D == 2) {
+    LaunchCfg x2 = plan_launch<KFusedJ1x2<T, false, false>, T, D>(g, tune, true);
+    m = std::max(m, (size_t)x2.gx * x2.gy * x2.gz * 2);
+  }
   for (const LaunchCfg* L : {&a, &b, &c, &d}) m = std::max(m, (size_t)L->gx * L->gy * L->gz * 2);
   m = std::max(m, (size_t)e.gx * e.gy * e.gz * 4);
   return m + 64;
@@ -542,7 +555,36 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       a.fin.kind = FIN_ENERGY; a.fin.stats = st; a.fin.history = p->energy_history; a.fin.iter = it; a.fin.nb = g.nb;
       TVDK_TRY((run<KEnergy<T, D>, T, D>(a, g, tune, false, sc, stream)));
     }
-    if (fp.fusedj1 && !expl_now) {
+    bool pair = false;
+    if constexpr (D == 2) {
+      // two outer iterations per pass (K1x2) wherever nothing has to happen between them
+      // Measured (profiles/r1_x2.txt, 4000x7000x3): 0.74 vs 0.82 ms per iteration for anisotropic fp64 with
+      // scalar coefficients; slower than K1 for isotropic (sqrt + divide in two of the four stages), per-voxel
+      // maps and fp32 (the pipeline holds > 200 registers per thread) and for small images => only the
+      // winning case takes it by default, fused = 2 forces it everywhere (tests).
+      const bool wins = std::is_same<T, double>::value && !iso && !het && (long long)g.n0 * g.nx >= (1LL << 23);
+      pair = fp.fusedj1 && !expl_now && p->eps < 0.0 && p->verbose_every <= 0 && it + 1 < p->max_num_iter &&
+             !(fp.adapt) && p->fused != 3 && (wins || p->fused == 2);
+      if (pair) {
+        Fin fn = outer_fin(it, 1 - cur);
+        fn.kind = FIN_OUTER2;
+        TVDK_TRY(dispatch2(iso, het, [&](auto I, auto H) {
+          typedef KFusedJ1x2<T, decltype(I)::value, decltype(H)::value> K;
+          typename K::Args a;
+          memset(&a, 0, sizeof a);
+          a.k = k; a.f = f; a.u_in = ubuf[cur]; a.u_out = ubuf[1 - cur];
+          a.t_in = tbuf[cur]; a.t_out = tbuf[1 - cur]; a.tcs_in = tcs[cur]; a.tcs_out = tcs[1 - cur];
+          a.skip = st; a.fin = fn;
+          return run<K, T, D>(a, g, tune, true, sc, stream);
+        }));
+        cur = 1 - cur;
+        ++it;  // this launch was iterations it and it + 1
+        ++launched;
+      }
+    }
+    if (pair) {
+      // (both iterations done above)
+    } else if (fp.fusedj1 && !expl_now) {
       const Fin fn = outer_fin(it, 1 - cur);
       TVDK_TRY(dispatch2(iso, het, [&](auto I, auto H) {
         typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
@@ -1031,6 +1073,27 @@ static int fj1_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const
 }
 
 template <typename T, int D>
+static int fj1x2_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
+                      const tvdk_coef_t* el, const void* f, const void* u_in, void* u_out, const void* t_in,
+                      void* t_out, int64_t tcs, double* sum_out, void* ws, size_t wsb, void* stream) {
+  if constexpr (D != 2) {
+    return fail(TVDK_ERR_UNSUPPORTED, "the two-iteration fused kernel is 2-D only");
+  } else {
+    OpCtx<T, D> o;
+    TVDK_TRY(o.init(gg, ws, wsb, stream));
+    const Coefs<T> k = make_coefs<T>(mu, om, el, D);
+    return dispatch2(iso != 0, k.sc.hetero != 0, [&](auto I, auto H) {
+      typedef KFusedJ1x2<T, decltype(I)::value, decltype(H)::value> K;
+      typename K::Args a;
+      memset(&a, 0, sizeof a);
+      a.k = k; a.f = (const T*)f; a.u_in = (const T*)u_in; a.u_out = (T*)u_out;
+      a.t_in = (const T*)t_in; a.t_out = (T*)t_out; a.tcs_in = tcs; a.tcs_out = tcs; a.fin = sum_fin(sum_out);
+      return run<K, T, D>(a, o.g, o.tune, true, o.sc, stream);
+    });
+  }
+}
+
+template <typename T, int D>
 static int cginit_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
                        const tvdk_coef_t* el, const void* f, const void* t, int64_t tcs, const void* u, void* x,
                        void* r, double* sum_out, void* ws, size_t wsb, void* stream) {
@@ -1325,4 +1388,15 @@ int tvdk_jacobi_sweeps(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvd
     return fail(TVDK_ERR_INVALID, "jacobi_sweeps works on whole volumes (slabs sweep one at a time)");
   TVDK_C_ENTRY(g, (sweeps_impl<T, D>(g, omega, ell, xa, rhs, xb, nsweeps, result_in_b, workspace, workspace_bytes,
                                      stream)))
+}
+
+int tvdk_fused_jacobi1_x2(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* omega,
+                          const tvdk_coef_t* ell, const void* f, const void* u_in, void* u_out, const void* t_in,
+                          void* t_out, int64_t t_comp_stride, double* sum_out, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+  if (u_in == u_out || t_in == t_out) return fail(TVDK_ERR_INVALID, "fused kernel is out-of-place");
+  if (g && (g->z_begin != 0 || g->z_end != g->n[0] || g->g0_off != 0 || g->g0_n != g->n[0]))
+    return fail(TVDK_ERR_INVALID, "fused_jacobi1_x2 works on whole images");
+  TVDK_C_ENTRY(g, (fj1x2_impl<T, D>(g, isotropic, mu, omega, ell, f, u_in, u_out, t_in, t_out, t_comp_stride,
+                                    sum_out, workspace, workspace_bytes, stream)))
 }

@@ -119,8 +119,10 @@ typedef struct tvdk_problem {
   int32_t verbose_every;   /* 0 = never compute the energy functional */
   int32_t check_every;     /* host polls the device "all done" flag every N outer iterations */
   int32_t fused;           /* 1 = allow the fused per-iteration kernels (default), 0 = building blocks only,
-                            * 2 = also take the single-pass CG iterations and the blocked Jacobi sweeps in
-                            *     3-D (default: 2-D only -- in 3-D their halo rows cost more than they save) */
+                            * 2 = take every temporally blocked / single-pass variant wherever it is implemented,
+                            *     not only where it measured faster (3-D single-pass CG and blocked sweeps,
+                            *     K1x2 pairs for isotropic / per-voxel / fp32 problems and small images),
+                            * 3 = as 1 but one outer iteration per launch (no K1x2 pairs) */
   int32_t tile_x, tile_y, zchunk; /* 0 = library default; thread-block shape / planes per CTA */
   /* `adaptive` schedule (split_bregman_tvd.py:26, :149-158): HOST array of max_num_iter flags,
    * adaptive_mask[it] != 0 <=> adaptive(it) is true: after the shrinkage of iteration `it`
@@ -209,6 +211,16 @@ int tvdk_fused_jacobi1(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* m
                        const void* u_in, void* u_out, const void* t_in, void* t_out,
                        int64_t t_comp_stride, double* sum_out, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* TWO fused outer iterations with Jacobi(maxiter=1) in one pass (2-D only; what tvdk_solve runs for
+ * pairs of iterations of large anisotropic fp64 problems with scalar coefficients when eps is None):
+ * (u_in, t_in) -> two iterations -> (u_out, t_out);
+ * sum_out[2b], sum_out[2b+1] = the two increments' squared norms. */
+int tvdk_fused_jacobi1_x2(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu,
+                          const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* f,
+                          const void* u_in, void* u_out, const void* t_in, void* t_out,
+                          int64_t t_comp_stride, double* sum_out, void* workspace,
+                          size_t workspace_bytes, void* stream);
 
 /* CG building blocks for the slab-decomposed driver (scalars supplied by the caller after the
  * cross-rank reduction; each returns per-problem partial sums in sum_out, device doubles).

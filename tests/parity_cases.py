@@ -119,3 +119,37 @@ def run_jacobi_blocked_pair(da, oracle, shape, dim, tile, K, iso, dtype, batch):
     out = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, fused=2, **kw)  # 2: blocked in 3-D too
     one = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=K), tile=tile, fused=False, **kw)
     return out, one, ref
+
+
+def jacobi1_pair_cases():
+    """(shape, tile, outer iterations, isotropic, hetero, dtype, batch): Jacobi(maxiter=1) without eps in 2-D
+    runs TWO outer iterations per launch (K1x2, a four-stage pipeline); odd counts end with a single one."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((37, 150), (32, 0, 5), 6, False, False, f8, ()),
+        ((37, 150), (32, 0, 7), 7, True, False, f8, (2,)),
+        ((37, 150), (32, 0, 5), 5, False, True, f8, ()),
+        ((37, 150), (32, 0, 5), 6, True, True, f4, ()),
+        ((3, 40), (0, 0, 0), 6, False, False, f8, ()),
+        ((1, 40), (0, 0, 0), 4, False, False, f8, ()),
+        ((2, 7), (0, 0, 0), 5, True, False, f8, ()),
+        ((70, 300), (0, 0, 0), 9, False, False, f8, ()),
+        ((5, 9), (0, 0, 0), 2, False, False, f8, ()),
+    ]
+
+
+def run_jacobi1_pair(da, oracle, shape, tile, nit, iso, het, dtype, batch):
+    img = phantom(tuple(shape) + tuple(batch), 5, dtype)
+    kw = dict(mu=0.1, omega=0.5, ell=1.0)
+    if het:
+        kw["mu"] = coeff_field(shape, 8, 0.05, 0.1, 0.1).astype(dtype)
+        kw["omega"] = coeff_field(shape, 9, 0.5, 2.0).astype(dtype)
+        kw["ell"] = coeff_field(shape, 10, 0.5, 1.5).astype(dtype)
+    hist = []
+    ref = oracle.split_bregman_tvd(img, dim=2, max_num_iter=nit, isotropic=iso, solver=oracle.Jacobi(maxiter=1),
+                                   history=hist, **kw)
+    out, info = da.split_bregman_tvd(img, dim=2, max_num_iter=nit, isotropic=iso, solver=da.Jacobi(maxiter=1), tile=tile,
+                                     return_info=True, fused=2, **kw)  # 2: pairs for every variant, not only where they win
+    one = da.split_bregman_tvd(img, dim=2, max_num_iter=nit, isotropic=iso, solver=da.Jacobi(maxiter=1), tile=tile,
+                               fused=3, **kw)  # 3: one iteration per launch
+    return out, one, ref, info, hist

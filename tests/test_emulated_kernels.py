@@ -11,8 +11,9 @@ import pytest
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from emu.harness import emulated
-from parity_cases import (adaptive_cases, cg_fixed_count_cases, jacobi_blocked_cases, run_adaptive_pair,
-                          run_cg_fixed_pair, run_jacobi_blocked_pair, run_pair, small_grid)
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, jacobi1_pair_cases, jacobi_blocked_cases,
+                          run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
+                          small_grid)
 
 import darsia_b200 as da
 
@@ -54,6 +55,18 @@ def test_jacobi_sweeps_temporally_blocked(shape, dim, tile, K, iso, dtype, batch
     out, one, ref = run_jacobi_blocked_pair(da, oracle, shape, dim, tile, K, iso, dtype, batch)
     np.testing.assert_array_equal(out, one)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+
+
+@pytest.mark.parametrize("shape,tile,nit,iso,het,dtype,batch", jacobi1_pair_cases())
+def test_jacobi1_two_iterations_per_launch(shape, tile, nit, iso, het, dtype, batch):
+    """K1x2 == K1 applied twice, bitwise; both agree with the oracle, and the per-iteration increments of
+    the paired launches are the oracle's."""
+    out, one, ref, info, hist = run_jacobi1_pair(da, oracle, shape, tile, nit, iso, het, dtype, batch)
+    np.testing.assert_array_equal(out, one)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+    assert list(info.iters) == [nit] * max(1, int(np.prod(batch, dtype=int)))
+    for b, h in enumerate(hist if batch else [hist]):
+        np.testing.assert_allclose(info.history[: len(h), b], h, rtol=(1e-9 if dtype == np.float64 else 1e-3))
 
 
 @pytest.mark.parametrize("shape,dim,tile,solver,iso", adaptive_cases())

@@ -94,6 +94,12 @@ def main():
         "sweep_x2": (3 / 2, lambda: lib.jacobi_sweeps(bg, bo, be, u.data_ptr(), f.data_ptr(), u2.data_ptr(), 2, None, *ws(), s)),
         "matvec": (2, lambda: lib.cg_matvec(bg, bo, be, u.data_ptr(), u2.data_ptr(), *ws(), s)),
         "dot": (2, lambda: lib.dot(bg, u.data_ptr(), f.data_ptr(), sums.data_ptr(), *ws(), s)),
+        "fj1x2_iso": ((3 + 2 * dim + nh) / 2, lambda: lib.fused_jacobi1_x2(bg, 1, bm, bo, be, f.data_ptr(), u.data_ptr(),
+                                                                           u2.data_ptr(), t.data_ptr(), t2.data_ptr(),
+                                                                           eng.batch_elems, sums.data_ptr(), *ws(), s)),
+        "fj1x2_aniso": ((3 + 2 * dim + nh) / 2, lambda: lib.fused_jacobi1_x2(bg, 0, bm, bo, be, f.data_ptr(), u.data_ptr(),
+                                                                             u2.data_ptr(), t.data_ptr(), t2.data_ptr(),
+                                                                             eng.batch_elems, sums.data_ptr(), *ws(), s)),
         "fj1_iso": (3 + 2 * dim + nh, lambda: lib.fused_jacobi1(bg, 1, bm, bo, be, f.data_ptr(), u.data_ptr(),
                                                                 u2.data_ptr(), t.data_ptr(), t2.data_ptr(),
                                                                 eng.batch_elems, sums.data_ptr(), *ws(), s)),
@@ -118,7 +124,7 @@ def main():
             e1.record()
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / args.reps
-            nsw = {"sweep_x4": 4, "sweep_x2": 2}.get(name, 1)  # per SWEEP for the blocked passes
+            nsw = {"sweep_x4": 4, "sweep_x2": 2, "fj1x2_iso": 2, "fj1x2_aniso": 2}.get(name, 1)  # per sweep / iteration
             gbs = words * nsw * W * N / (ms * 1e-3) / 1e9
             print(f"{name:10s} shape={shape} nb={args.nb} {dt.name} tile=({tx},{ty},{zc}) {ms / nsw:8.4f} ms  "
                   f"{gbs:7.1f} GB/s algo ({words} words)  {gbs / peak:5.3f} of measured peak", flush=True)
