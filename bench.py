@@ -447,6 +447,7 @@ def run_ours(args, w, wname):
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": ncu_traffic(f"{dom_key}:{wname}"), "peak_source": peak_src,
+        "frac_of_8TBs_spec": achieved / 8000.0,  # north_star quotes the ~8 TB/s nominal HBM3e figure
         "algo_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
         "whole_step": {"algo_words_per_voxel_iter": words_iter, "achieved": step_gbs, "frac": step_gbs / peak,
                        "survey_words_per_voxel_iter": survey_words,

@@ -719,6 +719,10 @@ struct KFusedJ1 {
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 1, RH = 2, NRED = 1, NROWS = 2 * D + 2;
   static constexpr int PF2D = ISO ? 3 : 2, PF3D = 3;  // L2 prefetch distance (profiles/r1_pf_sweep.txt)
+  // 3-D launch shape (profiles/r1_tile3d_v2.txt): 64 planes per CTA (0.79 vs 0.76 of peak at 32); fp32 with
+  // 16 threads = 64 columns per row like fp64 (0.82 vs 0.70 with 32 threads)
+  static constexpr int ZC3D = 64;
+  static constexpr int NTX3D = sizeof(T) == 4 ? 16 : 32;
   typedef Col<T, D, LH, RH> C;
   struct Args {
     Geom g;

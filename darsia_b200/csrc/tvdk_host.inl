@@ -106,6 +106,22 @@ struct KernelZc<K, std::void_t<decltype(K::ZC2D)>> {
   static int get(int dim) { return dim == 2 ? K::ZC2D : 32; }
 };
 template <class K, typename = void>
+struct KernelZc3 {
+  static constexpr int value = 32;
+};
+template <class K>
+struct KernelZc3<K, std::void_t<decltype(K::ZC3D)>> {
+  static constexpr int value = K::ZC3D;
+};
+template <class K, typename = void>
+struct KernelNtx3 {
+  static constexpr int value = 32;
+};
+template <class K>
+struct KernelNtx3<K, std::void_t<decltype(K::NTX3D)>> {
+  static constexpr int value = K::NTX3D;
+};
+template <class K, typename = void>
 struct KernelPf {
   static int get(int) { return 0; }
 };
@@ -209,7 +225,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     L.ntx = ntx;
     L.nty = 1;
   } else {
-    int ntx = tune.tile_x > 0 ? tune.tile_x : 32;
+    int ntx = tune.tile_x > 0 ? tune.tile_x : KernelNtx3<K>::value;
     ntx = std::min(ntx, round_up(need_x, 8));
     ntx = std::max(ntx, 8);
     int nty = tune.tile_y > 0 ? tune.tile_y : (big_tile ? 16 : 8);
@@ -242,7 +258,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     zc = std::min(zc, 32);
     // kernels with a deep chunk prologue (K7 re-reads 6 planes per chunk) prefer longer chunks as long
     // as a problem alone still fills the GPU several times over
-    const int pref = KernelZc<K>::get(D);
+    const int pref = D == 2 ? KernelZc<K>::get(D) : KernelZc3<K>::value;
     if (pref > zc && tiles * ((nz + pref - 1) / pref) >= 148LL * 8) zc = pref;
   }
   zc = std::min(zc, nz);

