@@ -30,6 +30,39 @@ def frames_per_batch(frame_voxels: int, itemsize: int, dim: int, budget_bytes: f
     return max(1, int(budget_bytes // max(per_frame, 1)))
 
 
+def _run_overlapped(solve, starts, device) -> None:
+    """Two worker threads, one CUDA stream each: copies of one sub-batch overlap kernels of the other."""
+    import threading
+
+    import torch
+
+    from ._runtime import resolve_device
+
+    dev = resolve_device(device)
+    errors = []
+
+    def worker(items) -> None:
+        try:
+            if dev.type == "cuda":
+                torch.cuda.set_device(dev)
+                with torch.cuda.stream(torch.cuda.Stream(dev)):
+                    for b0 in items:
+                        solve(b0)
+            else:  # the CPU test-suite's kernel emulator
+                for b0 in items:
+                    solve(b0)
+        except BaseException as exc:  # re-raised in the caller's thread
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(starts[i::2],)) for i in range(2)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    if errors:
+        raise errors[0]
+
+
 def tvd_series(
     series: np.ndarray,
     dim: int = 2,
@@ -38,6 +71,7 @@ def tvd_series(
     batch: Optional[int] = None,
     gather: bool = False,
     group=None,
+    overlap: bool = True,
     **kwargs,
 ):
     """Denoise the frames ``series[..., t]`` owned by this rank.
@@ -50,6 +84,9 @@ def tvd_series(
         batch: frames per device-resident sub-batch (default: sized from the HBM budget).
         gather: if True the full denoised series is assembled on every rank (``all_gather_object``
             of the host arrays -- convenience for modest sizes, not a data-path collective).
+        overlap: process the sub-batches from two host threads, each on its own CUDA stream, so that the
+            host<->device copies of one sub-batch overlap the kernels of the other (libtvdk keeps no global
+            state; results are identical -- every sub-batch is an independent solve).
         **kwargs: forwarded to ``split_bregman_tvd`` (``mu``, ``omega``, ``ell``, ``solver``, ...).
     Returns ``(frames, (s, e))``: the denoised frames of this rank and their index range.
     """
@@ -67,11 +104,20 @@ def tvd_series(
     mine = series[(slice(None),) * dim + (slice(s, e),)]
     out = np.empty_like(mine)
     if batch is None:
+        # (two sub-batches are resident at a time when the copies are overlapped)
         batch = frames_per_batch(int(np.prod(series.shape[:dim])) * int(np.prod(series.shape[dim + 1:], dtype=np.int64)),
                                  series.dtype.itemsize, dim)
-    for b0 in range(0, e - s, batch):
+    starts = list(range(0, e - s, batch))
+
+    def solve(b0: int) -> None:
         sel = (slice(None),) * dim + (slice(b0, min(b0 + batch, e - s)),)
         out[sel] = split_bregman_tvd(np.ascontiguousarray(mine[sel]), dim=dim, **kwargs)
+
+    if overlap and len(starts) > 1:
+        _run_overlapped(solve, starts, kwargs.get("device"))
+    else:
+        for b0 in starts:
+            solve(b0)
     if gather and world > 1:
         parts = [None] * world
         dist.all_gather_object(parts, (s, e, out), group=group)

@@ -63,6 +63,23 @@ def test_cfg2_constant_image_is_fixed_point_100_iterations(da):
     assert rel_l2(out, img) <= 1e-12
 
 
+def test_full_size_jacobi1_pairs_and_blocked_sweeps(da):
+    """4000x7000 anisotropic fp64 with scalar coefficients: Jacobi(1) takes the two-iterations-per-launch kernel
+    (K1x2) by default here, Jacobi(9) the temporally blocked sweeps (K4x4): both against the oracle, and against
+    the one-step-per-launch route at a higher iteration count."""
+    img = _phantom((4000, 7000), 7)
+    kw = dict(mu=0.1, omega=1.0, ell=1.0, dim=2, isotropic=False)
+    out = da.split_bregman_tvd(img, max_num_iter=5, **kw)  # 2 pairs + 1 single
+    ref = oracle.split_bregman_tvd(img, max_num_iter=5, **kw)
+    assert rel_l2(out, ref) <= 1e-10
+    a = da.split_bregman_tvd(img, max_num_iter=40, **kw)
+    b = da.split_bregman_tvd(img, max_num_iter=40, fused=3, **kw)  # 3: one iteration per launch
+    assert rel_l2(a, b) <= 1e-13
+    out = da.split_bregman_tvd(img, max_num_iter=2, solver=da.Jacobi(maxiter=9), **kw)
+    ref = oracle.split_bregman_tvd(img, max_num_iter=2, solver=oracle.Jacobi(maxiter=9), **kw)
+    assert rel_l2(out, ref) <= 1e-10
+
+
 def test_cfg3_hetero_frames_full_size(da):
     """Two 4000x7000 frames with per-pixel mu (10 % zero mask) and omega, fused Jacobi(1): frame 0 vs the
     oracle after 4 iterations; fused route == building-block route after 30."""

@@ -233,3 +233,20 @@ def test_mg_inner_solver_batched_and_stopping(da):
     out, info = da.split_bregman_tvd(img, solver=mk(da, tol=1e-2), return_info=True, **kw2)
     assert [len(h) for h in hist] == list(info.iters)
     assert rel_l2(out, ref) <= 1e-13
+
+
+def test_series_sub_batches_overlapped(da):
+    """tvd_series: sub-batches solved from two host threads (one stream each on the GPU) == one after the other
+    == the oracle per frame."""
+    from golden.generate_golden import phantom
+
+    series = np.stack([phantom((24, 40), 10 + t) for t in range(5)], axis=-1)
+    kw = dict(dim=2, mu=0.1, omega=1.0, ell=1.0, max_num_iter=6, isotropic=True, batch=2)
+    a, rng_a = da.tvd_series(series, overlap=True, **kw)
+    b, rng_b = da.tvd_series(series, overlap=False, **kw)
+    assert rng_a == rng_b == (0, 5)
+    np.testing.assert_array_equal(a, b)
+    for t in range(5):
+        ref = oracle.split_bregman_tvd(np.ascontiguousarray(series[..., t]), dim=2, mu=0.1, omega=1.0, ell=1.0,
+                                       max_num_iter=6, isotropic=True)
+        assert rel_l2(a[..., t], ref) <= 1e-13
