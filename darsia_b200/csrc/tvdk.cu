@@ -51,13 +51,10 @@ struct max_threads : std::integral_constant<int, kMaxThreads> {};
 template <class K>
 struct max_threads<K, std::void_t<decltype(K::MAXT)>> : std::integral_constant<int, K::MAXT> {};
 
-template <class K, typename = void>
-struct min_blocks : std::integral_constant<int, 1> {};
+// (no minBlocksPerMultiprocessor argument: even "1" makes ptxas spend ~20 more registers per thread on
+//  every kernel, which costs occupancy -- measured -15 % on the shrink kernel, profiles/r1_ab_launch_bounds.txt)
 template <class K>
-struct min_blocks<K, std::void_t<decltype(K::MINB)>> : std::integral_constant<int, K::MINB> {};
-
-template <class K>
-__global__ void __launch_bounds__(max_threads<K>::value, min_blocks<K>::value) tvdk_kernel(const typename K::Args a, double* partials,
+__global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel(const typename K::Args a, double* partials,
                                                             unsigned* counters) {
   extern __shared__ __align__(16) unsigned char smem[];
   LaunchCtx lc;

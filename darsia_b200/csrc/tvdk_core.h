@@ -941,9 +941,6 @@ struct KFusedJ1x2 {
   static constexpr int PF2D = 3, PF3D = 3;
   static constexpr int ZC2D = 64;  // 4 extra march steps per chunk
   static constexpr int MAXT = 128;  // block size cap: the four-stage pipeline needs > 128 registers per thread
-#if defined(TVDK_X2_MINB)
-  static constexpr int MINB = TVDK_X2_MINB;  // tuning builds: resident blocks per SM asked of ptxas
-#endif
   typedef Col<T, D, LH, RH, 1, RHXV> C;
   struct Args {
     Geom g;

@@ -76,7 +76,7 @@ def split_bregman_tvd(
     device=None,
     return_info: bool = False,
     return_state: bool = False,
-    fused: bool = True,
+    fused: Union[bool, int] = True,
     tile=(0, 0, 0),
 ):
     """Split Bregman algorithm for TV denoising (drop-in for ``darsia.split_bregman_tvd``).
@@ -96,11 +96,14 @@ def split_bregman_tvd(
         return_info: also return a ``SolveInfo`` (iterations, increments, history).
         return_state: return ``(u, d, b)`` instead of ``u`` -- exactly the tuple the reference takes as
             ``x0`` (``split_bregman_tvd.py:93-97``), so consecutive frames of a series can be warm-started.
+        fused: kernel route (``tvdk_problem_t.fused``): True / 1 = fused and temporally blocked kernels where
+            they measured faster (default); False / 0 = one building-block kernel per step; 2 = every
+            blocked variant wherever it is implemented; 3 = as 1 but one outer iteration per launch.
+            All routes compute the same numbers (tests compare them).
+        tile: (block_x, block_y, planes_per_block) launch-shape override, 0 = default (tuning/tests).
     Device-resident callers: ``img`` (and ``x0``, ``mu``, ``omega``, ``ell``) may be
     ``torch`` tensors on the CUDA device; the result (and the state) then stays on that device as a
     tensor and no host<->device copy is made.
-        fused: allow the fused one-kernel-per-iteration path (default True).
-        tile: (block_x, block_y, planes_per_block) launch-shape override, 0 = default (tuning/tests).
     """
     on_device = _is_tensor(img)
     if not isinstance(img, np.ndarray) and not on_device:
