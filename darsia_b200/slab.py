@@ -172,6 +172,11 @@ class SlabSolver:
         self.t = eng.zero_fields(D)
         ws = eng.op_workspace()
         self.sums = torch.zeros(8, dtype=torch.float64, device=eng.device)  # 3 launches x up to 2 sums
+        self._tot = torch.zeros(2, dtype=torch.float64, device=eng.device)
+        # Boundary-first splitting of the CG kernels: measured +12 % on 2 GPUs, -4 % on 8 (1024^3: the NCCL
+        # transfers then share the SMs with the interior launch and every kernel pays two more small launches),
+        # +2..3 % for the fused Jacobi-1 kernel on 2 and on 8 GPUs (profiles/r1_slab_*).
+        self._split_cg = eng.world <= 4
         with device_guard(eng.device):  # ||img|| over all ranks (split_bregman_tvd.py:58)
             lib.check(lib.dot(C.byref(g), self.f.data_ptr(), self.f.data_ptr(), self.sums.data_ptr(), ws.data_ptr(),
                               ws.numel(), eng.stream()), "tvdk_dot")
@@ -186,7 +191,7 @@ class SlabSolver:
             self.rho, self.rho_prev, self.pq, self.alpha, self.beta = (
                 torch.zeros(1, dtype=torch.float64, device=eng.device) for _ in range(5))
 
-    def _split(self, launch, halo, nsum: int = 1, lo_planes: int = 0, hi_planes: int = 0):
+    def _split(self, launch, halo, nsum: int = 1, lo_planes: int = 0, hi_planes: int = 0, overlap: bool = True):
         """Boundary-first overlap of one kernel with the halo exchange of what it produces.
 
         ``launch(geom_ptr, sum_ptr)`` enqueues the kernel on the owned planes of ``geom``; it is called for
@@ -197,20 +202,22 @@ class SlabSolver:
         eng, sums = self.eng, self.sums
         nlo = max(self.HB, lo_planes) if eng.lo is not None else 0
         nhi = max(self.HB, hi_planes) if eng.hi is not None else 0
-        sums.zero_()
 
         def run(z0, z1, slot):
             gg = eng.sub_geom(z0, z1)
             launch(C.byref(gg), sums[slot * nsum:(slot + 1) * nsum].data_ptr())
 
-        if eng.world > 1 and eng.nown >= nlo + nhi + 1:
+        if overlap and eng.world > 1 and eng.nown >= nlo + nhi + 1:
+            if not (nlo and nhi):  # the slot of the missing end must not carry an old value
+                sums[nsum:3 * nsum].zero_()
             if nlo:
                 run(eng.zb, eng.zb + nlo, 1)
             if nhi:
                 run(eng.ze - nhi, eng.ze, 2)
             reqs = eng.exchange(halo, wait=False)
             run(eng.zb + nlo, eng.ze - nhi, 0)
-            sums[0:nsum].add_(sums[nsum:2 * nsum]).add_(sums[2 * nsum:3 * nsum])
+            torch.sum(sums[: 3 * nsum].view(3, nsum), dim=0, out=self._tot[:nsum])
+            sums[:nsum].copy_(self._tot[:nsum])
         else:
             run(eng.zb, eng.ze, 0)
             reqs = eng.exchange(halo, wait=False)
@@ -273,7 +280,7 @@ class SlabSolver:
                         lambda gp, sp: call(lib.cg_init(gp, iso, bm, bo, be, self.f.data_ptr(), t.data_ptr(), tcs,
                                                         u.data_ptr(), x.data_ptr(), r.data_ptr(), sp, wsp, wsn, s_),
                                             "tvdk_cg_init"),
-                        [(r, 0, 1, 1)], nsum=2)
+                        [(r, 0, 1, 1)], nsum=2, overlap=self._split_cg)
                     eng.allreduce(sums[0:2])
                     bnrm = torch.sqrt(sums[0:1])
                     atol = float(spec.tol) * bnrm
@@ -293,7 +300,7 @@ class SlabSolver:
                             lambda gp, sp: call(lib.cg_pq(gp, bo, be, pin.data_ptr(), r.data_ptr(), pout.data_ptr(),
                                                           beta.data_ptr(), 1 if i == 0 else 0, sp, wsp, wsn, s_),
                                                 "tvdk_cg_pq"),
-                            [(pout, 0, 1, 1)])
+                            [(pout, 0, 1, 1)], overlap=self._split_cg)
                         pq.copy_(eng.allreduce(sums[0:1]))
                         torch.div(rho, pq, out=alpha)
                         eng.finish(reqs)  # ghosts of p
@@ -301,7 +308,7 @@ class SlabSolver:
                         reqs = self._split(
                             lambda gp, sp: call(lib.cg_update(gp, bo, be, pout.data_ptr(), x.data_ptr(), r.data_ptr(),
                                                               alpha.data_ptr(), sp, wsp, wsn, s_), "tvdk_cg_update"),
-                            [(r, 0, 1, 1)] + ([(x, 0, 0, 1)] if (last or spec.tol > 0.0) else []))
+                            [(r, 0, 1, 1)] + ([(x, 0, 0, 1)] if (last or spec.tol > 0.0) else []), overlap=self._split_cg)
                         updated = True
                         rho_prev.copy_(rho)
                         rho.copy_(eng.allreduce(sums[0:1]))
@@ -313,7 +320,7 @@ class SlabSolver:
                     self._pending = self._split(
                         lambda gp, sp: call(lib.shrink(gp, iso, bm, be, x.data_ptr(), u.data_ptr(), u.data_ptr(),
                                                        t.data_ptr(), t.data_ptr(), tcs, sp, wsp, wsn, s_), "tvdk_shrink"),
-                        [(u, 0, 1, 1)] + [(t, d, 1, 1) for d in range(D)], lo_planes=1)
+                        [(u, 0, 1, 1)] + [(t, d, 1, 1) for d in range(D)], lo_planes=1, overlap=self._split_cg)
             inc2 = eng.allreduce(sums[0:1].clone())
             self.incs.append(torch.sqrt(inc2 / self.nrm2))
             ran += 1
