@@ -13,8 +13,16 @@ import os
 from typing import Optional
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# (TVDK_LIB: tuning runs compare alternative builds of the same CUDA library; there is still no CPU path)
-LIB_PATH = os.environ.get("TVDK_LIB") or os.path.join(HERE, "csrc", "libtvdk.so")
+LIB_PATH = os.path.join(HERE, "csrc", "libtvdk.so")
+# Tuning runs (tools/ab.sh) compare alternative BUILDS of the same CUDA sources: TVDK_LIB may name another
+# libtvdk*.so inside darsia_b200/csrc/ -- nothing else, and there is still no CPU path.
+_alt = os.environ.get("TVDK_LIB")
+if _alt:
+    _alt = os.path.abspath(_alt)
+    if os.path.dirname(_alt) == os.path.join(HERE, "csrc") and os.path.basename(_alt).startswith("libtvdk"):
+        LIB_PATH = _alt
+    else:
+        raise ImportError(f"TVDK_LIB={_alt!r}: only alternative builds libtvdk*.so inside darsia_b200/csrc are accepted")
 
 TVDK_F64, TVDK_F32 = 0, 1
 TVDK_SOLVER_JACOBI, TVDK_SOLVER_CG = 0, 1
