@@ -74,6 +74,8 @@ class Stat(C.Structure):
         ("jac_stop", C.c_int32),
         ("jac_sel", C.c_int32),
         ("cur_buf", C.c_int32),
+        ("e_init", C.c_double),
+        ("e_prev", C.c_double),
     ]
 
 
@@ -113,6 +115,27 @@ class Problem(C.Structure):
     ]
 
 
+class Chambolle(C.Structure):
+    """``tvdk_chambolle_t``."""
+
+    _fields_ = [
+        ("geom", Geom),
+        ("weight", C.c_double),
+        ("eps", C.c_double),
+        ("max_num_iter", C.c_int32),
+        ("check_every", C.c_int32),
+        ("f", C.c_void_p),
+        ("out", C.c_void_p),
+        ("p0", C.c_void_p),
+        ("p1", C.c_void_p),
+        ("p_comp_stride", C.c_int64),
+        ("workspace", C.c_void_p),
+        ("workspace_bytes", C.c_size_t),
+        ("stats", C.c_void_p),
+        ("history", C.c_void_p),
+    ]
+
+
 _PG = C.POINTER(Geom)
 _PC = C.POINTER(Coef)
 _VP = C.c_void_p
@@ -148,6 +171,7 @@ SIGNATURES = {
     "tvdk_cg_pq": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _I, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_update": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_jacobi_sweeps": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _I, C.POINTER(C.c_int), _VP, _SZ, _VP]),
+    "tvdk_chambolle": (C.c_int, [C.POINTER(Chambolle), _VP, C.POINTER(C.c_int)]),
     "tvdk_residual": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_mg_restrict": (C.c_int, [_PG, _PG, _VP, _VP, _VP]),
     "tvdk_mg_prolong_add": (C.c_int, [_PG, _PG, _VP, _VP, _VP]),

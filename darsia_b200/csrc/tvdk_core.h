@@ -215,7 +215,8 @@ enum FinKind {
   FIN_CGFIRST, // totals = {r.q, q.q}, q = A r_0          (single-pass CG route, K7)
   FIN_CGFUSED, // totals = {r.r, p.q, r.q, q.q}
   FIN_JTOL,    // totals = {sum (x_new - x)^2, sum x_in^2}
-  FIN_ENERGY   // totals = {sum (omega (x - f))^2, sum |mu G x|}
+  FIN_ENERGY,  // totals = {sum (omega (x - f))^2, sum |mu G x|}
+  FIN_CHAMB    // totals = {sum d^2, sum |grad out|}: Chambolle energy and stopping rule
 };
 
 struct Fin {
@@ -227,7 +228,9 @@ struct Fin {
   double* history;     // optional, [iter * nb + b]
   int iter, nb;
   int* ndone;          // number of converged problems (host polls it)
-  int buf_id;          // FIN_OUTER: buffer now holding u ; FIN_JTOL: buffer the sweep wrote
+  double weight;       // FIN_CHAMB: TV weight
+  double inv_size;     // FIN_CHAMB: 1 / number of voxels
+  int buf_id;          // FIN_OUTER: buffer now holding u ; FIN_JTOL: buffer the sweep wrote ; FIN_CHAMB: buffer read
   int first_sweep;     // FIN_JTOL: this sweep started from x0
 };
 
@@ -326,6 +329,22 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
         s.jac_stop = 1;
       else
         s.jac_sel = f.buf_id;
+    } break;
+    case FIN_CHAMB: {  // skimage _denoise_tv_chambolle_nd: E, E_init, E_previous, break test
+      const double e = (tot[0] + f.weight * tot[1]) * f.inv_size;
+      s.energy = e;
+      s.iters += 1;
+      s.cur_buf = f.buf_id;  // the p this iteration READ: the result is image + div of it
+      if (f.history) f.history[(long long)f.iter * f.nb + b] = e;
+      if (f.iter == 0) {
+        s.e_init = e;
+        s.e_prev = e;
+      } else if (fabs(s.e_prev - e) < f.eps * s.e_init) {
+        s.done = 1;
+        if (f.ndone) atomic_inc(f.ndone);
+      } else {
+        s.e_prev = e;
+      }
     } break;
     case FIN_ENERGY:  // split_bregman_tvd.py:71-77
       s.energy = 0.5 * tot[0] + tot[1];
@@ -2301,6 +2320,175 @@ struct KSelectCopy {
   TVDK_DEV void pre(const Args&, unsigned char*) {}
   TVDK_DEV void post(const Args&, unsigned char*) {}
   static TVDK_DEV void finalize(const Args&, int, const double*) {}
+};
+
+// ==========================================================================================
+// Chambolle's projection algorithm -- what darsia.tvd(img) runs by default through
+// skimage.restoration.denoise_tv_chambolle (restoration/tvd.py:77-83; third party, PARITY UNPINNED,
+// see oracle/chambolle_oracle.py).  One launch = one iteration, every axis spatial:
+//     d = div p ; out = f + d ; g = grad out ; n = |g| ; p <- (p - tau g) / (1 + tau/weight n)
+//     sums: d.d and sum n (energy).   out(j) is formed for plane j, the update of plane j-1 follows
+//     one step later (it needs out(j)); out is needed on a +1 halo, p on -1 of that.
+//   MODE 0: the iteration (p_in -> p_out);  MODE 1: the result  out = f + div p  (p chosen per problem
+//           by stats[b].cur_buf: the p the last executed iteration read)
+//     Shared rows: [slot*(D-1) + a-1] = p_a(j) (a >= 1), [2(D-1) + slot] = out ring.
+// ==========================================================================================
+template <typename T, int D, int MODE>
+struct KChamb {
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = 1, RH = 1, NRED = MODE == 0 ? 2 : 0, NROWS = 2 * D;
+  static constexpr int PF2D = 3, PF3D = 3;
+  typedef Col<T, D, LH, RH> C;
+  struct Args {
+    Geom g;
+    const T* f;
+    const T* p_in;   // MODE 0: D components, stride pcs ; MODE 1: buffer 0
+    const T* p_in1;  // MODE 1: buffer 1
+    T* p_out;        // MODE 0
+    T* out;          // MODE 1
+    long long pcs;
+    T tau, tau_over_w;
+    const tvdk_stat_t* skip;  // MODE 0: done ; MODE 1: cur_buf selects the p buffer
+    Fin fin;
+  };
+  C c;
+  int j, rowe;
+  const T* pin;
+  Vec<T> pc[D], pprev[D], p0_lo, out_prev, f_c;
+  Vec<T> nx_p[D], nx_f;
+  double red[2];
+
+  TVDK_DEV void load_plane(const Args& a, long long o) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) nx_p[d] = ldo(pin + d * a.pcs, o);
+    nx_f = ldo(a.f, o);
+  }
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char*) {
+    if (MODE == 0 && a.skip && a.skip[lc.bz].done) return false;
+    pin = (MODE == 1 && a.skip && a.skip[lc.bz].cur_buf == 1) ? a.p_in1 : a.p_in;
+    c.setup(a.g, lc);
+    rowe = C::row_elems(lc.ntx, lc.nty);
+    red[0] = red[1] = 0.0;
+    j = c.z0;
+    const long long o = c.at(a.g, j);
+    p0_lo = vsplat<T>((T)0);
+    if (j > 0) p0_lo = ldo(pin, o - c.s0b);
+    out_prev = p0_lo;
+#pragma unroll
+    for (int d = 0; d < D; ++d) pprev[d] = p0_lo;
+    load_plane(a, o);
+    return true;
+  }
+  // the iteration marches one plane past the chunk (out(z1) closes the gradient of plane z1 - 1)
+  TVDK_DEV bool more() const { return MODE == 0 ? j <= c.z1 : j < c.z1; }
+
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if (j >= a.g.n0) return;
+    const int slot = j & 1;
+#pragma unroll
+    for (int d = 0; d < D; ++d) pc[d] = nx_p[d];
+    f_c = nx_f;
+#pragma unroll
+    for (int d = 1; d < D; ++d) sst(srow<T>(smem, slot * (D - 1) + d - 1, rowe), c, pc[d]);
+    const int last = MODE == 0 ? c.z1 : c.z1 - 1;
+    if (j + 1 <= last && j + 1 < a.g.n0) load_plane(a, c.cur + c.s0b);
+    if (c.pf_ok(j)) {
+      const long long o = c.cur + c.pfb;
+      pfo(a.f, o);
+#pragma unroll
+      for (int d = 0; d < D; ++d) pfo(pin + d * a.pcs, o);
+    }
+  }
+
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    const int slot = j & 1;
+    Vec<T> out_c = out_prev;
+    if (j < a.g.n0) {
+      // d = sum_a ( p_a[k - e_a] (k_a >= 1) - p_a[k] )
+      Vec<T> d;
+#pragma unroll
+      for (int v = 0; v < V; ++v) d.v[v] = -pc[0].v[v];
+      if (D == 3) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) d.v[v] = d.v[v] - pc[1].v[v];
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) d.v[v] = d.v[v] - pc[D - 1].v[v];
+      if (j > 0) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) d.v[v] += p0_lo.v[v];
+      }
+      if (D == 3 && c.hylo) {
+        const Vec<T> ym = sym(srow<T>(smem, slot * (D - 1) + 0, rowe), c);
+#pragma unroll
+        for (int v = 0; v < V; ++v) d.v[v] += ym.v[v];
+      }
+      {
+        const T xl = sxm(srow<T>(smem, slot * (D - 1) + (D - 2), rowe), c);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const T left = v > 0 ? pc[D - 1].v[v > 0 ? v - 1 : 0] : xl;
+          if (c.hl[v]) d.v[v] += left;
+        }
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) out_c.v[v] = f_c.v[v] + d.v[v];
+      if (MODE == 1) {
+        sto(c, a.out, c.cur, out_c);
+      } else {
+        sst(srow<T>(smem, 2 * (D - 1) + slot, rowe), c, out_c);
+        if (c.st && j < c.z1) {
+#pragma unroll
+          for (int v = 0; v < V; ++v)
+            if (c.okc[v]) red[0] += (double)d.v[v] * (double)d.v[v];
+        }
+      }
+    }
+    if (MODE == 0 && j > c.z0) {
+      // gradient of out at plane j-1, norm, projection step for p(j-1)
+      const int zo = j - 1;
+      const T* orow = srow<T>(smem, 2 * (D - 1) + (zo & 1), rowe);
+      Vec<T> g[D];
+      const bool zhi = zo + 1 < a.g.n0;
+#pragma unroll
+      for (int v = 0; v < V; ++v) g[0].v[v] = zhi ? out_c.v[v] - out_prev.v[v] : (T)0;
+      if (D == 3) {
+        const Vec<T> yp = syp(orow, c);
+#pragma unroll
+        for (int v = 0; v < V; ++v) g[1].v[v] = c.hyhi ? yp.v[v] - out_prev.v[v] : (T)0;
+      }
+      {
+        const T xr = sxp(orow, c);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          const T right = v < V - 1 ? out_prev.v[v < V - 1 ? v + 1 : 0] : xr;
+          g[D - 1].v[v] = c.hr[v] ? right - out_prev.v[v] : (T)0;
+        }
+      }
+      Vec<T> pn[D];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        T s2 = g[0].v[v] * g[0].v[v];
+#pragma unroll
+        for (int d = 1; d < D; ++d) s2 = s2 + g[d].v[v] * g[d].v[v];
+        const T nrm = tsqrt(s2);
+        const T den = nrm * a.tau_over_w + (T)1;
+#pragma unroll
+        for (int d = 0; d < D; ++d) pn[d].v[v] = tdiv(pprev[d].v[v] - a.tau * g[d].v[v], den);
+        if (c.st && c.okc[v]) red[1] += (double)nrm;
+      }
+      const long long oo = c.cur - c.s0b;
+#pragma unroll
+      for (int d = 0; d < D; ++d) sto(c, a.p_out + d * a.pcs, oo, pn[d]);
+    }
+    p0_lo = pc[0];
+#pragma unroll
+    for (int d = 0; d < D; ++d) pprev[d] = pc[d];
+    out_prev = out_c;
+    c.cur += c.s0b;
+    ++j;
+  }
+  static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED > 0 ? NRED : 1, b, tot); }
 };
 
 // Multigrid grid transfer (utils/linear_solvers/mg.py).  One thread per element of the TARGET grid.

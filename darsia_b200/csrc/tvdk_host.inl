@@ -291,7 +291,8 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   LaunchCfg c = plan_launch<KShrink<T, D, false, false>, T, D>(g, tune, false);
   LaunchCfg d = plan_launch<KDot<T, D, 0>, T, D>(g, tune, false);
   LaunchCfg e = plan_launch<KCgFused<T, D, false>, T, D>(g, tune, true);
-  size_t m = 0;
+  LaunchCfg ch = plan_launch<KChamb<T, D, 0>, T, D>(g, tune, true);
+  size_t m = (size_t)ch.gx * ch.gy * ch.gz * 2;
   if constexpr (D == 2) {
     LaunchCfg x2 = plan_launch<KFusedJ1x2<T, false, false>, T, D>(g, tune, true);
     m = std::max(m, (size_t)x2.gx * x2.gy * x2.gz * 2);
@@ -1193,6 +1194,65 @@ static int cgfused_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk
 }
 
 template <typename T, int D>
+static int chambolle_impl(const tvdk_chambolle_t* c, void* stream, int* iters_launched) {
+  const Geom g = make_geom(c->geom);
+  const Tune tune = merge_tune(0, 0, 0);
+  Scratch sc;
+  TVDK_TRY((op_scratch<T, D>(&c->geom, c->workspace, c->workspace_bytes, &sc, stream)));
+  tvdk_stat_t* st = c->stats;
+  TVDK_TRY(backend::memset_async(st, 0, sizeof(tvdk_stat_t) * (size_t)g.nb, stream));
+  TVDK_TRY(backend::memset_async(sc.ndone, 0, sizeof(int), stream));
+  T* P[2] = {reinterpret_cast<T*>(c->p0), reinterpret_cast<T*>(c->p1)};
+  const double tau = 1.0 / (2.0 * D);
+  const int check_every = c->check_every > 0 ? c->check_every : 8;
+  int launched = 0, slot = 0;
+  bool pending[2] = {false, false}, all_done = false;
+  for (int it = 0; it < c->max_num_iter && !all_done; ++it) {
+    typedef KChamb<T, D, 0> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.f = reinterpret_cast<const T*>(c->f);
+    a.p_in = P[it & 1]; a.p_out = P[(it & 1) ^ 1]; a.pcs = c->p_comp_stride;
+    a.tau = (T)tau; a.tau_over_w = (T)(tau / c->weight);
+    a.skip = st;
+    a.fin = no_fin();
+    a.fin.kind = FIN_CHAMB; a.fin.stats = st; a.fin.eps = c->eps; a.fin.history = c->history; a.fin.iter = it;
+    a.fin.nb = g.nb; a.fin.ndone = sc.ndone; a.fin.buf_id = it & 1; a.fin.weight = c->weight;
+    a.fin.inv_size = 1.0 / ((double)g.n0 * g.ny * g.nx);
+    TVDK_TRY((run<K, T, D>(a, g, tune, true, sc, stream)));
+    ++launched;
+    if ((launched % check_every) == 0 && it + 1 < c->max_num_iter) {  // stop enqueueing once every image is done
+      const int other = slot ^ 1;
+      TVDK_TRY(backend::poll_begin(slot, sc.ndone, stream));
+      pending[slot] = true;
+      if (pending[other]) {
+        int v = 0;
+        TVDK_TRY(backend::poll_end(other, &v));
+        pending[other] = false;
+        if (v >= g.nb) all_done = true;
+      }
+      slot = other;
+    }
+  }
+  for (int s2 = 0; s2 < 2; ++s2)
+    if (pending[s2]) {
+      int v = 0;
+      TVDK_TRY(backend::poll_end(s2, &v));
+    }
+  {  // the result: image + div of the p the last executed iteration read (stats[b].cur_buf)
+    typedef KChamb<T, D, 1> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.f = reinterpret_cast<const T*>(c->f);
+    a.p_in = P[0]; a.p_in1 = P[1]; a.pcs = c->p_comp_stride; a.out = reinterpret_cast<T*>(c->out);
+    a.skip = st; a.fin = no_fin();
+    TVDK_TRY((run<K, T, D>(a, g, tune, true, sc, stream)));
+  }
+  if (iters_launched) *iters_launched = launched;
+  return 0;
+}
+
+template <typename T, int D>
 static int sweeps_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_coef_t* el, void* xa, const void* rhs,
                        void* xb, int n, int* result_in_b, void* ws, size_t wsb, void* stream) {
   OpCtx<T, D> o;
@@ -1415,4 +1475,17 @@ int tvdk_fused_jacobi1_x2(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t
     return fail(TVDK_ERR_INVALID, "fused_jacobi1_x2 works on whole images");
   TVDK_C_ENTRY(g, (fj1x2_impl<T, D>(g, isotropic, mu, omega, ell, f, u_in, u_out, t_in, t_out, t_comp_stride,
                                     sum_out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_chambolle(const tvdk_chambolle_t* c, void* stream, int* iters_launched) {
+  if (!c) return fail(TVDK_ERR_INVALID, "problem is NULL");
+  TVDK_TRY(check_geom(&c->geom));
+  if (c->max_num_iter < 1) return fail(TVDK_ERR_INVALID, "max_num_iter must be >= 1");
+  if (!(c->weight > 0.0)) return fail(TVDK_ERR_INVALID, "weight must be positive");
+  if (!c->f || !c->out || !c->p0 || !c->p1 || !c->stats) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  if (c->geom.z_begin != 0 || c->geom.z_end != c->geom.n[0] || c->geom.g0_off != 0 || c->geom.g0_n != c->geom.n[0])
+    return fail(TVDK_ERR_INVALID, "tvdk_chambolle works on whole images");
+  int rc = 0;
+  TVDK_DISPATCH(c->geom, rc = (chambolle_impl<T, D>(c, stream, iters_launched)));
+  return rc;
 }

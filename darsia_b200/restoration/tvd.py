@@ -61,10 +61,15 @@ class TVD:
                 eps=self.eps,
                 **self.kwargs,
             )
-        elif self.method in ("chambolle", "anisotropic bregman", "isotropic bregman"):
+        elif self.method == "chambolle":  # tvd.py:77-83 -> skimage.restoration.denoise_tv_chambolle
+            # third-party algorithm restated without scikit-image at hand: parity unpinned (chambolle.py)
+            from .chambolle import denoise_tv_chambolle
+
+            return denoise_tv_chambolle(img, weight=self.weight, max_num_iter=self.max_num_iter, eps=self.eps)
+        elif self.method in ("anisotropic bregman", "isotropic bregman"):
             raise NotImplementedError(
-                f"method {self.method!r} is scikit-image's algorithm (tvd.py:77-101) and is not part of the "
-                "B200 path; use method='heterogeneous bregman'"
+                f"method {self.method!r} is scikit-image's Gauss-Seidel split Bregman (tvd.py:85-101, Cython, "
+                "sequential by construction) and is not part of the B200 path; use method='heterogeneous bregman'"
             )
         else:
             raise ValueError(f"Method {self.method} not supported.")

@@ -90,6 +90,7 @@ typedef struct tvdk_stat {
   int32_t cg_stop, cg_first, cg_iters;
   int32_t jac_stop, jac_sel;
   int32_t cur_buf;  /* internal: which buffer holds the iterate */
+  double e_init, e_prev; /* Chambolle: energy of iteration 0 and of the previous iteration */
 } tvdk_stat_t;
 
 /* One call of darsia.split_bregman_tvd (restoration/split_bregman_tvd.py:14-27). */
@@ -259,6 +260,26 @@ int tvdk_cg_fused(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coe
 int tvdk_jacobi_sweeps(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, void* xa,
                        const void* rhs, void* xb, int nsweeps, int* result_in_b, void* workspace,
                        size_t workspace_bytes, void* stream);
+
+/* One call of skimage.restoration.denoise_tv_chambolle(image, weight, eps, max_num_iter) with every axis
+ * spatial -- what darsia.tvd(img) runs by default (restoration/tvd.py:77-83).  Third-party algorithm,
+ * PARITY UNPINNED (oracle/chambolle_oracle.py).  geom.nb must be 1 or a batch of independent images. */
+typedef struct tvdk_chambolle {
+  tvdk_geom_t geom;
+  double weight, eps;
+  int32_t max_num_iter;    /* >= 1 */
+  int32_t check_every;     /* host polls the device "all done" flag every N iterations (0: 8) */
+  const void* f;           /* device: image field */
+  void* out;               /* device: result field */
+  void* p0;                /* device: dim fields, zero on entry (the dual variable) */
+  void* p1;                /* device: dim fields, scratch */
+  int64_t p_comp_stride;
+  void* workspace;         /* device, tvdk_op_workspace_bytes(&geom) bytes */
+  size_t workspace_bytes;
+  tvdk_stat_t* stats;      /* device, nb entries: iters, energy, done */
+  double* history;         /* device or NULL: max_num_iter * nb energies */
+} tvdk_chambolle_t;
+int tvdk_chambolle(const tvdk_chambolle_t* c, void* stream, int* iters_launched);
 
 /* Multigrid building blocks (darsia.MG, utils/linear_solvers/mg.py:94-242; the V-cycle itself is
  * host logic over these and tvdk_jacobi_sweep):

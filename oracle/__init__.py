@@ -14,6 +14,7 @@ hot-path files verbatim (``tests/golden/generate_golden.py``) and committed as
 fixtures under ``tests/golden/*.npz``.
 """
 
+from .chambolle_oracle import denoise_tv_chambolle  # noqa: F401  (parity unpinned, see its header)
 from .tvd_oracle import (  # noqa: F401
     CG,
     H1_regularization,

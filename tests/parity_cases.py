@@ -153,3 +153,18 @@ def run_jacobi1_pair(da, oracle, shape, tile, nit, iso, het, dtype, batch):
     one = da.split_bregman_tvd(img, dim=2, max_num_iter=nit, isotropic=iso, solver=da.Jacobi(maxiter=1), tile=tile,
                                fused=3, **kw)  # 3: one iteration per launch
     return out, one, ref, info, hist
+
+
+def chambolle_cases():
+    """(shape, dtype, weight, eps, max_num_iter) for ``method="chambolle"`` (every axis spatial)."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((37, 52), f8, 0.1, 2e-4, 200),
+        ((37, 150), f8, 0.3, 1e-5, 60),
+        ((11, 19, 33), f8, 0.1, 2e-4, 200),
+        ((37, 52), f4, 0.1, 2e-4, 200),
+        ((3, 40), f8, 0.1, 2e-4, 30),
+        ((1, 40), f8, 0.1, 2e-4, 10),
+        ((2, 1, 7), f8, 0.1, 0.0, 5),
+        ((24, 40, 3), f8, 0.2, 2e-4, 1),
+    ]

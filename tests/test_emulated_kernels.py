@@ -11,7 +11,7 @@ import pytest
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from emu.harness import emulated
-from parity_cases import (adaptive_cases, cg_fixed_count_cases, jacobi1_pair_cases, jacobi_blocked_cases,
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, chambolle_cases, jacobi1_pair_cases, jacobi_blocked_cases,
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
@@ -179,3 +179,37 @@ def test_series_sub_batches_overlapped():
         ref = oracle.split_bregman_tvd(np.ascontiguousarray(series[..., t]), dim=2, mu=0.1, omega=1.0, ell=1.0,
                                        max_num_iter=6, isotropic=True)
         assert rel_l2(a[..., t], ref) <= 1e-13
+
+
+@pytest.mark.parametrize("shape,dtype,weight,eps,nit", chambolle_cases())
+def test_chambolle_matches_its_restatement(shape, dtype, weight, eps, nit):
+    """method="chambolle" (scikit-image's algorithm; PARITY UNPINNED -- the checker is a restatement of the
+    published algorithm, not scikit-image itself): same result, same stopping iteration, same energies."""
+    from golden.generate_golden import phantom
+
+    from darsia_b200.restoration.chambolle import denoise_tv_chambolle
+
+    img = phantom(shape, 5, dtype)
+    ref, ri = oracle.denoise_tv_chambolle(img, weight, eps, nit, return_info=True)
+    out, oi = denoise_tv_chambolle(img, weight, eps, nit, return_info=True)
+    assert out.dtype == img.dtype and out.shape == img.shape
+    assert oi["iterations"] == ri["iterations"]
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 1e-6)
+    np.testing.assert_allclose(oi["energies"], ri["energies"], rtol=(1e-12 if dtype == np.float64 else 1e-5))
+
+
+def test_tvd_default_method_is_chambolle():
+    """darsia.tvd(img) defaults to method="chambolle", weight=1.0 (tvd.py:132-139); properties that hold for the
+    algorithm independently of any implementation: one iteration returns the image, the mean is preserved
+    (out = image + div p and div p sums to zero), the total variation drops."""
+    from golden.generate_golden import phantom
+
+    img = phantom((40, 56), 12)
+    out = da.tvd(img, weight=0.2)
+    assert rel_l2(out, oracle.denoise_tv_chambolle(img, 0.2, 2e-4, 200)) <= 1e-13
+    np.testing.assert_array_equal(da.tvd(img, weight=0.2, max_num_iter=1), img)
+    assert abs(out.mean() - img.mean()) <= 1e-14
+    tv = lambda x: np.abs(np.diff(x, axis=0)).sum() + np.abs(np.diff(x, axis=1)).sum()  # noqa: E731
+    assert tv(out) < 0.6 * tv(img)
+    with pytest.raises(NotImplementedError):
+        da.tvd(img, method="isotropic bregman")

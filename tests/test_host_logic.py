@@ -69,7 +69,7 @@ def test_errors(img):
     with pytest.raises(ValueError):
         da.tvd(img, method="no such method")
     with pytest.raises(NotImplementedError):
-        da.tvd(img, method="chambolle")
+        da.tvd(img, method="anisotropic bregman")  # scikit-image's sequential Gauss-Seidel scheme
     with pytest.raises(TypeError):
         da.split_bregman_tvd((img * 255).astype(np.uint8))
     with pytest.raises(TypeError):
