@@ -72,6 +72,9 @@ SLAB_CASES = [
     (2, dict(kind="slab", shape=(10, 8, 24), dtype="float32", iso=False, solver="j1", nit=8)),
     (2, dict(kind="slab", shape=(40, 70), dtype="float64", iso=False, solver="j1", nit=6)),
     (2, dict(kind="slab", shape=(11, 9, 20), dtype="float64", iso=False, solver="j1", nit=60, eps=2e-2)),
+    # 5 ranks: CG kernels are launched whole (the boundary-first split is for <= 4 ranks), fused Jacobi-1 split
+    (5, dict(kind="slab", shape=(27, 6, 12), dtype="float64", iso=True, solver="cg4", nit=3)),
+    (5, dict(kind="slab", shape=(46, 6, 12), dtype="float64", iso=False, solver="j1", nit=4)),
 ]
 
 
