@@ -7,6 +7,7 @@ because the arithmetic is the reference's up to reciprocal-multiplies and FMA co
 import numpy as np
 import pytest
 
+import fuzz_cases
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from parity_cases import (adaptive_cases, cg_fixed_count_cases, chambolle_cases, jacobi1_pair_cases, jacobi_blocked_cases,
@@ -284,3 +285,10 @@ def test_tvd_default_method_is_chambolle(da):
     assert tv(out) < 0.6 * tv(img)
     with pytest.raises(NotImplementedError):
         da.tvd(img, method="isotropic bregman")
+
+
+@pytest.mark.parametrize("case", fuzz_cases.draw(seed=12, n=80), ids=lambda c: f"{c['kind']}-{c['dim']}d-f{c['fused']}")
+def test_random_problems_over_every_route(da, case):
+    """Seeded random shapes / tiles / batches / dtypes / coefficient maps / solvers / kernel routes vs the oracle."""
+    out, ref = fuzz_cases.run(da, oracle, case)
+    assert rel_l2(out, ref) <= (1e-12 if case["dtype"] == np.float64 else 1e-5)  # north_star's bars are 1e-10 / 1e-5
