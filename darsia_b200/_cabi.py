@@ -76,6 +76,8 @@ class Stat(C.Structure):
         ("cur_buf", C.c_int32),
         ("e_init", C.c_double),
         ("e_prev", C.c_double),
+        ("rho_pred", C.c_double),
+        ("cg_pred_dev", C.c_double),
     ]
 
 

@@ -307,6 +307,7 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
       s.alpha = al;
       s.rho_prev = rho;
       s.beta = rho_next / rho;
+      s.rho_pred = rho_next;
       s.cg_first = 0;
       s.cg_iters = 1;
     } break;
@@ -314,6 +315,9 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
       const double rho = tot[0];
       const double al = rho / tot[1];
       const double rho_next = fma(al, fma(al, tot[3], -2.0 * tot[2]), rho);
+      const double dev = fabs(s.rho_pred - rho) / rho;  // how well the previous launch predicted this rho
+      if (dev > s.cg_pred_dev) s.cg_pred_dev = dev;
+      s.rho_pred = rho_next;
       s.rho_prev = s.rho;
       s.rho = rho;
       s.pq = tot[1];

@@ -374,7 +374,9 @@ static FieldPlan field_plan(const tvdk_problem_t* p) {
   // test would act on a predicted instead of a summed residual norm
   // ... and 2-D only: in 3-D its two halo rows on each side of y cost more (0.5 of the HBM peak
   // measured, profiles/r1_pf_sweep2.txt) than the 2 words per iteration it saves
-  fp.cgfused = fp.cg && p->fused && p->solver_tol == 0.0 && (p->geom.dim == 2 || p->fused >= 2);
+  // ... and not with the adaptive ell schedule: ell = 1/|grad u| makes the systems so ill-conditioned that the
+  // predicted rho costs 3-4 more digits than the directly summed one (2e-7 vs 1e-12 against the oracle)
+  fp.cgfused = fp.cg && p->fused && p->solver_tol == 0.0 && (p->geom.dim == 2 || p->fused >= 2) && !fp.adapt;
   fp.jac = !fp.cg;
   const int D = p->geom.dim;
   int n = 0;

@@ -40,6 +40,7 @@ class SolveInfo:
     history: Optional[np.ndarray]  # (max_num_iter, nb) relative increments (NaN where not run)
     energy: Optional[np.ndarray]  # (max_num_iter, nb) energies when verbose
     launched: int  # outer iterations enqueued by the host
+    cg_pred_dev: Optional[np.ndarray] = None  # single-pass CG: largest relative deviation of the predicted rho
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -309,4 +310,5 @@ class Engine:
             history=None if hist is None else hist.cpu().numpy().reshape(-1, self.nb),
             energy=None if ehist is None else ehist.cpu().numpy().reshape(-1, self.nb),
             launched=int(launched.value),
+            cg_pred_dev=np.array([r.cg_pred_dev for r in recs]),
         )

@@ -91,6 +91,9 @@ typedef struct tvdk_stat {
   int32_t jac_stop, jac_sel;
   int32_t cur_buf;  /* internal: which buffer holds the iterate */
   double e_init, e_prev; /* Chambolle: energy of iteration 0 and of the previous iteration */
+  /* single-pass CG (K7): the predicted rho of the next iteration, and the largest relative deviation
+   * |rho_predicted - rho_summed| / rho_summed seen during the solve (diagnostic: ~1e-15 on well-conditioned systems) */
+  double rho_pred, cg_pred_dev;
 } tvdk_stat_t;
 
 /* One call of darsia.split_bregman_tvd (restoration/split_bregman_tvd.py:14-27). */

@@ -39,7 +39,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     # sizes the C side computes with sizeof(tvdk_stat_t)/sizeof(double|int)
-    assert ctypes.sizeof(_cabi.Stat) == 12 * 8 + 8 * 4 + 2 * 8
+    assert ctypes.sizeof(_cabi.Stat) == 12 * 8 + 8 * 4 + 4 * 8
     assert ctypes.sizeof(_cabi.Geom) == 11 * 4
     assert ctypes.sizeof(_cabi.Coef) == 24
 

@@ -221,3 +221,17 @@ def test_random_problems_over_every_route(case):
     """Seeded random shapes / tiles / batches / dtypes / coefficient maps / solvers / kernel routes vs the oracle."""
     out, ref = fuzz_cases.run(da, oracle, case)
     assert rel_l2(out, ref) <= (1e-12 if case["dtype"] == np.float64 else 1e-5)  # north_star's bars are 1e-10 / 1e-5
+
+
+def test_single_pass_cg_predicted_rho_diagnostic():
+    """K7 predicts rho = r.r of the next CG iteration from the sums of the current one; the largest relative
+    deviation from the directly summed value is recorded per problem (tvdk_stat_t.cg_pred_dev)."""
+    from golden.generate_golden import phantom
+
+    img = phantom((60, 200, 2), 4)
+    out, info = da.split_bregman_tvd(img, mu=0.1, omega=1.0, ell=1.0, isotropic=True, max_num_iter=20,
+                                     solver=da.CG(maxiter=10, tol=0.0), return_info=True)
+    assert info.cg_pred_dev.shape == (2,) and np.all(info.cg_pred_dev > 0) and np.all(info.cg_pred_dev < 1e-12)
+    ref = oracle.split_bregman_tvd(img, mu=0.1, omega=1.0, ell=1.0, isotropic=True, max_num_iter=20,
+                                   solver=oracle.CG(maxiter=10, tol=0.0))
+    assert rel_l2(out, ref) <= 1e-13
