@@ -498,7 +498,9 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
   };
 
   bool het = k.sc.hetero != 0;
-  const bool het0 = het;
+  // the Jacobi sweeps only see omega and ell (initial values, k0): a per-voxel mu alone -- the usual
+  // "weight = mask * mu" case, examples/regularization.py:13-22 -- leaves them on the scalar kernels
+  const bool het0 = k0.omega.p != nullptr || k0.ell.p != nullptr;
 
   // shrink + Bregman update + in-place u update, shared by the unfused routes
   const int stat_dstride = (int)(sizeof(tvdk_stat_t) / sizeof(double));

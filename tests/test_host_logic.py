@@ -118,3 +118,25 @@ def test_standalone_solvers(img):
         s_ref = mk(oracle)
         s_ref.reset()
         assert rel_l2(mk(da)(x0=img, rhs=rhs), s_ref(x0=img, rhs=rhs)) < 1e-12
+
+
+def test_reference_example_script_runs(tmp_path, capsys):
+    """examples/regularization.py is the reference's example with ``darsia`` replaced by ``darsia_b200``
+    (heterogeneous weight, Jacobi(20), 3-D; then H1 regularisation)."""
+    import os
+    import runpy
+    import sys
+
+    from conftest import ROOT
+    from golden.generate_golden import phantom
+
+    path = tmp_path / "vol.npy"
+    np.save(path, phantom((12, 20, 28), 3))
+    argv = sys.argv
+    sys.argv = ["examples/regularization.py", str(path)]
+    try:
+        runpy.run_path(os.path.join(ROOT, "examples", "regularization.py"), run_name="__main__")
+    finally:
+        sys.argv = argv
+    out = capsys.readouterr().out
+    assert "TVD" in out and "H1" in out
