@@ -9,12 +9,14 @@ matplotlib; image I/O and plotting are outside this package's scope, so the volu
 file (or is synthesised) and the result is summarised on stdout.
 """
 
+import os
 import sys
 import time
 
 import numpy as np
 
-import darsia_b200 as darsia
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+import darsia_b200 as darsia  # noqa: E402
 
 if len(sys.argv) > 1:
     vol = np.load(sys.argv[1]).astype(np.float64)
