@@ -31,6 +31,10 @@ img = darsia.Image(vol)  # duck-typed stand-in for darsia.Image: .img + .copy()
 mu = np.ones_like(img.img)
 mu[:, 0:100, :] = 0.5
 
+# (the first GPU call of a process pays for the CUDA context and for loading the kernels -- about 3 s; keep it
+#  out of the timings below)
+darsia.tvd(np.zeros((8, 8, 32)) + 0.5, method="heterogeneous bregman", dim=3, max_num_iter=1)
+
 t0 = time.perf_counter()
 img_regularized_tvd = darsia.tvd(  # examples/regularization.py:18-30
     img=img,
