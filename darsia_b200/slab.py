@@ -9,7 +9,7 @@ boundary rules are evaluated on global plane indices inside the kernels (``tvdk_
 single-GPU run; only the summation order of the reductions differs (about 1e-16 relative).
 
 Reference semantics: ``split_bregman_tvd`` (restoration/split_bregman_tvd.py:14-177) with
-``Jacobi`` (jacobi.py:74-133, without ``tol``) or ``CG`` (cg.py:16-59 + SciPy's recurrence).
+``Jacobi`` (jacobi.py:74-133, incl. the ``tol`` branch) or ``CG`` (cg.py:16-59 + SciPy's recurrence).
 The reference itself has no distributed code; this is row (e) of SURVEY.md section 8.
 """
 
@@ -139,8 +139,6 @@ class SlabSolver:
         if len(global_shape) != dim:
             raise AssertionError("slab decomposition handles one volume (no batch axes)")
         self.spec = _solver_spec(solver)
-        if self.spec.kind == _cabi.TVDK_SOLVER_JACOBI and self.spec.tol is not None:
-            raise NotImplementedError("Jacobi with tol is not implemented for slabs")
         if ell is None:
             ell = 2 * mu
         _check_positive("ell", ell)
@@ -148,7 +146,7 @@ class SlabSolver:
         self.cdtype = np.dtype(dtype)
         self.eng = eng = SlabEngine(global_shape, rank, world, dtype=self.cdtype, device=device, group=group)
         self._coefs = [self._coef(v, n) for v, n in ((mu, "mu"), (omega, "omega"), (ell, "ell"))]
-        self.fused = self.spec.kind == _cabi.TVDK_SOLVER_JACOBI and self.spec.maxiter == 1
+        self.fused = self.spec.kind == _cabi.TVDK_SOLVER_JACOBI and self.spec.maxiter == 1 and self.spec.tol is None
         self.cur = 0
         self.incs: List[torch.Tensor] = []
         self.done = False
@@ -257,12 +255,28 @@ class SlabSolver:
                     call(lib.rhs(bg, iso, bm, bo, be, self.f.data_ptr(), t.data_ptr(), tcs, self.rhs.data_ptr(), wsp, wsn,
                                  s_), "tvdk_rhs")
                     xin = u
+                    x0n2 = None
                     for k in range(spec.maxiter):
-                        xout = self.xa if k % 2 == 0 else self.xb
+                        xout = self.xb if xin is self.xa else self.xa
                         eng.exchange([(xin, 0, 1, 1)])
                         call(lib.jacobi_sweep(bg, bo, be, xin.data_ptr(), self.rhs.data_ptr(), xout.data_ptr(), wsp, wsn,
                                               s_), "tvdk_jacobi_sweep")
+                        if spec.tol is not None:
+                            # jacobi.py:118-131 over the whole volume: err = ||x_new - x|| / ||x0||; on convergence the
+                            # PREVIOUS iterate is kept (one host sync per sweep, only with a tolerance)
+                            if x0n2 is None:
+                                call(lib.dot(bg, xin.data_ptr(), xin.data_ptr(), sums.data_ptr(), wsp, wsn, s_), "tvdk_dot")
+                                x0n2 = float(eng.allreduce(sums[0:1].clone()).item())
+                            call(lib.norm_diff2(bg, xout.data_ptr(), xin.data_ptr(), sums.data_ptr(), wsp, wsn, s_),
+                                 "tvdk_norm_diff2")
+                            d2 = float(eng.allreduce(sums[0:1].clone()).item())
+                            with np.errstate(divide="ignore", invalid="ignore"):
+                                if np.sqrt(d2) / np.sqrt(x0n2) < spec.tol:
+                                    break
                         xin = xout
+                    if xin is u:  # converged before the first accepted sweep: u+ = u (the shrink kernel needs a copy)
+                        self.xa.copy_(u)
+                        xin = self.xa
                     eng.exchange([(xin, 0, 0, 1)])
                     call(lib.shrink(bg, iso, bm, be, xin.data_ptr(), u.data_ptr(), u.data_ptr(), t.data_ptr(),
                                     t.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, s_), "tvdk_shrink")
@@ -376,7 +390,7 @@ def split_bregman_tvd_slab(
         img_owned: this rank's planes ``[s, e) = slab_range(global_shape[0], rank, world)`` of the image.
         global_shape: shape of the whole volume.
         mu, omega, ell: scalars, or per-voxel maps given as this rank's owned planes.
-        Other arguments as ``split_bregman_tvd``; ``solver`` is ``Jacobi(maxiter=K)`` (no tol) or
+        Other arguments as ``split_bregman_tvd``; ``solver`` is ``Jacobi(maxiter=K[, tol=...])`` or
         ``CG(maxiter=m, tol=...)``.
     Returns this rank's owned planes of the result (and, with ``return_info``, the relative increments).
     """

@@ -43,7 +43,8 @@ def _worker(rank, world, port, case, outdir):
                     om = coeff_field(case["shape"], 6, 0.5, 2.0).astype(vol.dtype)
                     kw.update(mu=mu[s:e], omega=om[s:e])
                 solver = {"j1": lambda: da.Jacobi(maxiter=1), "j3": lambda: da.Jacobi(maxiter=3),
-                          "cg4": lambda: da.CG(maxiter=4, tol=0.0), "cgtol": lambda: da.CG(maxiter=30, tol=1e-3)}[case["solver"]]()
+                          "cg4": lambda: da.CG(maxiter=4, tol=0.0), "cgtol": lambda: da.CG(maxiter=30, tol=1e-3),
+                          "jtol": lambda: da.Jacobi(maxiter=12, tol=2e-2)}[case["solver"]]()
                 out, hist = da.split_bregman_tvd_slab(np.ascontiguousarray(vol[s:e]), vol.shape, dim=len(case["shape"]),
                                                       max_num_iter=case["nit"], isotropic=case["iso"], solver=solver,
                                                       eps=case.get("eps"), return_info=True, **kw)
@@ -72,6 +73,7 @@ SLAB_CASES = [
     (2, dict(kind="slab", shape=(10, 8, 24), dtype="float32", iso=False, solver="j1", nit=8)),
     (2, dict(kind="slab", shape=(40, 70), dtype="float64", iso=False, solver="j1", nit=6)),
     (2, dict(kind="slab", shape=(11, 9, 20), dtype="float64", iso=False, solver="j1", nit=60, eps=2e-2)),
+    (2, dict(kind="slab", shape=(11, 9, 20), dtype="float64", iso=False, solver="jtol", nit=5)),
     # 5 ranks: CG kernels are launched whole (the boundary-first split is for <= 4 ranks), fused Jacobi-1 split
     (5, dict(kind="slab", shape=(27, 6, 12), dtype="float64", iso=True, solver="cg4", nit=3)),
     (5, dict(kind="slab", shape=(46, 6, 12), dtype="float64", iso=False, solver="j1", nit=4)),
@@ -92,7 +94,8 @@ def test_slab_decomposition_equals_oracle(world, case):
         kw.update(mu=coeff_field(case["shape"], 5, 0.05, 0.1, 0.1).astype(vol.dtype),
                   omega=coeff_field(case["shape"], 6, 0.5, 2.0).astype(vol.dtype))
     solver = {"j1": lambda: oracle.Jacobi(maxiter=1), "j3": lambda: oracle.Jacobi(maxiter=3),
-              "cg4": lambda: oracle.CG(maxiter=4, tol=0.0), "cgtol": lambda: oracle.CG(maxiter=30, tol=1e-3)}[case["solver"]]()
+              "cg4": lambda: oracle.CG(maxiter=4, tol=0.0), "cgtol": lambda: oracle.CG(maxiter=30, tol=1e-3),
+              "jtol": lambda: oracle.Jacobi(maxiter=12, tol=2e-2)}[case["solver"]]()
     hist = []
     ref = oracle.split_bregman_tvd(vol, dim=len(case["shape"]), max_num_iter=case["nit"], isotropic=case["iso"],
                                    solver=solver, eps=case.get("eps"), history=hist, **kw)
