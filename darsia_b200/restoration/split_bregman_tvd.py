@@ -285,6 +285,9 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
                                      wsp, wsn, eng.stream()), "tvdk_energy")
                 en = sums[: 2 * nb].cpu().numpy().reshape(nb, 2)
                 energy = 0.5 * en[:, 0] + en[:, 1]
+                if it == 0:  # split_bregman_tvd.py:103-104 (u = img at this point)
+                    for b in range(nb):
+                        print(f"The energy functional starts at {energy[b]}")
             lib.check(lib.rhs(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(omc), C.byref(elc), f.data_ptr(),
                               t.data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, eng.stream()), "tvdk_rhs")  # :84-89
         x = hier.solve(u, rhs, solver.maxiter, solver.tol)  # :133
