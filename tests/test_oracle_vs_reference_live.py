@@ -43,6 +43,8 @@ while n < 30:
         kw["omega"] = gg.coeff_field(shape, 7, 0.5, 2.0).astype(dt)
         if not iso:
             kw["mu"] = gg.coeff_field(shape, 6, 0.05, 0.1, 0.1).astype(dt)
+            if rng.random() < 0.5:  # per-voxel ell: Jacobi multiplies it after, CG puts it inside the divergence (Q18)
+                kw["ell"] = gg.coeff_field(shape, 5, 0.5, 1.5).astype(dt)
     K = int(rng.integers(1, 9))
     def mk(api):
         return {"j": lambda: api.Jacobi(maxiter=K), "jtol": lambda: api.Jacobi(maxiter=20, tol=1e-2),
