@@ -166,8 +166,18 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------------------------
-# CPU arm: the NumPy oracle (port of the reference's algorithm) on a bounded sample
+# CPU arm: the UNMODIFIED reference (oracle/_ref, staged by __graft_entry__.build()) on the host cores;
+# the NumPy oracle (a port of the same algorithm) only where the reference itself cannot run the workload
 # --------------------------------------------------------------------------------------------
+def config_of(w, wname):
+    """The workload description both arms print (identical dicts => the driver can compare like with like)."""
+    return {"workload": wname, "shape": list(w["shape"]), "channels_per_rank": w["nb"], "isotropic": w["iso"],
+            "solver": list(w["solver"]), "outer_iterations": w["outer"], "hetero": w["hetero"],
+            "l2_policy": "inputs larger than L2 (126 MB)",
+            "sharding": ("slabs along axis 0, halo + partial-sum pushes over peer memory" if w.get("slab")
+                         else "one image per rank, no collective")}
+
+
 def cpu_sample(w, budget_voxels=7_000_000):
     """A crop of one channel of the workload such that ~3 outer iterations take 10-30 s."""
     shape = list(w["shape"])
@@ -177,33 +187,58 @@ def cpu_sample(w, budget_voxels=7_000_000):
     return tuple(shape)
 
 
-_ORACLE_WARM = False
+def reference_can_run(w):
+    """The verbatim reference handles this workload (its isotropic shrinkage is 2-D fp64 with scalar mu)."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        return False
+    if w["iso"] and (len(w["shape"]) != 2 or w["dtype"] != "float64" or w["hetero"]):
+        return False
+    return True
 
 
-def cpu_time_oracle(w, seed, n1=1, n2=3):
-    """Seconds per outer iteration of the oracle on the bounded sample: marginal cost
-    (t(n2) - t(n1)) / (n2 - n1) (falls back to t(n2)/n2 if noise makes it non-positive)."""
-    global _ORACLE_WARM
-    import oracle
+_CPU_API = {}
 
+
+def cpu_api(w):
+    """(module with the reference's names, kind): the verbatim reference where it can run, else the port."""
+    key = reference_can_run(w)
+    if key not in _CPU_API:
+        if key:
+            from oracle import ref_loader
+
+            _CPU_API[key] = (ref_loader.load_reference(), "reference")
+        else:
+            import oracle
+
+            _CPU_API[key] = (oracle, "port")
+    return _CPU_API[key]
+
+
+def cpu_solve(w, img, n_iter, seed):
+    """One call of the reference's entry point on one channel/frame: tvd(img, 'heterogeneous bregman', ...)
+    (restoration/tvd.py:132-163; ell = 1.0 is what that entry point passes)."""
+    api, _ = cpu_api(w)
+    kind, m, tol = w["solver"]
+    solver = api.Jacobi(maxiter=m, tol=tol) if kind == "jacobi" else api.CG(maxiter=m, tol=tol)
+    kw = dict(weight=MU, omega=w.get("omega", OMEGA), dim=len(img.shape), isotropic=w["iso"], max_num_iter=n_iter, eps=None,
+              solver=solver)
+    if w["hetero"]:
+        mu, om = hetero_maps(dict(w, shape=img.shape), seed)
+        kw.update(weight=mu, omega=om)
+    t0 = time.perf_counter()
+    api.tvd(img, method="heterogeneous bregman", **kw)
+    return time.perf_counter() - t0
+
+
+def cpu_time_marginal(w, seed, n1=1, n2=3):
+    """Seconds per outer iteration on the bounded sample: marginal cost (t(n2) - t(n1)) / (n2 - n1) of two calls
+    (absorbs the per-call Numba compile of the reference; falls back to t(n2)/n2 if noise makes it <= 0)."""
     shape = cpu_sample(w)
     img = phantom_np(shape, seed, w["dtype"])
-    kind, m, tol = w["solver"]
-    mk = (lambda: oracle.Jacobi(maxiter=m, tol=tol)) if kind == "jacobi" else (lambda: oracle.CG(maxiter=m, tol=tol))
-    kw = dict(mu=MU, omega=w.get("omega", OMEGA), ell=ELL, dim=len(shape), isotropic=w["iso"])
-    if w["hetero"]:
-        mu, om = hetero_maps(dict(w, shape=shape), seed)
-        kw.update(mu=mu, omega=om)
-    if not _ORACLE_WARM:  # one-time costs (imports, BLAS thread pool) paid on a tiny problem
-        tiny = phantom_np(tuple(16 for _ in shape), 0, w["dtype"])
-        oracle.split_bregman_tvd(tiny, max_num_iter=1, solver=mk(), mu=MU, omega=OMEGA, ell=ELL, dim=len(shape),
-                                 isotropic=w["iso"])
-        _ORACLE_WARM = True
-    ts = []
-    for n in (n1, n2):
-        t0 = time.perf_counter()
-        oracle.split_bregman_tvd(img, max_num_iter=n, solver=mk(), **kw)
-        ts.append(time.perf_counter() - t0)
+    cpu_solve(w, phantom_np(tuple(16 for _ in shape), 0, w["dtype"]), 1, 0)  # imports, BLAS pool
+    ts = [cpu_solve(w, img, n, seed) for n in (n1, n2)]
     per_iter = (ts[1] - ts[0]) / (n2 - n1)
     if per_iter <= 0:
         per_iter = ts[1] / n2
@@ -220,60 +255,67 @@ def blas_threads():
 
 
 def _ref_worker(job):
-    """One channel/frame of the bounded sample through the oracle; returns (voxels*iters, seconds)."""
-    w, seed, n_iter = job
-    import oracle
-
-    shape = cpu_sample(w)
+    """One channel/frame of the sample through the reference; returns (voxels*iters, seconds)."""
+    w, shape, seed, n_iter = job
     img = phantom_np(shape, seed, w["dtype"])
-    kind, m, tol = w["solver"]
-    solver = oracle.Jacobi(maxiter=m, tol=tol) if kind == "jacobi" else oracle.CG(maxiter=m, tol=tol)
-    kw = dict(mu=MU, omega=w.get("omega", OMEGA), ell=ELL, dim=len(shape), isotropic=w["iso"])
-    if w["hetero"]:
-        mu, om = hetero_maps(dict(w, shape=shape), seed)
-        kw.update(mu=mu, omega=om)
-    t0 = time.perf_counter()
-    oracle.split_bregman_tvd(img, max_num_iter=n_iter, solver=solver, **kw)
-    return int(np.prod(shape)) * n_iter, time.perf_counter() - t0
+    dt = cpu_solve(w, img, n_iter, seed)
+    return int(np.prod(shape)) * n_iter, dt
 
 
 def run_reference_arm(args, w, wname):
-    """--impl reference: the reference's CPU algorithm on the host cores.  The Python reference itself
-    cannot travel to the GPU box, so this is the NumPy oracle -- a port of the same
-    algorithm, pinned against the reference's outputs.  The reference is single-threaded per image
-    (element-wise NumPy); to use the host's cores the way a user could, the channels/frames of the
-    workload are solved in parallel processes (one bounded crop each)."""
+    """--impl reference: the reference's own CPU implementation of the path on the host cores -- the UNMODIFIED
+    DarSIA files (oracle/_ref, executed verbatim by oracle/ref_loader.py, Numba shrinkage included) through
+    darsia.tvd(), on the GPU arm's workload: full-size channels, same solver, same config dict.  The reference is
+    single-threaded per image (element-wise NumPy, only np.dot is threaded); to use the host's cores the way a
+    user could, the channels/frames of the workload run in parallel processes.  One step = ONE outer iteration
+    per channel (a bounded sample of the 100 the GPU arm runs; the cost per outer iteration is constant)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     import multiprocessing as mp
 
+    _, kind = cpu_api(w)
     nproc = max(1, min(w["nb"] if not w.get("slab") else 1, (os.cpu_count() or 2) // 2, 8))
-    n_iter = 2
-    shape = cpu_sample(w)
+    n_iter = 1
+    full = tuple(w["shape"])
+    if w.get("slab"):  # a 1024^3 volume does not fit the host with NumPy temporaries: 256^3-class sub-volume
+        full = cpu_sample(w, 20_000_000)
+    budget_s = float(os.environ.get("BENCH_REF_BUDGET_S", "240"))
     ctx = mp.get_context("fork")
     vals, secs = [], []
+    tiny = tuple(max(16, n // 16) for n in full)
     with ctx.Pool(nproc) as pool:
-        pool.map(_ref_worker, [(dict(w, shape=(16,) * len(shape)), 0, 1)] * nproc)  # start-up costs
-        for s in range(args.warmup + args.steps):
+        pool.map(_ref_worker, [(w, tiny, 0, 1)] * nproc)  # start-up costs (imports, Numba/BLAS initialisation)
+        # the first warm-up step runs the FULL sample and sizes the timed steps: if K of them would exceed the budget the
+        # sample becomes a band of full-width rows (cost per voxel is size-independent for this streaming code)
+        shape = full
+        for s_ in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            res = pool.map(_ref_worker, [(w, 2 + 10 * s + c, n_iter) for c in range(nproc)])
+            warm = s_ < args.warmup
+            shp = shape if (not warm or s_ == 0) else tiny
+            res = pool.map(_ref_worker, [(w, shp, 2 + 10 * s_ + c, n_iter) for c in range(nproc)])
             wall = time.perf_counter() - t0
-            if s >= args.warmup:
+            if s_ == 0 and wall * args.steps > budget_s and (warm or args.warmup == 0):
+                rows = max(64, int(full[0] * budget_s / (wall * args.steps)) // 8 * 8)
+                shape = (min(full[0], rows),) + full[1:]
+            if not warm:
                 vals.append(sum(r[0] for r in res) / wall / 1e6)
                 secs.append(wall)
     v = float(np.mean(vals))
-    sample = (f"NumPy oracle (port of the reference algorithm) on {nproc} channel/frame crop(s) of {shape} in {nproc} "
-              f"parallel processes, {n_iter} outer iterations each per step; element-wise NumPy is single-threaded "
-              f"per process, BLAS threads={blas_threads()}, host cpus={os.cpu_count()}")
+    what = ("the UNMODIFIED DarSIA reference (oracle/_ref, verbatim, Numba shrinkage incl. its per-call JIT) through darsia.tvd()"
+            if kind == "reference" else
+            "NumPy oracle (port of the reference algorithm: the reference itself cannot run this workload, SURVEY Q3)")
+    sample = (f"{what}: {nproc} channel(s)/frame(s) of shape {tuple(shape)} (workload shape {tuple(w['shape'])}) in {nproc} parallel "
+              f"processes, {n_iter} outer iteration per channel and step; element-wise NumPy is single-threaded per process, "
+              f"BLAS threads={blas_threads()}, host cpus={os.cpu_count()}")
     line = {
         "impl": "reference", "metric": "tvd_mvoxel_iter_per_s", "value": v, "unit": "Mvoxel*iter/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": 1e3 * float(np.mean(secs)), "higher_is_better": True,
+        "scaling": "strong" if w.get("slab") else "weak", "vs_baseline": None,
         "dtype": "f64" if w["dtype"] == "float64" else "f32", "data": "synthetic",
-        "config": {"workload": wname, "shape": list(w["shape"]), "channels_per_rank": w["nb"], "isotropic": w["iso"],
-                   "solver": list(w["solver"]), "outer_iterations": w["outer"], "hetero": w["hetero"]},
-        "cpu_baseline": {"value": v, "unit": "Mvoxel*iter/s", "cores": nproc, "kind": "port", "sample": sample},
+        "config": config_of(w, wname),
+        "cpu_baseline": {"value": v, "unit": "Mvoxel*iter/s", "cores": nproc, "kind": kind, "sample": sample},
         "e2e": {"value": v, "unit": "Mvoxel*iter/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -378,9 +420,24 @@ def run_ours(args, w, wname):
     ms_per_step = ms_total / args.steps
     value = world * nvox_step * outer / (ms_per_step * 1e-3) / 1e6
 
-    # ---- parity spot-check of what was just timed (cheap, not timed): determinism + finite ----
+    # ---- parity spot-check of what was just timed (cheap, not timed): finite result, the single-pass CG diagnostic,
+    #      and the same solver at the config's iteration counts on a reduced shape against the oracle ----
     res = eng.unpack(u)
     assert bool(torch.isfinite(res).all()), "non-finite result"
+    info_full = eng.solve(f, u.copy_(f), t.zero_(), mu, om, ELL, w["iso"], spec, min(outer, 5), None, sync=True)
+    cg_pred_dev = float(np.max(info_full.cg_pred_dev)) if info_full.cg_pred_dev is not None else None
+    parity = None
+    if rank == 0 and not args.no_cpu and not w["hetero"]:
+        import oracle
+
+        red = tuple(max(24, n // 16) + 1 for n in w["shape"])  # odd extents, several tiles per axis
+        small = phantom_np(red, 77, w["dtype"])
+        mk = (lambda mod: mod.CG(maxiter=m, tol=tol)) if kind == "cg" else (lambda mod: mod.Jacobi(maxiter=m, tol=tol))
+        kws = dict(mu=MU, omega=w.get("omega", OMEGA), ell=ELL, dim=dim, isotropic=w["iso"], max_num_iter=outer)
+        got = da.split_bregman_tvd(small, solver=mk(da), device=dev, **kws)
+        want = oracle.split_bregman_tvd(small, solver=mk(oracle), **kws)
+        parity = {"rel_l2_vs_oracle": float(np.linalg.norm(got - want) / np.linalg.norm(want)), "shape": list(red),
+                  "outer_iterations": outer, "bar": 1e-10 if np_dtype == np.float64 else 1e-5}
 
     # ---- dominant kernel alone: average launch duration with CUDA events ----
     W = np_dtype.itemsize
@@ -484,6 +541,15 @@ def run_ours(args, w, wname):
     e2e_breakdown = {k: round(v, 4) for k, v in _sbt.LAST_TIMINGS.items()}
     e2e_breakdown["each_call_s"] = e2e_each
     e2e_breakdown["input_is_pinned"] = bool(torch.from_numpy(pinned_np).is_pinned())
+    # the same call on a PAGEABLE ndarray (what a drop-in caller of darsia.tvd passes)
+    da.tvd(host_img, **kw)
+    torch.cuda.synchronize(dev)
+    tp0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        outp = da.tvd(host_img, **kw)
+    torch.cuda.synchronize(dev)
+    e2e_pageable_s = (time.perf_counter() - tp0) / e2e_steps
+    del outp
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
@@ -496,14 +562,31 @@ def run_ours(args, w, wname):
     # ---- CPU baseline on rank 0 (N = 1 only) ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        shape_s, per_iter, ts = cpu_time_oracle(w, seed=2)
+        shape_s, per_iter, ts = cpu_time_marginal(w, seed=2)
+        _, cpu_kind = cpu_api(w)
         cpu = {
-            "value": float(np.prod(shape_s)) / per_iter / 1e6, "unit": "Mvoxel*iter/s", "cores": 1, "kind": "port",
-            "sample": (f"NumPy oracle (port of the reference algorithm; the Python reference cannot travel to the GPU "
-                       f"box) on one channel cropped to {tuple(shape_s)}: marginal cost (t(3 its)-t(1 it))/2 = "
+            "value": float(np.prod(shape_s)) / per_iter / 1e6, "unit": "Mvoxel*iter/s", "cores": 1, "kind": cpu_kind,
+            "sample": (("the UNMODIFIED DarSIA reference (oracle/_ref, executed verbatim) through darsia.tvd()" if cpu_kind == "reference"
+                        else "NumPy oracle (port of the reference algorithm)") +
+                       f" on one channel cropped to {tuple(shape_s)}: marginal cost (t(3 its)-t(1 it))/2 = "
                        f"{per_iter:.3f} s per outer iteration; raw {ts[1] / 3:.3f} s/iter; element-wise NumPy is "
                        f"single-threaded, host has {os.cpu_count()} cpus, BLAS threads={blas_threads()}"),
         }
+    # ---- the slab-decomposed configs (one volume over all ranks: halo + partial-sum pushes), strong scaling ----
+    slab = None
+    if wname == DEFAULT_WORKLOAD and not args.no_slab:
+        del f, u, t, res, out, pinned_in, dom  # (dom's closure holds the dominant-kernel buffers)
+        eng = None
+        import gc
+
+        gc.collect()
+        torch.cuda.empty_cache()
+        slab = {}
+        for sname in ("cfg4_3d_slab_cg10", "cfg5_3d_slab_j1_f32"):
+            slab[sname] = slab_measure(WORKLOADS[sname], sname, rank, world, local, dev, steps=2, warmup=1,
+                                       want_e2e=world > 1, barrier=barrier)
+            gc.collect()
+            torch.cuda.empty_cache()
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -513,28 +596,161 @@ def run_ours(args, w, wname):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64" if np_dtype == np.float64 else "f32",
         "data": "synthetic (seeded block phantom + noise; random-free weights: scalar mu/omega/ell)",
-        "config": {"workload": wname, "shape": list(w["shape"]), "channels_per_rank": w["nb"], "isotropic": w["iso"],
-                   "solver": list(w["solver"]), "outer_iterations": outer, "hetero": w["hetero"],
-                   "l2_policy": "inputs larger than L2 (each field is %.0f MB, L2 is 126 MB)" % (eng.batch_elems * W / 1e6),
-                   "sharding": "one image per rank, no collective"},
+        "config": config_of(w, wname),
         "roofline": roofline,
         "cpu_baseline": cpu,
         "e2e": {"value": e2e_val, "unit": "Mvoxel*iter/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "s_per_step": float(te.item()), "matches_device_timed_result": same,
-                "breakdown_s": e2e_breakdown},
+                "breakdown_s": e2e_breakdown,
+                "pageable_input": {"value": world * nvox_step * outer / e2e_pageable_s / 1e6, "s_per_step": e2e_pageable_s}},
+        "parity": parity, "cg_pred_dev": cg_pred_dev,
         "gpu_launches": launches,
         "clocks": clocks,
     }
+    if slab is not None:
+        line["slab"] = slab
     print(json.dumps(line))
+
+
+def phantom_torch(shape, seed, tdtype, dev):
+    """Device-side synthetic volume of the same kind as phantom_np (blocks + noise, clipped): used where a host
+    array of the whole volume would take minutes to generate (1024^3 on one GPU)."""
+    import torch
+
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    cells = [max(2, n // 8) for n in shape]
+    checker = None
+    for a, n in enumerate(shape):
+        ix = (torch.arange(n, device=dev) // cells[a]).reshape([-1 if i == a else 1 for i in range(len(shape))])
+        checker = ix if checker is None else checker + ix
+    base = torch.tensor([0.2, 0.5, 0.8], device=dev, dtype=torch.float32)[checker % 3]
+    base += 0.1 * torch.randn(shape, generator=g, device=dev, dtype=torch.float32)
+    return base.clamp_(0.0, 1.0).to(tdtype)
+
+
+def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, barrier, transport="p2p"):
+    """One volume cut into slabs over the ranks (BASELINE configs 4/5), through tvdk_solve_slab: device-resident
+    loop timed with CUDA events (max over ranks), the same slab solved WITHOUT neighbours (what the kernels alone
+    cost), a parity check of the decomposition against one GPU on a reduced volume, optionally e2e with host buffers."""
+    import torch
+    import torch.distributed as dist
+
+    import darsia_b200 as da
+    from darsia_b200.slab_p2p import SlabGroup
+
+    shape = tuple(w["shape"])
+    dim = len(shape)
+    kind, m, tol = w["solver"]
+    np_dtype = np.dtype(w["dtype"])
+    tdtype = torch.float64 if np_dtype == np.float64 else torch.float32
+    mk = lambda: (da.CG(maxiter=m, tol=tol) if kind == "cg" else da.Jacobi(maxiter=m, tol=tol))  # noqa: E731
+    s, e = da.slab_range(shape[0], rank, world)
+    outer = w["outer"]
+    nvox = int(np.prod(shape))
+    W = np_dtype.itemsize
+
+    def reduce_max(x):
+        tx = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        return float(tx.item())
+
+    def timed(grp, n):
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        for _ in range(n):
+            grp.reset()
+            grp.solve(outer)
+        ev1.record()
+        barrier()
+        return reduce_max(ev0.elapsed_time(ev1)) / n
+
+    grp = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
+    owned_dev = phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev)
+    grp.setup([owned_dev])
+    del owned_dev
+    for _ in range(warmup):
+        grp.reset()
+        grp.solve(outer)
+    grp.lib.launch_count(1)
+    ms_per_step = timed(grp, steps)
+    launches = int(grp.lib.launch_count(1)) // steps
+    grp.check()
+    value = nvox * outer / (ms_per_step * 1e-3) / 1e6
+    fin = bool(torch.isfinite(grp.ranks[0].field("u")).all())
+    words = algo_words_per_voxel_iter(dim, w["solver"], 0, single_pass=False)  # 3-D / slabs: two-kernel CG iterations
+    peak, peak_src = measured_peak()
+    gbs = words * W * nvox * outer / (ms_per_step * 1e-3) / 1e9
+    rec = {"value": value, "unit": "Mvoxel*iter/s", "ms_per_step": ms_per_step, "n_gpus": world, "scaling": "strong",
+           "config": config_of(w, wname), "finite": fin, "steps": steps, "warmup": warmup,
+           "roofline_per_gpu": {"achieved": gbs / world, "peak": peak, "unit": "GB/s", "frac": gbs / world / peak,
+                                "algo_words_per_voxel_iter": words, "peak_source": peak_src},
+           "gpu_launches_per_step": launches,
+           "transport": "peer-memory pushes + flags (tvdk_solve_slab); no NCCL call inside the timed region"}
+    # comm steps per solve: 2 (handshake, ||f||) + per outer iteration 1 (fused J1) / 2m + 2 (CG) / K + 1 (Jacobi K)
+    per_it = 1 if (kind == "jacobi" and m == 1) else (2 * m + 2 if kind == "cg" else m + 1)
+    rec["comm_steps_per_solve"] = 2 + per_it * outer
+    if world > 1:
+        # the same slab without neighbours (kernels + the same tiny launches, no peer traffic, no waiting on anybody)
+        del grp
+        torch.cuda.empty_cache()
+        alone = SlabGroup.local((e - s,) + shape[1:], dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), world=1, devices=[dev])
+        alone.setup([phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev)])
+        alone.reset()
+        alone.solve(outer)
+        ms_alone = timed(alone, steps)
+        del alone
+        torch.cuda.empty_cache()
+        rec["breakdown_ms"] = {"total": ms_per_step, "own_slab_without_neighbours": ms_alone,
+                               "halo_pushes_and_flag_waits": ms_per_step - ms_alone,
+                               "per_comm_step_us": 1e3 * (ms_per_step - ms_alone) / rec["comm_steps_per_solve"]}
+        # decomposition == one GPU on a reduced volume (same per-voxel arithmetic; only the order of the partial sums differs)
+        red = (max(4 * world, 64),) + tuple(max(48, n // 8) for n in shape[1:])
+        small = phantom_np(red, 11, w["dtype"])
+        rs, re_ = da.slab_range(red[0], rank, world)
+        g2 = SlabGroup.distributed(red, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
+        g2.setup([np.ascontiguousarray(small[rs:re_])])
+        g2.solve(outer)
+        mine = torch.from_numpy(g2.results()[0]).to(dev)
+        g2.check()
+        parts = [torch.empty((da.slab_range(red[0], r, world)[1] - da.slab_range(red[0], r, world)[0],) + red[1:], dtype=mine.dtype,
+                             device=dev) for r in range(world)]
+        dist.all_gather(parts, mine)
+        if rank == 0:
+            whole = torch.cat(parts, dim=0).cpu().numpy()
+            single = da.split_bregman_tvd(small, mu=MU, omega=OMEGA, ell=ELL, dim=dim, max_num_iter=outer, isotropic=w["iso"],
+                                          solver=mk(), device=dev)
+            rec["parity_vs_one_gpu"] = {"rel_l2": float(np.linalg.norm(whole - single) / np.linalg.norm(single)),
+                                        "shape": list(red), "outer_iterations": outer}
+        del g2, parts, mine
+        torch.cuda.empty_cache()
+        if want_e2e:
+            owned = phantom_np((e - s,) + shape[1:], 4 + rank, w["dtype"])
+            g3 = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
+            g3.setup([owned])
+            g3.solve(outer)
+            g3.results()  # warm-up of the allocators / pinned staging
+            barrier()
+            t0 = time.perf_counter()
+            g3.setup([owned])
+            g3.solve(outer)
+            out = g3.results(w["dtype"])[0]
+            torch.cuda.synchronize(dev)
+            te = reduce_max(time.perf_counter() - t0)
+            rec["e2e"] = {"value": nvox * outer / te / 1e6, "unit": "Mvoxel*iter/s", "s_per_step": te,
+                          "h2d_bytes_per_step": int(owned.nbytes), "d2h_bytes_per_step": int(out.nbytes),
+                          "input": "pageable ndarray of the owned planes"}
+            del g3, owned, out
+            torch.cuda.empty_cache()
+    return rec
 
 
 def run_slab(args, w, wname):
     """One volume, slab-decomposed over the ranks (BASELINE configs 4/5): strong scaling."""
     import torch
     import torch.distributed as dist
-
-    import darsia_b200 as da
-    from darsia_b200.slab import SlabSolver
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -550,6 +766,39 @@ def run_slab(args, w, wname):
             dist.barrier(device_ids=[local])
         torch.cuda.synchronize(dev)
 
+    if args.transport == "nccl":
+        return run_slab_nccl(args, w, wname, rank, world, local, dev, barrier)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    rec = slab_measure(w, wname, rank, world, local, dev, args.steps, args.warmup, want_e2e=world > 1, barrier=barrier)
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    e2e = rec.pop("e2e", None)
+    rl = rec.pop("roofline_per_gpu")
+    line = {
+        "metric": "tvd_mvoxel_iter_per_s", "value": rec.pop("value"), "unit": "Mvoxel*iter/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": rec.pop("ms_per_step"), "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if w["dtype"] == "float64" else "f32", "data": "synthetic",
+        "config": rec.pop("config"),
+        "roofline": dict(rl, bound="hbm", kernel="whole step (all kernels + halo pushes + flag waits)", traffic=None, per_gpu=True),
+        "cpu_baseline": None, "e2e": e2e, "gpu_launches": rec.pop("gpu_launches_per_step") * args.steps, "clocks": clocks,
+        "slab": rec,
+    }
+    print(json.dumps(line))
+
+
+def run_slab_nccl(args, w, wname, rank, world, local, dev, barrier):
+    """The round-1 slab driver (Python loop, NCCL isend/irecv + all_reduce), kept for A/B runs: --transport nccl."""
+    import torch
+    import torch.distributed as dist
+
+    import darsia_b200 as da
+    from darsia_b200.slab import SlabSolver
+
     shape = tuple(w["shape"])
     dim = len(shape)
     kind, m, tol = w["solver"]
@@ -563,11 +812,6 @@ def run_slab(args, w, wname):
     for _ in range(args.warmup):
         sol.reset()
         sol.iterate(outer)
-    barrier()
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-    sol.eng.lib.launch_count(1)
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
@@ -576,46 +820,21 @@ def run_slab(args, w, wname):
         sol.iterate(outer)
     ev1.record()
     barrier()
-    launches = int(sol.eng.lib.launch_count(1))
-    clocks = sampler.stop() if rank == 0 else None
     tm = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-    ms_per_step = float(tm.item()) / args.steps
-    value = nvox * outer / (ms_per_step * 1e-3) / 1e6
-    res = sol.result()
-    assert np.isfinite(res).all()
-    W = np.dtype(w["dtype"]).itemsize
-    words = algo_words_per_voxel_iter(dim, w["solver"], 0, single_pass=False)  # slabs: two-kernel CG iterations
-    peak, peak_src = measured_peak()
-    gbs = words * W * nvox * outer / (ms_per_step * 1e-3) / 1e9
-    # e2e: host planes in, host planes out
-    t0 = time.perf_counter()
-    out = da.split_bregman_tvd_slab(owned, shape, mu=MU, omega=OMEGA, ell=ELL, dim=dim, max_num_iter=outer,
-                                    isotropic=w["iso"], solver=solver, device=dev)
-    torch.cuda.synchronize(dev)
-    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
         dist.destroy_process_group()
+    ms_per_step = float(tm.item()) / args.steps
     if rank != 0:
         return
-    line = {
-        "metric": "tvd_mvoxel_iter_per_s", "value": value, "unit": "Mvoxel*iter/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
-        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if W == 8 else "f32", "data": "synthetic",
-        "config": {"workload": wname, "shape": list(shape), "isotropic": w["iso"], "solver": list(w["solver"]),
-                   "outer_iterations": outer, "sharding": "slabs along axis 0, halo exchange + all-reduce (NCCL)",
-                   "l2_policy": "inputs larger than L2"},
-        "roofline": {"bound": "hbm", "kernel": "whole step (all kernels + halo exchange)", "achieved": gbs / world,
-                     "peak": peak, "unit": "GB/s", "frac": gbs / world / peak, "traffic": None,
-                     "peak_source": peak_src, "algo_words_per_voxel_iter": words, "per_gpu": True},
-        "cpu_baseline": None,
-        "e2e": {"value": nvox * outer / float(te.item()) / 1e6, "unit": "Mvoxel*iter/s",
-                "h2d_bytes_per_step": int(owned.nbytes), "d2h_bytes_per_step": int(out.nbytes)},
-        "gpu_launches": launches, "clocks": clocks,
-    }
-    print(json.dumps(line))
+    W = np.dtype(w["dtype"]).itemsize
+    words = algo_words_per_voxel_iter(dim, w["solver"], 0, single_pass=False)
+    peak, peak_src = measured_peak()
+    gbs = words * W * nvox * outer / (ms_per_step * 1e-3) / 1e9
+    print(json.dumps({"metric": "tvd_mvoxel_iter_per_s", "value": nvox * outer / (ms_per_step * 1e-3) / 1e6,
+                      "unit": "Mvoxel*iter/s", "n_gpus": world, "ms_per_step": ms_per_step, "scaling": "strong",
+                      "config": config_of(w, wname), "transport": "nccl (round-1 Python driver)",
+                      "roofline": {"frac": gbs / world / peak, "peak": peak, "per_gpu": True}}))
 
 
 def main():
@@ -626,6 +845,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed sub-record of the default workload")
+    ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="slab workloads: tvdk_solve_slab or the NCCL driver")
     ap.add_argument("--shape", type=int, nargs="+", default=None, help="override the workload's spatial shape")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]

@@ -138,6 +138,23 @@ class Chambolle(C.Structure):
     ]
 
 
+TVDK_MAX_SLABS, TVDK_SLAB_GL, TVDK_SLAB_GH = 16, 1, 2
+
+
+class SlabComm(C.Structure):
+    """``tvdk_slab_comm_t``."""
+
+    _fields_ = [
+        ("world", C.c_int32),
+        ("rank", C.c_int32),
+        ("nown", C.c_int32 * TVDK_MAX_SLABS),
+        ("arena", C.c_void_p * TVDK_MAX_SLABS),
+        ("arena_bytes", C.c_size_t),
+        ("seq", C.POINTER(C.c_uint64)),
+        ("timeout_ms", C.c_int32),
+    ]
+
+
 _PG = C.POINTER(Geom)
 _PC = C.POINTER(Coef)
 _VP = C.c_void_p
@@ -179,6 +196,16 @@ SIGNATURES = {
     "tvdk_mg_prolong_add": (C.c_int, [_PG, _PG, _VP, _VP, _VP]),
     "tvdk_cg_first": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_fused": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _SZ, _VP]),
+    "tvdk_slab_header_bytes": (_SZ, []),
+    "tvdk_slab_workspace_bytes": (_SZ, [C.POINTER(Problem)]),
+    "tvdk_solve_slab": (C.c_int, [_I, C.POINTER(C.POINTER(Problem)), C.POINTER(C.POINTER(SlabComm)), C.POINTER(_VP),
+                                  C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "tvdk_slab_error": (C.c_int, [_VP, _VP, C.POINTER(_I64)]),
+    "tvdk_slab_exchange": (C.c_int, [_I, C.POINTER(_PG), C.POINTER(C.POINTER(SlabComm)), _I, C.POINTER(C.POINTER(_VP)),
+                                     _I, _I, C.POINTER(_VP), C.POINTER(C.c_int)]),
+    "tvdk_ipc_export": (C.c_int, [_VP, C.POINTER(C.c_ubyte * 64), C.POINTER(_I64)]),
+    "tvdk_ipc_open": (C.c_int, [C.POINTER(C.c_ubyte * 64), _I64, C.POINTER(_VP)]),
+    "tvdk_enable_peer": (C.c_int, [_I]),
 }
 
 

@@ -138,14 +138,24 @@ namespace backend {
 
 static int cuda_fail(cudaError_t e, const char* what);
 
+constexpr int kMaxDevices = 64;
+static int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 template <class K>
 int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem, void* stream,
            double* partials, unsigned* counters) {
-  static thread_local size_t smem_set = 48 * 1024;
-  if (smem > smem_set) {
-    cudaError_t e = cudaFuncSetAttribute(tvdk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
-    smem_set = smem;
+  // the opt-in above 48 KB is a per-DEVICE function attribute: cache it per (thread, kernel, device)
+  static thread_local size_t smem_set[kMaxDevices] = {};
+  if (smem > 48 * 1024) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices || smem > smem_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(tvdk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+      if (dev >= 0 && dev < kMaxDevices) smem_set[dev] = smem;
+    }
   }
   dim3 grid(gx, gy, gz), block(ntx, nty, 1);
   tvdk_kernel<K><<<grid, block, smem, (cudaStream_t)stream>>>(a, partials, counters);
@@ -159,40 +169,195 @@ static int memset_async(void* p, int value, size_t bytes, void* stream) {
   return e == cudaSuccess ? 0 : cuda_fail(e, "cudaMemsetAsync");
 }
 
-// two pinned ints + events per host thread for the convergence polling
+// two pinned ints + events per (host thread, device) for the convergence polling: events belong to the
+// device that was current when they were created
 struct PollState {
   int* host = nullptr;
   cudaEvent_t ev[2];
   bool ready = false;
 };
-static thread_local PollState g_poll;
+static thread_local PollState g_poll[kMaxDevices];
 
-static int poll_init() {
-  if (g_poll.ready) return 0;
-  cudaError_t e = cudaHostAlloc((void**)&g_poll.host, 2 * sizeof(int), cudaHostAllocDefault);
-  if (e != cudaSuccess) return cuda_fail(e, "cudaHostAlloc");
-  for (int i = 0; i < 2; ++i) {
-    e = cudaEventCreateWithFlags(&g_poll.ev[i], cudaEventDisableTiming);
-    if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+static PollState* poll_state() {
+  const int dev = current_device();
+  if (dev < 0 || dev >= kMaxDevices) {
+    cuda_fail(cudaErrorInvalidDevice, "convergence polling: no current device");
+    return nullptr;
   }
-  g_poll.ready = true;
-  return 0;
+  PollState& ps = g_poll[dev];
+  if (ps.ready) return &ps;
+  cudaError_t e = cudaHostAlloc((void**)&ps.host, 2 * sizeof(int), cudaHostAllocDefault);
+  if (e != cudaSuccess) {
+    cuda_fail(e, "cudaHostAlloc");
+    return nullptr;
+  }
+  for (int i = 0; i < 2; ++i) {
+    e = cudaEventCreateWithFlags(&ps.ev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      cuda_fail(e, "cudaEventCreate");
+      return nullptr;
+    }
+  }
+  ps.ready = true;
+  return &ps;
 }
 
 static int poll_begin(int slot, const int* dev_flag, void* stream) {
-  int rc = poll_init();
-  if (rc) return rc;
-  cudaError_t e = cudaMemcpyAsync(&g_poll.host[slot], dev_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  PollState* ps = poll_state();
+  if (!ps) return TVDK_ERR_INVALID;
+  cudaError_t e = cudaMemcpyAsync(&ps->host[slot], dev_flag, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
   if (e != cudaSuccess) return cuda_fail(e, "cudaMemcpyAsync");
-  e = cudaEventRecord(g_poll.ev[slot], (cudaStream_t)stream);
+  e = cudaEventRecord(ps->ev[slot], (cudaStream_t)stream);
   return e == cudaSuccess ? 0 : cuda_fail(e, "cudaEventRecord");
 }
 
 static int poll_end(int slot, int* value) {
-  cudaError_t e = cudaEventSynchronize(g_poll.ev[slot]);
+  PollState* ps = poll_state();
+  if (!ps) return TVDK_ERR_INVALID;
+  cudaError_t e = cudaEventSynchronize(ps->ev[slot]);
   if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
-  *value = g_poll.host[slot];
+  *value = ps->host[slot];
   return 0;
+}
+
+// ---- slab decomposition: halo + partial-sum push over peer memory, flag wait + ordered sum --------------
+// Push: grid-stride 128-bit copy of the boundary planes into the neighbours' ghost planes (peer stores over
+// NVLink; plain stores when the neighbour lives on the same device), then the last block publishes the partial
+// sums and raises this rank's flag in every rank's mailbox.
+__global__ void __launch_bounds__(256) comm_push_kernel(const CommPush a) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const long long nth = (long long)gridDim.x * blockDim.x;
+  for (int k = 0; k < a.nseg; ++k) {
+    const uint4* src = reinterpret_cast<const uint4*>(a.seg[k].src);
+    uint4* dst = reinterpret_cast<uint4*>(a.seg[k].dst);
+    const long long n = a.seg[k].bytes >> 4;
+    long long i = tid;
+    for (; i + 3 * nth < n; i += 4 * nth) {  // four independent 128-bit loads in flight per thread
+      const uint4 v0 = src[i], v1 = src[i + nth], v2 = src[i + 2 * nth], v3 = src[i + 3 * nth];
+      dst[i] = v0;
+      dst[i + nth] = v1;
+      dst[i + 2 * nth] = v2;
+      dst[i + 3 * nth] = v3;
+    }
+    for (; i < n; i += nth) dst[i] = src[i];
+  }
+  __threadfence_system();  // this thread's peer stores are visible system-wide before the block is counted
+  __syncthreads();
+  __shared__ bool last;
+  if (threadIdx.x == 0) last = atomicAdd(a.counter, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (!last) return;
+  __threadfence_system();
+  if ((int)threadIdx.x < a.world) {
+    MailSlot* m = a.mail[threadIdx.x];
+    for (int r = 0; r < a.nred; ++r) m->v[r] = __ldcg(a.sums + r);
+    __threadfence_system();
+    *reinterpret_cast<volatile unsigned long long*>(&m->flag) = a.flag;
+  }
+  if (threadIdx.x == 0) *a.counter = 0;
+}
+
+// Finalize: lane s waits for rank s's flag (bounded), then one thread adds the partial sums in rank order
+// and applies the scalar update (finalize_fin) -- identical bits on every rank.
+__global__ void __launch_bounds__(32) comm_finalize_kernel(const CommFin a) {
+  const int lane = threadIdx.x;
+  bool ok = true;
+  if (lane < a.world) {
+    const volatile unsigned long long* fl = &a.mail[lane].flag;
+    if (*fl != a.flag) {
+      unsigned long long t0;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+      unsigned ns = 32;
+      while (*fl != a.flag) {
+        __nanosleep(ns);
+        if (ns < 1024) ns <<= 1;
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if ((long long)(t1 - t0) > a.timeout_ns) {
+          ok = false;
+          break;
+        }
+      }
+    }
+  }
+  const bool all_ok = __all_sync(0xffffffffu, ok);
+  __threadfence_system();  // order the reads of planes / sums after the flag reads
+  if (lane == 0) {
+    if (!all_ok) {
+      if (*a.error == 0) *a.error = (long long)a.flag;
+      return;
+    }
+    comm_finalize_body(a);
+  }
+}
+
+static int comm_push(const CommPush& a, void* stream) {
+  long long bytes = 0;
+  for (int k = 0; k < a.nseg; ++k) bytes += a.seg[k].bytes;
+  // enough CTAs to drive one NVLink direction (a few MB per step), few enough to leave the SMs to compute
+  int grid = (int)((bytes / 16 + 256 * 8 - 1) / (256 * 8));
+  grid = grid < 1 ? 1 : (grid > 64 ? 64 : grid);
+  comm_push_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "comm_push launch");
+}
+
+static int comm_finalize(const CommFin& a, void* stream) {
+  comm_finalize_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  return e == cudaSuccess ? 0 : cuda_fail(e, "comm_finalize launch");
+}
+
+static int set_device(int dev) {
+  if (dev < 0) return 0;
+  cudaError_t e = cudaSetDevice(dev);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "cudaSetDevice");
+}
+
+// event edges between the streams of the ranks one host thread drives: after this call, work enqueued on any
+// of the streams runs after everything enqueued so far on all of them
+static int comm_sync_local(int n, void* const* streams, const int* devices) {
+  static thread_local cudaEvent_t ev[TVDK_MAX_SLABS];
+  static thread_local int ev_dev[TVDK_MAX_SLABS];
+  static thread_local bool ev_ok[TVDK_MAX_SLABS] = {};
+  bool same = true;
+  for (int i = 1; i < n; ++i) same = same && streams[i] == streams[0] && devices[i] == devices[0];
+  if (same) return 0;  // one stream: already ordered
+  for (int i = 0; i < n; ++i) {
+    int rc = set_device(devices[i]);
+    if (rc) return rc;
+    const int dev = current_device();
+    if (!ev_ok[i] || ev_dev[i] != dev) {
+      if (ev_ok[i]) cudaEventDestroy(ev[i]);
+      cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+      ev_ok[i] = true;
+      ev_dev[i] = dev;
+    }
+    cudaError_t e = cudaEventRecord(ev[i], (cudaStream_t)streams[i]);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaEventRecord");
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc = set_device(devices[i]);
+    if (rc) return rc;
+    for (int j = 0; j < n; ++j) {
+      if (j == i) continue;
+      cudaError_t e = cudaStreamWaitEvent((cudaStream_t)streams[i], ev[j], 0);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamWaitEvent");
+    }
+  }
+  return 0;
+}
+
+static int read_int(const int* dev_ptr, void* stream, int* value) {
+  cudaError_t e = cudaMemcpyAsync(value, dev_ptr, sizeof(int), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "read_int");
+}
+static int read_i64(const long long* dev_ptr, void* stream, long long* value) {
+  cudaError_t e = cudaMemcpyAsync(value, dev_ptr, sizeof(long long), cudaMemcpyDeviceToHost, (cudaStream_t)stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize((cudaStream_t)stream);
+  return e == cudaSuccess ? 0 : cuda_fail(e, "read_i64");
 }
 
 static int device_ok(char* msg, size_t n) {
@@ -221,6 +386,7 @@ static int device_ok(char* msg, size_t n) {
 }  // namespace tvdk
 
 #include "tvdk_host.inl"
+#include "tvdk_slab.inl"
 
 namespace tvdk {
 namespace backend {
@@ -229,3 +395,62 @@ static int cuda_fail(cudaError_t e, const char* what) {
 }
 }  // namespace backend
 }  // namespace tvdk
+
+// ---- peer mapping helpers (include/tvdk.h) ---------------------------------------------------------------
+#include <cuda.h>
+
+int tvdk_ipc_export(const void* device_ptr, unsigned char handle_out[64], int64_t* offset_out) {
+  using namespace tvdk;
+  if (!device_ptr || !handle_out || !offset_out) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  // the IPC handle names the whole cudaMalloc allocation: find its base (driver entry point, no -lcuda needed)
+  typedef CUresult (*range_fn)(CUdeviceptr*, size_t*, CUdeviceptr);
+  static range_fn get_range = nullptr;
+  if (!get_range) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn) return backend::cuda_fail(e, "cudaGetDriverEntryPoint(cuMemGetAddressRange)");
+    get_range = (range_fn)fn;
+  }
+  CUdeviceptr base = 0;
+  size_t size = 0;
+  if (get_range(&base, &size, (CUdeviceptr)device_ptr) != CUDA_SUCCESS)
+    return fail(TVDK_ERR_INVALID, "cuMemGetAddressRange failed: not a device allocation");
+  cudaIpcMemHandle_t h;
+  cudaError_t e = cudaIpcGetMemHandle(&h, (void*)base);
+  if (e != cudaSuccess) return backend::cuda_fail(e, "cudaIpcGetMemHandle");
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle_out, &h, 64);
+  *offset_out = (int64_t)((CUdeviceptr)device_ptr - base);
+  return 0;
+}
+
+int tvdk_ipc_open(const unsigned char handle[64], int64_t offset, void** ptr_out) {
+  using namespace tvdk;
+  if (!handle || !ptr_out) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  cudaIpcMemHandle_t h;
+  memcpy(&h, handle, 64);
+  void* base = nullptr;
+  cudaError_t e = cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess);
+  if (e != cudaSuccess) return backend::cuda_fail(e, "cudaIpcOpenMemHandle");
+  *ptr_out = reinterpret_cast<unsigned char*>(base) + offset;
+  return 0;
+}
+
+int tvdk_enable_peer(int peer_device) {
+  using namespace tvdk;
+  int dev = -1;
+  cudaError_t e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return backend::cuda_fail(e, "cudaGetDevice");
+  if (dev == peer_device) return 0;
+  int can = 0;
+  e = cudaDeviceCanAccessPeer(&can, dev, peer_device);
+  if (e != cudaSuccess) return backend::cuda_fail(e, "cudaDeviceCanAccessPeer");
+  if (!can) return fail(TVDK_ERR_UNSUPPORTED, "device %d cannot access device %d", dev, peer_device);
+  e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    cudaGetLastError();
+    return 0;
+  }
+  return e == cudaSuccess ? 0 : backend::cuda_fail(e, "cudaDeviceEnablePeerAccess");
+}

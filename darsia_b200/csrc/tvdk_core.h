@@ -2582,4 +2582,70 @@ struct KPack {
   static TVDK_DEV void finalize(const Args&, int, const double*) {}
 };
 
+// ==========================================================================================
+// Slab decomposition: halo exchange + all-reduce over peer memory (tvdk_slab.inl; include/tvdk.h)
+//   Every rank's arena starts with a SlabHeader.  slot[parity][s] is the mailbox rank s writes into
+//   (on EVERY rank, its own included): up to 8 partial sums, then -- after a system-wide fence --
+//   the sequence number of the step.  The halo planes a rank pushes into its neighbours' ghost planes
+//   are fenced the same way, so "flag of rank s seen" implies "planes and sums of rank s landed".
+// ==========================================================================================
+struct alignas(128) MailSlot {
+  double v[8];
+  unsigned long long flag;
+  unsigned long long pad[7];
+};
+struct SlabHeader {
+  MailSlot slot[2][TVDK_MAX_SLABS];
+  double local_sums[8];   // this rank's partial sums of the current step (written by the compute kernel)
+  long long error_seq;    // first step whose flag wait timed out (0 = none)
+  unsigned counter;       // last-block detection of the push kernel
+  unsigned pad_[27];
+};
+
+struct CommPush {
+  static constexpr int kMaxSeg = 16;
+  struct Seg {
+    const unsigned char* src;
+    unsigned char* dst;
+    long long bytes;  // multiple of 16
+  } seg[kMaxSeg];
+  int nseg;
+  const double* sums;
+  int nred;
+  MailSlot* mail[TVDK_MAX_SLABS];  // mail[s]: this rank's slot in rank s's header
+  int world;
+  unsigned long long flag;
+  unsigned* counter;
+};
+
+struct CommFin {
+  const MailSlot* mail;  // this rank's header: slot[parity][0 .. world)
+  int world, nred;
+  unsigned long long flag;
+  long long timeout_ns;
+  long long* error;
+  Fin fin;
+  int skip_mask;  // 1: stats.done, 2: stats.cg_stop, 4: stats.jac_stop -- the compute kernel skipped, keep the scalars
+  const tvdk_stat_t* stats;
+};
+
+// (mailbox lines are written by peers while this kernel polls them: read them past L1)
+TVDK_DEV double ld_mail(const double* p) { return *reinterpret_cast<const volatile double*>(p); }
+
+// ordered sum over the ranks + scalar update; runs in ONE thread once every flag has been seen
+TVDK_DEV void comm_finalize_body(const CommFin& a) {
+  if (a.stats) {
+    const tvdk_stat_t& s = a.stats[0];
+    if (((a.skip_mask & 1) && s.done) || ((a.skip_mask & 2) && s.cg_stop) || ((a.skip_mask & 4) && s.jac_stop)) return;
+  }
+  if (a.nred <= 0) return;
+  double tot[8];
+  for (int r = 0; r < a.nred; ++r) {
+    double t = 0.0;
+    for (int s = 0; s < a.world; ++s) t += ld_mail(&a.mail[s].v[r]);  // rank order: bitwise identical on every rank
+    tot[r] = t;
+  }
+  finalize_fin(a.fin, a.nred, 0, tot);
+}
+
 }  // namespace tvdk

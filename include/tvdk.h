@@ -297,6 +297,73 @@ int tvdk_mg_restrict(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, const v
 int tvdk_mg_prolong_add(const tvdk_geom_t* fine, const tvdk_geom_t* coarse, const void* e_coarse, void* x_fine,
                         void* stream);
 
+/* ---- slab-decomposed solve: ONE volume cut along axis 0 over several GPUs -----------------------
+ *
+ * The reference has no distributed code; this is split_bregman_tvd.py:14-177 (same arithmetic per voxel
+ * as tvdk_solve) for a volume whose planes of axis 0 are distributed over `world` ranks, SURVEY.md 8(e).
+ * No NCCL on the data path: every rank owns an ARENA (one device allocation holding a small header, the
+ * fields f, u, t and the workspace) that all other ranks have mapped (CUDA peer access inside one process,
+ * CUDA IPC between processes).  After each kernel a rank PUSHES the boundary planes its neighbours need
+ * straight into their ghost planes and its partial sums into every rank's mailbox (peer stores over
+ * NVLink), then raises a flag; a one-warp kernel waits for the flags of all ranks, adds the partial sums
+ * in rank order (bitwise identical on every rank) and applies the scalar update (alpha, beta, increment,
+ * stopping flags) on the device -- halo exchange + all-reduce in two tiny launches, no host round trip.
+ *
+ * Layout rules shared by all ranks (so that a field has the same arena offset everywhere):
+ *   - local arrays hold  TVDK_SLAB_GL ghost planes | owned planes | TVDK_SLAB_GH ghost planes (+ unused
+ *     planes up to the common capacity): geom.n[0] = GL + max_r nown[r] + GH on every rank,
+ *     geom.z_begin = GL, geom.z_end = GL + nown[rank], geom.g0_off = first owned global plane - GL;
+ *   - problem.f / u / t / workspace / per-voxel coefficient maps all point into the rank's arena, at the
+ *     same offsets on every rank; the first tvdk_slab_header_bytes() bytes of the arena belong to the
+ *     library and must be zero before the first solve.
+ * Unsupported here (TVDK_ERR_UNSUPPORTED): warm starts (x0_d / x0_b), the adaptive schedule, verbose energy.
+ */
+#define TVDK_MAX_SLABS 16
+#define TVDK_SLAB_GL 1
+#define TVDK_SLAB_GH 2
+
+typedef struct tvdk_slab_comm {
+  int32_t world;                 /* number of slabs (ranks) */
+  int32_t rank;                  /* this slab */
+  int32_t nown[TVDK_MAX_SLABS];  /* owned planes of every rank */
+  void* arena[TVDK_MAX_SLABS];   /* base of every rank's arena as mapped for THIS rank's device (own included) */
+  size_t arena_bytes;
+  uint64_t* seq;                 /* host counter, advanced by the library; identical on all ranks (start at 0) */
+  int32_t timeout_ms;            /* flag wait limit inside the kernels (0: 20000); on expiry the header records it */
+} tvdk_slab_comm_t;
+
+size_t tvdk_slab_header_bytes(void);
+/* Workspace needed by tvdk_solve_slab for this problem (scratch + the solver's extra fields). */
+size_t tvdk_slab_workspace_bytes(const tvdk_problem_t* p);
+
+/* Drive `nlocal` ranks of one decomposition from this host thread in lock step (nlocal = 1 with one process
+ * per GPU; nlocal = world with every slab in one process: tests, or one process driving all GPUs).  Local
+ * ranks are ordered by event dependencies between their streams, remote ranks by the flags.  problems[i],
+ * comms[i], streams[i], devices[i] (CUDA device ordinal made current for rank i's launches; -1: leave the
+ * current device) describe local rank i.  All ranks must pass the same solver parameters.
+ * With eps >= 0 the stop test is read back (blocking) every check_every outer iterations so that all ranks
+ * take the same decision.  Returns after enqueueing. */
+int tvdk_solve_slab(int nlocal, const tvdk_problem_t* const* problems, const tvdk_slab_comm_t* const* comms,
+                    void* const* streams, const int* devices, int* iters_launched);
+
+/* First sequence number whose flag wait timed out on this rank (0 = none); reads the arena header
+ * (synchronises the stream). */
+int tvdk_slab_error(const void* arena, void* stream, int64_t* seq_out);
+
+/* One halo exchange of whole planes without a solve (static fields: the image, coefficient maps):
+ * `fields[k]` (arena pointers) each send n_up last owned planes up and n_down first owned planes down. */
+int tvdk_slab_exchange(int nlocal, const tvdk_geom_t* const* geoms, const tvdk_slab_comm_t* const* comms,
+                       int nfields, const void* const* const* fields, int n_up, int n_down,
+                       void* const* streams, const int* devices);
+
+/* Peer mapping helpers for one-process-per-GPU runs (CUDA IPC; thin wrappers so that callers need no CUDA
+ * bindings): export a 64-byte handle + offset for a device pointer / open one exported by another process
+ * of the same node (returns the pointer mapped in this process; never freed before exit) / enable peer access
+ * from the current device to `peer_device`. */
+int tvdk_ipc_export(const void* device_ptr, unsigned char handle_out[64], int64_t* offset_out);
+int tvdk_ipc_open(const unsigned char handle[64], int64_t offset, void** ptr_out);
+int tvdk_enable_peer(int peer_device);
+
 #ifdef __cplusplus
 }
 #endif

@@ -10,6 +10,7 @@ SRCS = [
     os.path.join(HERE, "tvdk_emu.cpp"),
     os.path.join(ROOT, "darsia_b200", "csrc", "tvdk_core.h"),
     os.path.join(ROOT, "darsia_b200", "csrc", "tvdk_host.inl"),
+    os.path.join(ROOT, "darsia_b200", "csrc", "tvdk_slab.inl"),
     os.path.join(ROOT, "include", "tvdk.h"),
 ]
 

@@ -20,11 +20,9 @@ operator-level cases).  A fresh solver object is used per call.
 
 from __future__ import annotations
 
-import importlib.util
 import json
 import os
 import sys
-import types
 
 import numpy as np
 
@@ -33,74 +31,13 @@ OUT = os.path.dirname(os.path.abspath(__file__))
 
 
 def load_reference():
-    """Execute the reference hot-path files verbatim under a stub namespace."""
-    import scipy.sparse.linalg as spla
+    """Execute the reference hot-path files verbatim under a stub namespace (``oracle/ref_loader.py``)."""
+    root = os.path.dirname(os.path.dirname(OUT))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    from oracle.ref_loader import load_reference as _load
 
-    skimage = types.ModuleType("skimage")
-
-    def _as(dtype):
-        def f(x):
-            x = np.asarray(x)
-            if not np.issubdtype(x.dtype, np.floating):
-                raise TypeError("stub skimage: float arrays only")
-            return x if dtype is None else x.astype(dtype, copy=False)
-
-        return f
-
-    skimage.img_as_float = _as(None)
-    skimage.img_as_float32 = _as(np.float32)
-    skimage.img_as_float64 = _as(np.float64)
-    sys.modules["skimage"] = skimage
-
-    darsia = types.ModuleType("darsia")
-
-    class Image:  # duck-typed stand-in for isinstance checks in tvd.py
-        def __init__(self, img):
-            self.img = img
-
-        def copy(self):
-            import copy
-
-            return copy.deepcopy(self)
-
-    darsia.Image = Image
-    sys.modules["darsia"] = darsia
-
-    if not getattr(spla.cg, "_tol_shim", False):
-        _cg = spla.cg
-
-        def cg(A, b, x0=None, *, tol=None, rtol=1e-5, atol=0.0, maxiter=None, M=None, callback=None):
-            if tol is not None:
-                rtol = tol
-            return _cg(A, b, x0=x0, rtol=rtol, atol=atol, maxiter=maxiter, M=M, callback=callback)
-
-        cg._tol_shim = True
-        spla.cg = cg
-
-    if not hasattr(np.lib, "pad"):  # NumPy >= 2 removed the alias mg.py:233 uses
-        np.lib.pad = np.pad
-
-    order = [
-        "utils/array_slice.py",
-        "utils/derivatives.py",
-        "utils/dtype.py",
-        "utils/linear_solvers/solver.py",
-        "utils/linear_solvers/jacobi.py",
-        "utils/linear_solvers/cg.py",
-        "utils/linear_solvers/mg.py",
-        "restoration/tvd.py",
-        "restoration/split_bregman_tvd.py",
-        "restoration/h1_regularization.py",
-    ]
-    for rel in order:
-        name = "darsia._ref_" + rel.replace("/", "_")[:-3]
-        spec = importlib.util.spec_from_file_location(name, os.path.join(REF, rel))
-        mod = importlib.util.module_from_spec(spec)
-        spec.loader.exec_module(mod)
-        for k, v in vars(mod).items():
-            if not k.startswith("_") and getattr(v, "__module__", None) == name:
-                setattr(darsia, k, v)
-    return darsia
+    return _load(REF if os.path.isdir(REF) else None)
 
 
 def phantom(shape, seed, dtype=np.float64):
