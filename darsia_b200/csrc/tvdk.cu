@@ -134,6 +134,65 @@ __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel(const typen
   }
 }
 
+// Runner of the TMA-staged kernels: the argument block is __grid_constant__ (the tensor maps are read from
+// kernel-parameter space by the TMA unit), the mbarriers are initialised before anybody may wait on them.
+template <class K>
+__global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel_tma(const __grid_constant__ typename K::Args a,
+                                                                         double* partials, unsigned* counters) {
+  extern __shared__ __align__(128) unsigned char smem_tma[];
+  LaunchCtx lc;
+  lc.tx = threadIdx.x; lc.ty = threadIdx.y; lc.ntx = blockDim.x; lc.nty = blockDim.y;
+  lc.bx = blockIdx.x; lc.by = blockIdx.y; lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
+  if (K::skipped(a, lc)) return;  // block-uniform (whole problems are skipped)
+  K::bar_init(a, lc, smem_tma);
+  __syncthreads();
+  K k;
+  k.init(a, lc, smem_tma);
+  while (k.more()) {
+    k.pre(a, smem_tma);
+    __syncthreads();
+    k.post(a, smem_tma);
+  }
+  if constexpr (K::NRED > 0) {
+    constexpr int NR = K::NRED;
+    __shared__ double wsum[kMaxWarps][NR];
+    __shared__ bool is_last;
+    const int tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const int nthreads = blockDim.x * blockDim.y;
+    const unsigned nblk = gridDim.x * gridDim.y;
+    const unsigned blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const int b = blockIdx.z;
+    double v[NR];
+#pragma unroll
+    for (int r = 0; r < NR; ++r) v[r] = k.red[r];
+    block_sum<NR>(v, wsum, tid, nthreads);
+    double* pb = partials + (size_t)b * nblk * NR;
+    if (tid == 0) {
+#pragma unroll
+      for (int r = 0; r < NR; ++r) pb[(size_t)r * nblk + blk] = v[r];
+      __threadfence();
+      const unsigned prev = atomicAdd(&counters[b], 1u);
+      is_last = (prev == nblk - 1);
+    }
+    __syncthreads();
+    if (is_last) {  // last block of this problem: ordered second stage + scalar updates (as in tvdk_kernel)
+      __threadfence();
+      double s[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) s[r] = 0.0;
+      for (unsigned i = tid; i < nblk; i += nthreads) {
+#pragma unroll
+        for (int r = 0; r < NR; ++r) s[r] += __ldcg(pb + (size_t)r * nblk + i);
+      }
+      block_sum<NR>(s, wsum, tid, nthreads);
+      if (tid == 0) {
+        K::finalize(a, b, s);
+        counters[b] = 0;
+      }
+    }
+  }
+}
+
 namespace backend {
 
 static int cuda_fail(cudaError_t e, const char* what);
@@ -163,6 +222,30 @@ int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, 
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return 0;
 }
+
+template <class K>
+int launch_tma(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem, void* stream,
+               double* partials, unsigned* counters) {
+  static thread_local size_t smem_set[kMaxDevices] = {};
+  if (smem > 48 * 1024) {
+    const int dev = current_device();
+    if (dev < 0 || dev >= kMaxDevices || smem > smem_set[dev]) {
+      cudaError_t e = cudaFuncSetAttribute(tvdk_kernel_tma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute");
+      if (dev >= 0 && dev < kMaxDevices) smem_set[dev] = smem;
+    }
+  }
+  dim3 grid(gx, gy, gz), block(ntx, nty, 1);
+  tvdk_kernel_tma<K><<<grid, block, smem, (cudaStream_t)stream>>>(a, partials, counters);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch (TMA)");
+  return 0;
+}
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda): a rank-3 tiled map of one field,
+// no swizzle, no interleave, zero fill outside the tensor
+static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long long ny, long long nz, long long row_bytes,
+                      long long plane_bytes, int bx, int by);
 
 static int memset_async(void* p, int value, size_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream);
@@ -398,6 +481,38 @@ static int cuda_fail(cudaError_t e, const char* what) {
 
 // ---- peer mapping helpers (include/tvdk.h) ---------------------------------------------------------------
 #include <cuda.h>
+
+namespace tvdk {
+namespace backend {
+static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long long ny, long long nz, long long row_bytes,
+                      long long plane_bytes, int bx, int by) {
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static encode_fn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+    if (e != cudaSuccess || !fn) return cuda_fail(e, "cudaGetDriverEntryPoint(cuTensorMapEncodeTiled)");
+    encode = (encode_fn)fn;
+  }
+  static_assert(sizeof(TmaMap) == sizeof(CUtensorMap), "TmaMap must be a CUtensorMap");
+  if (bx > 256 || by > 256 || (bx * esize) % 16 != 0) return fail(TVDK_ERR_INVALID, "internal: bad TMA box %d x %d", bx, by);
+  if (((uintptr_t)base & 15) || (row_bytes & 15) || (plane_bytes & 15))
+    return fail(TVDK_ERR_INVALID, "TMA needs 16-byte aligned fields and row pitches");
+  const cuuint64_t dims[3] = {(cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz};
+  const cuuint64_t strides[2] = {(cuuint64_t)row_bytes, (cuuint64_t)plane_bytes};
+  const cuuint32_t box[3] = {(cuuint32_t)bx, (cuuint32_t)by, 1u};
+  const cuuint32_t estr[3] = {1u, 1u, 1u};
+  const CUresult r = encode(reinterpret_cast<CUtensorMap*>(m), esize == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32,
+                            3, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(TVDK_ERR_INVALID, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return 0;
+}
+}  // namespace backend
+}  // namespace tvdk
 
 int tvdk_ipc_export(const void* device_ptr, unsigned char handle_out[64], int64_t* offset_out) {
   using namespace tvdk;

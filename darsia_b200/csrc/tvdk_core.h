@@ -2583,6 +2583,325 @@ struct KPack {
 };
 
 // ==========================================================================================
+// TMA staging (sm_100a: cp.async.bulk.tensor + mbarrier; tests/emu: a synchronous copy with zero fill)
+//   A TmaMap describes one field as a 3-D tensor (x: pitch, y: ny, z: nb * n0 planes) together with the box a
+//   CTA fetches per plane.  Out-of-range box elements are ZERO-filled by the hardware; every boundary rule
+//   below selects around them exactly like the march kernels select around their clamped loads.
+// ==========================================================================================
+#if defined(__CUDACC__)
+struct alignas(64) TmaMap {
+  unsigned long long opaque[16];  // CUtensorMap (filled by cuTensorMapEncodeTiled on the host)
+};
+TVDK_DEV unsigned smem_addr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+TVDK_DEV void mbar_init(unsigned long long* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_addr(bar)), "r"(count) : "memory");
+}
+TVDK_DEV void mbar_init_fence() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+TVDK_DEV void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_addr(bar)), "r"(bytes) : "memory");
+}
+TVDK_DEV void mbar_wait(unsigned long long* bar, unsigned parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_addr(bar)),
+      "r"(parity)
+      : "memory");
+}
+TVDK_DEV void tma_load_3d(void* dst, const TmaMap* map, int x, int y, int z, unsigned long long* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+          smem_addr(dst)),
+      "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_addr(bar))
+      : "memory");
+}
+#else
+struct TmaMap {  // emulator: plain description of the tensor and the box
+  const unsigned char* base;
+  long long dim[3];       // elements: x, y, z
+  long long stride_b[2];  // bytes between rows (y) and planes (z)
+  int box[3];
+  int esize;
+};
+TVDK_DEV void mbar_init(unsigned long long*, int) {}
+TVDK_DEV void mbar_init_fence() {}
+TVDK_DEV void mbar_expect_tx(unsigned long long*, unsigned) {}
+TVDK_DEV void mbar_wait(unsigned long long*, unsigned) {}
+TVDK_DEV void tma_load_3d(void* dst, const TmaMap* m, int x, int y, int z, unsigned long long*) {
+  unsigned char* d = reinterpret_cast<unsigned char*>(dst);
+  for (int k = 0; k < m->box[2]; ++k)
+    for (int j = 0; j < m->box[1]; ++j)
+      for (int i = 0; i < m->box[0]; ++i) {
+        const long long X = x + i, Y = y + j, Z = z + k;
+        unsigned char* q = d + ((long long)(k * m->box[1] + j) * m->box[0] + i) * m->esize;
+        const bool in = X >= 0 && X < m->dim[0] && Y >= 0 && Y < m->dim[1] && Z >= 0 && Z < m->dim[2];
+        for (int e = 0; e < m->esize; ++e) q[e] = in ? m->base[Z * m->stride_b[1] + Y * m->stride_b[0] + X * m->esize + e] : 0;
+      }
+}
+#endif
+
+// ==========================================================================================
+// K1-TMA  fused outer iteration for Jacobi(maxiter=1), 3-D, ANISOTROPIC, scalar coefficients
+//     (BASELINE config 5; same arithmetic as K1: split_bregman_tvd.py:84-89 rhs, jacobi.py:101-114 sweep,
+//      :142-146 shrink + Bregman update, :161 increment)
+//   All inputs of a plane arrive as TMA boxes (tile + halo) in a ring of NS shared-memory stages, issued by
+//   one thread NS - 1 planes ahead: no halo threads for u or t, no register prefetch, no per-thread load
+//   addresses.  The anisotropic w_a = ell (b_a - d_a) is a pointwise function of t_a alone, so the values the
+//   divergence needs at y - 1 and x - 1 are re-derived from the staged t instead of being published by halo
+//   threads: the only halo left is the one row / one vector on the high side where u+ is recomputed.
+//   Per step j (one barrier):  A: u+(j) from stage(j) (+ u(j+1) from stage(j+1)) -> ring[j & 1]
+//                              B: t+(j-1) from ring[(j-1) & 1] and registers, stores of plane j - 1
+//                              barrier ; one thread refills stage(j) with plane j + NS.
+//   Stage layout (elements): U (ntx+2)V x (nty+2) | F | T0 (ntx V x nty each) | T1 ntx V x (nty+1) | T2 (ntx+1)V x nty.
+// ==========================================================================================
+template <typename T>
+struct KFusedJ1T {
+  static constexpr int D = 3;
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = 0, RH = 1, NRED = 1;
+  static constexpr int NS = 3;
+  static constexpr int ZC3D = 64;
+  static constexpr int NTX3D = sizeof(T) == 4 ? 16 : 32;
+  static constexpr bool TMA = true;
+  typedef Col<T, D, LH, RH, 0, 1> C;
+  struct Args {
+    Geom g;
+    Coefs<T> k;
+    T* u_out;
+    T* t_out;
+    long long tcs_out;
+    const tvdk_stat_t* skip;  // problems with skip[b].done are left untouched
+    Fin fin;
+    TmaMap tm_u, tm_f, tm_t0, tm_t1, tm_t2;
+  };
+  // shared-memory layout for a thread block of ntx x nty threads (byte offsets; every buffer 128-byte aligned)
+  struct Lay {
+    int pU, pF, pT2;          // row pitches in elements (T0, T1 share pF)
+    int oU, oF, oT0, oT1, oT2;  // byte offsets inside one stage
+    int stage_bytes, ring_bytes, ring_off, stage_off, total;
+    unsigned tx_bytes;        // bytes one plane's five boxes deliver
+  };
+  static TVDK_HD int a128(int x) { return (x + 127) / 128 * 128; }
+  static TVDK_HD Lay layout(int ntx, int nty) {
+    Lay L;
+    const int W = (int)sizeof(T);
+    L.pU = (ntx + 2) * V;
+    L.pF = ntx * V;
+    L.pT2 = (ntx + 1) * V;
+    const int bU = L.pU * (nty + 2) * W, bF = L.pF * nty * W, bT1 = L.pF * (nty + 1) * W, bT2 = L.pT2 * nty * W;
+    L.oU = 0;
+    L.oF = L.oU + a128(bU);
+    L.oT0 = L.oF + a128(bF);
+    L.oT1 = L.oT0 + a128(bF);
+    L.oT2 = L.oT1 + a128(bT1);
+    L.stage_bytes = L.oT2 + a128(bT2);
+    L.tx_bytes = (unsigned)(bU + bF + bF + bT1 + bT2);
+    L.ring_bytes = a128((L.pF * (nty + 1) + V) * W);  // one row + one vector of slack for the halo threads' reads
+    L.ring_off = 128;                                 // [0, 128): the NS mbarriers
+    L.stage_off = L.ring_off + 2 * L.ring_bytes;
+    L.total = L.stage_off + NS * L.stage_bytes;
+    return L;
+  }
+  static TVDK_HD size_t smem_bytes(int ntx, int nty) { return (size_t)layout(ntx, nty).total; }
+
+  C c;
+  Lay L;
+  int j, pstart, x0b, y0b, zb;  // march plane; first staged plane; box origin of the tile; plane offset of the problem
+  int iU, iF, iT1, iT2;         // element offsets of the thread's vector inside the stage buffers (iT0 = iR = iF)
+  Vec<T> u_lo, u_c;             // u(j-1), u(j)
+  Vec<T> w0_prev, up_prev, b_prev[D];
+  bool leader;
+  double red[NRED];
+
+  static TVDK_DEV bool skipped(const Args& a, const LaunchCtx& lc) { return a.skip && a.skip[lc.bz].done; }
+  static TVDK_DEV void bar_init(const Args&, const LaunchCtx& lc, unsigned char* smem) {
+    if (lc.tx == 0 && lc.ty == 0) {
+      unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+      for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+      mbar_init_fence();
+    }
+  }
+  TVDK_DEV unsigned long long* bar(unsigned char* smem, int p) const {
+    return reinterpret_cast<unsigned long long*>(smem) + (p - pstart) % NS;
+  }
+  TVDK_DEV unsigned char* stage(unsigned char* smem, int p) const { return smem + L.stage_off + ((p - pstart) % NS) * L.stage_bytes; }
+  TVDK_DEV T* ring(unsigned char* smem, int slot) const { return reinterpret_cast<T*>(smem + L.ring_off + slot * L.ring_bytes); }
+  TVDK_DEV void issue(const Args& a, unsigned char* smem, int p) const {  // one thread: plane p -> its stage
+    unsigned long long* b = bar(smem, p);
+    unsigned char* s = stage(smem, p);
+    mbar_expect_tx(b, L.tx_bytes);
+    const int z = zb + p;
+    tma_load_3d(s + L.oU, &a.tm_u, x0b - V, y0b - 1, z, b);
+    tma_load_3d(s + L.oF, &a.tm_f, x0b, y0b, z, b);
+    tma_load_3d(s + L.oT0, &a.tm_t0, x0b, y0b, z, b);
+    tma_load_3d(s + L.oT1, &a.tm_t1, x0b, y0b - 1, z, b);
+    tma_load_3d(s + L.oT2, &a.tm_t2, x0b - V, y0b, z, b);
+  }
+  TVDK_DEV void wait(unsigned char* smem, int p) const { mbar_wait(bar(smem, p), (unsigned)(((p - pstart) / NS) & 1)); }
+
+  // w = ell (b - d), b of one component from its t (split_bregman_tvd.py:80-81, :142-146)
+  static TVDK_DEV void bw1(T t, const Scalars<T>& sc, T& b, T& w) {
+    T tt[1] = {t}, bb[1], ww[1];
+    bw_from_t<T, 1, false>(tt, sc.kappa, sc.ell, bb, ww);
+    b = bb[0];
+    w = ww[0];
+  }
+
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char* smem) {
+    c.setup(a.g, lc);
+    L = layout(lc.ntx, lc.nty);
+    red[0] = 0.0;
+    leader = lc.tx == 0 && lc.ty == 0;
+    const int xt = lc.bx % a.g.xtiles, yt = lc.bx / a.g.xtiles;
+    x0b = xt * C::iw(lc.ntx);
+    y0b = yt * C::ih(lc.nty);
+    zb = c.b * a.g.n0;
+    // (no halo threads on the low side: a tile that STARTS at the boundary must take the selecting path too)
+    c.edge = c.edge || x0b == 0 || y0b == 0;
+    iU = (lc.ty + 1) * L.pU + (lc.tx + 1) * V;
+    iF = lc.ty * L.pF + lc.tx * V;
+    iT1 = (lc.ty + 1) * L.pF + lc.tx * V;
+    iT2 = lc.ty * L.pT2 + (lc.tx + 1) * V;
+    j = c.z0;
+    pstart = c.z0 - 1;
+    if (leader) {
+      for (int p = pstart; p < pstart + NS && p <= c.z1 + 1; ++p) issue(a, smem, p);
+    }
+    // planes z0 - 1 (u below, w_0 below) and z0
+    wait(smem, pstart);
+    wait(smem, c.z0);
+    const unsigned char* sm1 = stage(smem, pstart);
+    u_c = vload(reinterpret_cast<const T*>(stage(smem, c.z0) + L.oU) + iU);
+    u_lo = u_c;
+    w0_prev = vsplat<T>((T)0);
+    if (c.has_zlo(a.g, j)) {
+      u_lo = vload(reinterpret_cast<const T*>(sm1 + L.oU) + iU);
+      const Vec<T> t0 = vload(reinterpret_cast<const T*>(sm1 + L.oT0) + iF);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        T b;
+        bw1(t0.v[v], a.k.sc, b, w0_prev.v[v]);
+      }
+    }
+    up_prev = vsplat<T>((T)0);
+#pragma unroll
+    for (int d = 0; d < D; ++d) b_prev[d] = vsplat<T>((T)0);
+    return true;
+  }
+  TVDK_DEV bool more() const { return j <= c.z1; }
+
+  template <bool E>
+  TVDK_DEV void step(const Args& a, unsigned char* smem) {
+    const Scalars<T>& sc = a.k.sc;
+    const int slot = (j - c.z0) & 1;
+    wait(smem, j + 1);  // (every issued plane is waited for, also when its data ends up unused)
+    const bool have_row = (j < c.z1) || c.plane_ok(a.g, j);
+    Vec<T> up = vsplat<T>((T)0), u_hi = u_c;
+    Vec<T> b_cur[D], w0_cur = w0_prev;
+#pragma unroll
+    for (int d = 0; d < D; ++d) b_cur[d] = b_prev[d];
+    if (have_row) {
+      const unsigned char* sj = stage(smem, j);
+      const T* U = reinterpret_cast<const T*>(sj + L.oU);
+      const T* T1 = reinterpret_cast<const T*>(sj + L.oT1);
+      const T* T2 = reinterpret_cast<const T*>(sj + L.oT2);
+      if (c.has_zhi(a.g, j)) u_hi = vload(reinterpret_cast<const T*>(stage(smem, j + 1) + L.oU) + iU);
+      const Vec<T> f = vload(reinterpret_cast<const T*>(sj + L.oF) + iF);
+      const Vec<T> t0 = vload(reinterpret_cast<const T*>(sj + L.oT0) + iF);
+      const Vec<T> t1 = vload(T1 + iT1), t1m = vload(T1 + iT1 - L.pF);
+      const Vec<T> t2 = vload(T2 + iT2);
+      const T t2l = T2[iT2 - 1];
+      const Vec<T> ym = vload(U + iU - L.pU), yp = vload(U + iU + L.pU);
+      const T xl = U[iU - 1], xr = U[iU + V];
+      Vec<T> w1, w2, w1m;
+      T w2l, bdummy;
+      bw1(t2l, sc, bdummy, w2l);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        bw1(t0.v[v], sc, b_cur[0].v[v], w0_cur.v[v]);
+        bw1(t1.v[v], sc, b_cur[1].v[v], w1.v[v]);
+        bw1(t2.v[v], sc, b_cur[2].v[v], w2.v[v]);
+        bw1(t1m.v[v], sc, bdummy, w1m.v[v]);
+      }
+      // rhs = omega f + H_0 w_0 + H_1 w_1 + H_2 w_2 in the reference's order (:84-89), then the sweep (jacobi.py:112-114)
+      const bool zlo = c.template ZLO<E>(a.g, j);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        T rhs = sc.omega * f.v[v];
+        if (zlo) rhs += w0_cur.v[v] - w0_prev.v[v];
+        if (c.template YLO<E>()) rhs += w1.v[v] - w1m.v[v];
+        const T wl = v > 0 ? w2.v[v > 0 ? v - 1 : 0] : w2l;
+        if (c.template HL<E>(v)) rhs += w2.v[v] - wl;
+        T nb = u_lo.v[v] + u_hi.v[v];
+        nb += c.template YLO<E>() ? ym.v[v] : u_c.v[v];
+        nb += c.template YHI<E>() ? yp.v[v] : u_c.v[v];
+        const T left = v > 0 ? u_c.v[v > 0 ? v - 1 : 0] : xl;
+        const T right = v < V - 1 ? u_c.v[v < V - 1 ? v + 1 : 0] : xr;
+        nb += c.template HL<E>(v) ? left : u_c.v[v];
+        nb += c.template HR<E>(v) ? right : u_c.v[v];
+        up.v[v] = rhs * sc.inv_diag + nb * sc.c_nb;
+      }
+      vstore(ring(smem, slot) + iF, up);
+    }
+    if (j > c.z0) {
+      // outputs of plane j-1: t_new = G u+ + b, u_out = u+, increment (:142-146, :161)
+      const int zo = j - 1;
+      const long long oo = c.cur - c.s0b;
+      const T* R = ring(smem, slot ^ 1);
+      const Vec<T> yp = vload(R + iF + L.pF);
+      const T xr = R[iF + V];
+      const bool zhi = c.template ZHI<E>(a.g, zo);
+      Vec<T> tn[D];
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        tn[0].v[v] = (zhi ? up.v[v] - up_prev.v[v] : (T)0) + b_prev[0].v[v];
+        tn[1].v[v] = (c.template YHI<E>() ? yp.v[v] - up_prev.v[v] : (T)0) + b_prev[1].v[v];
+        const T right = v < V - 1 ? up_prev.v[v < V - 1 ? v + 1 : 0] : xr;
+        tn[2].v[v] = (c.template HR<E>(v) ? right - up_prev.v[v] : (T)0) + b_prev[2].v[v];
+      }
+      sto(c, a.u_out, oo, up_prev);
+#pragma unroll
+      for (int d = 0; d < D; ++d) sto(c, a.t_out + d * a.tcs_out, oo, tn[d]);
+      if (c.st) {  // u_lo still holds u(j-1)
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (c.template OK<E>(v)) {
+            const double df = (double)up_prev.v[v] - (double)u_lo.v[v];
+            red[0] += df * df;
+          }
+      }
+    }
+    u_lo = u_c;
+    u_c = u_hi;
+    w0_prev = w0_cur;
+    up_prev = up;
+#pragma unroll
+    for (int d = 0; d < D; ++d) b_prev[d] = b_cur[d];
+  }
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if (c.edge || c.zedge(a.g, j) || c.zedge(a.g, j - 1))
+      step<true>(a, smem);
+    else
+      step<false>(a, smem);
+  }
+  // after the barrier: stage(j) (and, on the first step, the stage of plane z0 - 1) is free again
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (leader) {
+      if (j == c.z0 && pstart + NS <= c.z1 + 1) issue(a, smem, pstart + NS);
+      if (j + NS <= c.z1 + 1) issue(a, smem, j + NS);
+    }
+    c.cur += c.s0b;
+    ++j;
+  }
+  static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED, b, tot); }
+};
+
+// ==========================================================================================
 // Slab decomposition: halo exchange + all-reduce over peer memory (tvdk_slab.inl; include/tvdk.h)
 //   Every rank's arena starts with a SlabHeader.  slot[parity][s] is the mailbox rank s writes into
 //   (on EVERY rank, its own included): up to 8 partial sums, then -- after a system-wide fence --

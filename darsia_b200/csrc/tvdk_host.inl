@@ -122,6 +122,10 @@ struct KernelNtx3<K, std::void_t<decltype(K::NTX3D)>> {
   static constexpr int value = K::NTX3D;
 };
 template <class K, typename = void>
+struct KernelIsTma : std::false_type {};
+template <class K>
+struct KernelIsTma<K, std::void_t<decltype(K::TMA)>> : std::bool_constant<K::TMA> {};
+template <class K, typename = void>
 struct KernelPf {
   static int get(int) { return 0; }
 };
@@ -266,7 +270,10 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
   L.gx = g.xtiles * g.ytiles;
   L.gy = (nz + zc - 1) / zc;
   L.gz = g.nb;
-  L.smem = (size_t)K::NROWS * C::row_elems(L.ntx, L.nty) * sizeof(T);
+  if constexpr (KernelIsTma<K>::value)
+    L.smem = K::smem_bytes(L.ntx, L.nty);
+  else
+    L.smem = (size_t)K::NROWS * C::row_elems(L.ntx, L.nty) * sizeof(T);
   L.g = g;
   return L;
 }
@@ -293,6 +300,10 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   LaunchCfg e = plan_launch<KCgFused<T, D, false>, T, D>(g, tune, true);
   LaunchCfg ch = plan_launch<KChamb<T, D, 0>, T, D>(g, tune, true);
   size_t m = (size_t)ch.gx * ch.gy * ch.gz * 2;
+  if constexpr (D == 3) {
+    LaunchCfg tm = plan_launch<KFusedJ1T<T>, T, D>(g, tune, true);
+    m = std::max(m, (size_t)tm.gx * tm.gy * tm.gz * 2);
+  }
   if constexpr (D == 2) {
     LaunchCfg x2 = plan_launch<KFusedJ1x2<T, false, false>, T, D>(g, tune, true);
     m = std::max(m, (size_t)x2.gx * x2.gy * x2.gz * 2);
@@ -332,6 +343,53 @@ static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_ti
   return backend::launch<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
 }
 
+// TMA-staged kernels (3-D anisotropic fused Jacobi-1): on by default, TVDK_TMA=0 selects the march kernel (A/B runs)
+static bool tma_enabled() {
+  static const int v = env_int("TVDK_TMA", 1);
+  return v != 0;
+}
+
+// one field as a 3-D tensor (x: nx of pitch, y: ny, z: nb * n0 planes) with a (bx, by, 1) box per plane
+template <typename T>
+static int field_map(TmaMap* m, const T* base, const Geom& g, int bx, int by) {
+  return backend::tma_encode(m, base, (int)sizeof(T), g.nx, g.ny, (long long)g.nb * g.n0, (long long)g.pitch * (long long)sizeof(T),
+                             g.s0 * (long long)sizeof(T), bx, by);
+}
+
+// K1 for 3-D anisotropic problems with scalar coefficients: the TMA-staged kernel
+template <typename T>
+static int run_fj1_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const T* f, const T* u_in, T* u_out, const T* t_in,
+                       T* t_out, long long tcs_in, long long tcs_out, const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc,
+                       void* stream) {
+  typedef KFusedJ1T<T> K;
+  constexpr int V = Vec<T>::N;
+  LaunchCfg L = plan_launch<K, T, 3>(g, tune, true);
+  typename K::Args a;
+  memset(&a, 0, sizeof a);
+  a.g = L.g;
+  a.k = k;
+  a.u_out = u_out;
+  a.t_out = t_out;
+  a.tcs_out = tcs_out;
+  a.skip = skip;
+  a.fin = fin;
+  const int tx = L.ntx * V, ty = L.nty;
+  TVDK_TRY(field_map(&a.tm_u, u_in, L.g, tx + 2 * V, ty + 2));
+  TVDK_TRY(field_map(&a.tm_f, f, L.g, tx, ty));
+  TVDK_TRY(field_map(&a.tm_t0, t_in, L.g, tx, ty));
+  TVDK_TRY(field_map(&a.tm_t1, t_in + tcs_in, L.g, tx, ty + 1));
+  TVDK_TRY(field_map(&a.tm_t2, t_in + 2 * tcs_in, L.g, tx + V, ty));
+  if ((size_t)L.gx * L.gy * L.gz * K::NRED > sc.partial_cap) return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
+  ++g_launches;
+  return backend::launch_tma<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
+}
+
+// the fused Jacobi(1) iteration, whichever kernel serves this problem class
+template <typename T, int D>
+static int run_fj1(bool iso, bool het, const Geom& g, const Tune& tune, const Coefs<T>& k, const T* f, const T* u_in, T* u_out,
+                   const T* t_in, T* t_out, long long tcs_in, long long tcs_out, const tvdk_stat_t* skip, const Fin& fin,
+                   const Scratch& sc, void* stream);
+
 // run f(std::bool_constant<a>, std::bool_constant<b>) -- maps runtime flags onto template args
 template <class F>
 static int dispatch2(bool a, bool b, F&& f) {
@@ -349,6 +407,27 @@ static Fin no_fin() {
   f.kind = FIN_NONE;
   f.eps = -1.0;
   return f;
+}
+
+template <typename T, int D>
+static int run_fj1(bool iso, bool het, const Geom& g, const Tune& tune, const Coefs<T>& k, const T* f, const T* u_in, T* u_out,
+                   const T* t_in, T* t_out, long long tcs_in, long long tcs_out, const tvdk_stat_t* skip, const Fin& fin,
+                   const Scratch& sc, void* stream) {
+  if constexpr (D == 3) {
+    // (a TMA box holds at most 256 elements per axis: wider forced tiles stay on the march kernel)
+    const LaunchCfg probe = plan_launch<KFusedJ1T<T>, T, 3>(g, tune, true);
+    if (!iso && !het && tma_enabled() && (probe.ntx + 2) * Vec<T>::N <= 256 && probe.nty + 2 <= 256)
+      return run_fj1_tma<T>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
+  }
+  return dispatch2(iso, het, [&](auto I, auto H) {
+    typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.f = f; a.u_in = u_in; a.u_out = u_out;
+    a.t_in = t_in; a.t_out = t_out; a.tcs_in = tcs_in; a.tcs_out = tcs_out;
+    a.skip = skip; a.fin = fin;
+    return run<K, T, D>(a, g, tune, true, sc, stream);
+  });
 }
 
 // ---------------------------------------------------------------------------------------
@@ -607,15 +686,8 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       // (both iterations done above)
     } else if (fp.fusedj1 && !expl_now) {
       const Fin fn = outer_fin(it, 1 - cur);
-      TVDK_TRY(dispatch2(iso, het, [&](auto I, auto H) {
-        typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
-        typename K::Args a;
-        memset(&a, 0, sizeof a);
-        a.k = k; a.f = f; a.u_in = ubuf[cur]; a.u_out = ubuf[1 - cur];
-        a.t_in = tbuf[cur]; a.t_out = tbuf[1 - cur]; a.tcs_in = tcs[cur]; a.tcs_out = tcs[1 - cur];
-        a.skip = st; a.fin = fn;
-        return run<K, T, D>(a, g, tune, true, sc, stream);
-      }));
+      TVDK_TRY((run_fj1<T, D>(iso, het, g, tune, k, f, ubuf[cur], ubuf[1 - cur], tbuf[cur], tbuf[1 - cur], tcs[cur], tcs[1 - cur], st,
+                              fn, sc, stream)));
       cur = 1 - cur;
     } else if (fp.cg) {
       Fin fn = no_fin();
@@ -1083,14 +1155,8 @@ static int fj1_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const
   OpCtx<T, D> o;
   TVDK_TRY(o.init(gg, ws, wsb, stream));
   const Coefs<T> k = make_coefs<T>(mu, om, el, D);
-  return dispatch2(iso != 0, k.sc.hetero != 0, [&](auto I, auto H) {
-    typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
-    typename K::Args a;
-    memset(&a, 0, sizeof a);
-    a.k = k; a.f = (const T*)f; a.u_in = (const T*)u_in; a.u_out = (T*)u_out;
-    a.t_in = (const T*)t_in; a.t_out = (T*)t_out; a.tcs_in = tcs; a.tcs_out = tcs; a.fin = sum_fin(sum_out);
-    return run<K, T, D>(a, o.g, o.tune, true, o.sc, stream);
-  });
+  return run_fj1<T, D>(iso != 0, k.sc.hetero != 0, o.g, o.tune, k, (const T*)f, (const T*)u_in, (T*)u_out, (const T*)t_in, (T*)t_out,
+                       tcs, tcs, nullptr, sum_fin(sum_out), o.sc, stream);
 }
 
 template <typename T, int D>

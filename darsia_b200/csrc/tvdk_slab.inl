@@ -359,15 +359,8 @@ static int solve_slab_impl(int nlocal, const tvdk_problem_t* const* problems, co
       // K1: one launch per outer iteration, ping-pong (u, t); its outputs' ghosts: u 1 up / 2 down, t 1 each way
       const int cur = R[0].cur;
       TVDK_TRY(each([&](SlabRank<T>& r) {
-        return dispatch2(iso, het, [&](auto I, auto H) {
-          typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
-          typename K::Args a;
-          memset(&a, 0, sizeof a);
-          a.k = r.k; a.f = r.f; a.u_in = r.ubuf[cur]; a.u_out = r.ubuf[1 - cur];
-          a.t_in = r.tbuf[cur]; a.t_out = r.tbuf[1 - cur]; a.tcs_in = r.tcs[cur]; a.tcs_out = r.tcs[1 - cur];
-          a.skip = r.st; a.fin = local_fin(r);
-          return run<K, T, D>(a, r.g, tune, true, r.sc, r.stream);
-        });
+        return run_fj1<T, D>(iso, het, r.g, tune, r.k, r.f, r.ubuf[cur], r.ubuf[1 - cur], r.tbuf[cur], r.tbuf[1 - cur], r.tcs[cur],
+                             r.tcs[1 - cur], r.st, local_fin(r), r.sc, r.stream);
       }));
       TVDK_TRY(comm_step(R, halos_of([&](SlabRank<T>& r) {
                            std::vector<HaloSpec> h{{r.ubuf[1 - cur], 1, 2}};

@@ -23,6 +23,7 @@ from .tvd_oracle import (  # noqa: F401
     Solver,
     backward_diff,
     cg_matvec,
+    energy_functional,
     forward_diff,
     jacobi_sweep,
     laplace,

@@ -434,6 +434,13 @@ def _split_bregman_single(
     return u.astype(img.dtype, copy=False)  # :177 (float -> same float)
 
 
+def energy_functional(x: np.ndarray, img: np.ndarray, mu: Coeff, omega: Coeff, dim: int) -> float:
+    """``_functional`` of split_bregman_tvd.py:71-77 (what ``verbose`` prints):
+    ``0.5 ||omega (x - img)||^2 + sum_j sum |mu G_j x|`` for one ``dim``-dimensional problem."""
+    return float(0.5 * np.linalg.norm(omega * (x - img)) ** 2
+                 + sum(np.sum(np.abs(mu * backward_diff(x, j, dim))) for j in range(dim)))
+
+
 def _coeff_slice(c: Coeff, idx: tuple, spatial_shape: tuple, full_shape: tuple) -> Coeff:
     """Pick the coefficient for one trailing-axis slice (batching rule Q5/Q6)."""
     if not isinstance(c, np.ndarray) or c.ndim == 0:

@@ -11,6 +11,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
 #include <vector>
 
 #include "../../darsia_b200/csrc/tvdk_core.h"
@@ -18,15 +19,20 @@
 namespace tvdk {
 namespace backend {
 
+template <class K, typename = void>
+struct has_tma : std::false_type {};
+template <class K>
+struct has_tma<K, std::void_t<decltype(K::TMA)>> : std::bool_constant<K::TMA> {};
+
 template <class K>
 int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem_bytes, void*,
            double*, unsigned*) {
   const int nthreads = ntx * nty;
   std::vector<K> th(nthreads);
-  std::vector<unsigned char> smem_store(smem_bytes + 64, 0);
-  // 16-byte aligned base, like the device's dynamic shared memory
+  std::vector<unsigned char> smem_store(smem_bytes + 256, 0);
+  // 128-byte aligned base, like the device's dynamic shared memory
   unsigned char* smem = smem_store.data();
-  smem += (16 - (reinterpret_cast<uintptr_t>(smem) & 15)) & 15;
+  smem += (128 - (reinterpret_cast<uintptr_t>(smem) & 127)) & 127;
   constexpr int NR = K::NRED > 0 ? K::NRED : 1;
   for (int bz = 0; bz < gz; ++bz) {
     double tot[NR];
@@ -35,6 +41,12 @@ int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, 
     for (int by = 0; by < gy; ++by)
       for (int bx = 0; bx < gx; ++bx) {
         int alive = 0;
+        if constexpr (has_tma<K>::value) {
+          LaunchCtx l0;
+          l0.tx = l0.ty = 0; l0.ntx = ntx; l0.nty = nty; l0.bx = bx; l0.by = by; l0.bz = bz; l0.nbx = gx; l0.nby = gy;
+          if (K::skipped(a, l0)) continue;
+          K::bar_init(a, l0, smem);
+        }
         for (int t = 0; t < nthreads; ++t) {
           LaunchCtx lc;
           lc.tx = t % ntx; lc.ty = t / ntx; lc.ntx = ntx; lc.nty = nty;
@@ -58,6 +70,22 @@ int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, 
       }
     if (K::NRED > 0 && any) K::finalize(a, bz, tot);
   }
+  return 0;
+}
+
+// TMA-staged kernels: same stepping; the "TMA unit" is a synchronous copy inside the issuing thread
+template <class K>
+int launch_tma(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem_bytes, void* stream,
+               double* partials, unsigned* counters) {
+  return launch<K>(a, gx, gy, gz, ntx, nty, smem_bytes, stream, partials, counters);
+}
+static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long long ny, long long nz, long long row_bytes,
+                      long long plane_bytes, int bx, int by) {
+  m->base = reinterpret_cast<const unsigned char*>(base);
+  m->dim[0] = nx; m->dim[1] = ny; m->dim[2] = nz;
+  m->stride_b[0] = row_bytes; m->stride_b[1] = plane_bytes;
+  m->box[0] = bx; m->box[1] = by; m->box[2] = 1;
+  m->esize = esize;
   return 0;
 }
 

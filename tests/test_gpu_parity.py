@@ -14,6 +14,8 @@ from parity_cases import (adaptive_cases, cg_fixed_count_cases, chambolle_cases,
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
+from tma_cases import run_tma_case, tma_cases
+
 pytestmark = pytest.mark.gpu
 
 
@@ -306,3 +308,15 @@ def test_single_pass_cg_predicted_rho_diagnostic(da):
     ref = oracle.split_bregman_tvd(img, mu=0.1, omega=1.0, ell=1.0, isotropic=True, max_num_iter=20,
                                    solver=oracle.CG(maxiter=10, tol=0.0))
     assert rel_l2(out, ref) <= 1e-13
+
+
+@pytest.mark.parametrize("shape,batch,tile,dtype,nit", tma_cases() + [((70, 90, 200), (), (0, 0, 0), np.float64, 8),
+                                                                         ((130, 61, 257), (), (0, 0, 0), np.float32, 8)])
+def test_tma_staged_fused_jacobi1_3d(da, shape, batch, tile, dtype, nit):
+    """KFusedJ1T on the B200: cp.async.bulk.tensor boxes + mbarrier ring against the oracle (and the march kernel's bar)."""
+    out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+    nb = max(1, int(np.prod(batch, dtype=int)))
+    assert list(info.iters) == [nit] * nb
+    np.testing.assert_allclose(info.history[:nit].reshape(-1), np.array(hist).reshape(nb, nit).T.reshape(-1),
+                               rtol=1e-9 if dtype == np.float64 else 1e-3)

@@ -1,0 +1,34 @@
+"""Cases for the TMA-staged 3-D anisotropic fused Jacobi-1 kernel (KFusedJ1T), shared by the emulator (CPU) and
+the GPU test modules: shapes around tile / chunk seams, thin and tiny volumes (every plane on a boundary), batches
+(the tensor maps address plane b * n0 + z), fp32, forced tiny tiles."""
+
+import numpy as np
+
+from golden.generate_golden import phantom
+
+
+def tma_cases():
+    f8, f4 = np.float64, np.float32
+    return [
+        # shape, batch, tile (x, y, planes per CTA), dtype, outer iterations
+        ((11, 19, 70), (), (0, 0, 0), f8, 6),
+        ((11, 19, 70), (), (8, 6, 3), f8, 6),
+        ((11, 19, 70), (), (8, 6, 3), f4, 6),
+        ((13, 33, 131), (), (16, 8, 4), f8, 5),
+        ((9, 17, 66), (2,), (8, 5, 4), f8, 5),
+        ((9, 17, 66), (3,), (0, 0, 0), f4, 5),
+        ((2, 1, 7), (), (0, 0, 0), f8, 4),
+        ((1, 3, 5), (), (0, 0, 0), f8, 3),
+        ((9, 5, 6), (), (0, 0, 2), f8, 6),
+        ((5, 16, 64), (), (0, 0, 1), f8, 4),
+        ((7, 15, 62), (), (0, 0, 0), f8, 4),
+    ]
+
+
+def run_tma_case(da, oracle, shape, batch, tile, dtype, nit):
+    img = phantom(tuple(shape) + tuple(batch), 13, dtype)
+    kw = dict(mu=0.1, omega=1.3, ell=0.9, dim=3, max_num_iter=nit, isotropic=False)
+    hist = []
+    ref = oracle.split_bregman_tvd(img, solver=oracle.Jacobi(maxiter=1), history=hist, **kw)
+    out, info = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=1), tile=tile, return_info=True, **kw)
+    return out, ref, info, hist
