@@ -2664,9 +2664,15 @@ struct KFusedJ1T {
   static constexpr int D = 3;
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 0, RH = 1, NRED = 1;
-  static constexpr int NS = 3;
+#ifndef TVDK_TMA_NS
+#define TVDK_TMA_NS 3
+#endif
+  static constexpr int NS = TVDK_TMA_NS;
   static constexpr int ZC3D = 64;
-  static constexpr int NTX3D = sizeof(T) == 4 ? 16 : 32;
+  // launch shape (profiles/r2_tma_tiles.txt, 512^3): small CTAs win -- 16 x 8 threads (fp64: 0.92 of the HBM peak vs
+  // 0.82 with 32 x 16; five CTAs of 40 KB per SM instead of one of 148 KB), 16 x 12 for fp32 (0.91 vs 0.86)
+  static constexpr int NTX3D = 16;
+  static constexpr int NTY3D = sizeof(T) == 4 ? 12 : 8;
   static constexpr bool TMA = true;
   typedef Col<T, D, LH, RH, 0, 1> C;
   struct Args {
@@ -2711,7 +2717,8 @@ struct KFusedJ1T {
 
   C c;
   Lay L;
-  int j, pstart, x0b, y0b, zb;  // march plane; first staged plane; box origin of the tile; plane offset of the problem
+  int j, x0b, y0b, zb;  // march plane; box origin of the tile; plane offset of the problem
+  int sr, kq;           // stage of plane j and how many times that stage has been used before it
   int iU, iF, iT1, iT2;         // element offsets of the thread's vector inside the stage buffers (iT0 = iR = iF)
   Vec<T> u_lo, u_c;             // u(j-1), u(j)
   Vec<T> w0_prev, up_prev, b_prev[D];
@@ -2726,14 +2733,13 @@ struct KFusedJ1T {
       mbar_init_fence();
     }
   }
-  TVDK_DEV unsigned long long* bar(unsigned char* smem, int p) const {
-    return reinterpret_cast<unsigned long long*>(smem) + (p - pstart) % NS;
-  }
-  TVDK_DEV unsigned char* stage(unsigned char* smem, int p) const { return smem + L.stage_off + ((p - pstart) % NS) * L.stage_bytes; }
+  // ring bookkeeping without divisions: plane j sits in stage `sr` and is that stage's `kq`-th use
+  TVDK_DEV unsigned long long* bar_at(unsigned char* smem, int idx) const { return reinterpret_cast<unsigned long long*>(smem) + idx; }
+  TVDK_DEV unsigned char* stage_at(unsigned char* smem, int idx) const { return smem + L.stage_off + idx * L.stage_bytes; }
   TVDK_DEV T* ring(unsigned char* smem, int slot) const { return reinterpret_cast<T*>(smem + L.ring_off + slot * L.ring_bytes); }
-  TVDK_DEV void issue(const Args& a, unsigned char* smem, int p) const {  // one thread: plane p -> its stage
-    unsigned long long* b = bar(smem, p);
-    unsigned char* s = stage(smem, p);
+  TVDK_DEV void issue(const Args& a, unsigned char* smem, int p, int idx) const {  // one thread: plane p -> stage idx
+    unsigned long long* b = bar_at(smem, idx);
+    unsigned char* s = stage_at(smem, idx);
     mbar_expect_tx(b, L.tx_bytes);
     const int z = zb + p;
     tma_load_3d(s + L.oU, &a.tm_u, x0b - V, y0b - 1, z, b);
@@ -2742,7 +2748,6 @@ struct KFusedJ1T {
     tma_load_3d(s + L.oT1, &a.tm_t1, x0b, y0b - 1, z, b);
     tma_load_3d(s + L.oT2, &a.tm_t2, x0b - V, y0b, z, b);
   }
-  TVDK_DEV void wait(unsigned char* smem, int p) const { mbar_wait(bar(smem, p), (unsigned)(((p - pstart) / NS) & 1)); }
 
   // w = ell (b - d), b of one component from its t (split_bregman_tvd.py:80-81, :142-146)
   static TVDK_DEV void bw1(T t, const Scalars<T>& sc, T& b, T& w) {
@@ -2761,22 +2766,25 @@ struct KFusedJ1T {
     x0b = xt * C::iw(lc.ntx);
     y0b = yt * C::ih(lc.nty);
     zb = c.b * a.g.n0;
-    // (no halo threads on the low side: a tile that STARTS at the boundary must take the selecting path too)
-    c.edge = c.edge || x0b == 0 || y0b == 0;
+    // (no halo threads on the low side: a tile that STARTS at the boundary must take the selecting path too; and
+    //  u+ is formed on every thread row / vector, so a tile whose last thread row / vector reaches the last image
+    //  row / column needs the edge-replicating selects as well)
+    c.edge = c.edge || x0b == 0 || y0b == 0 || x0b + lc.ntx * V >= a.g.nx || y0b + lc.nty >= a.g.ny;
     iU = (lc.ty + 1) * L.pU + (lc.tx + 1) * V;
     iF = lc.ty * L.pF + lc.tx * V;
     iT1 = (lc.ty + 1) * L.pF + lc.tx * V;
     iT2 = lc.ty * L.pT2 + (lc.tx + 1) * V;
     j = c.z0;
-    pstart = c.z0 - 1;
+    sr = 1;  // plane z0 - 1 sits in stage 0, plane z0 in stage 1, ...
+    kq = 0;
     if (leader) {
-      for (int p = pstart; p < pstart + NS && p <= c.z1 + 1; ++p) issue(a, smem, p);
+      for (int i = 0; i < NS && c.z0 - 1 + i <= c.z1 + 1; ++i) issue(a, smem, c.z0 - 1 + i, i);
     }
     // planes z0 - 1 (u below, w_0 below) and z0
-    wait(smem, pstart);
-    wait(smem, c.z0);
-    const unsigned char* sm1 = stage(smem, pstart);
-    u_c = vload(reinterpret_cast<const T*>(stage(smem, c.z0) + L.oU) + iU);
+    mbar_wait(bar_at(smem, 0), 0);
+    mbar_wait(bar_at(smem, 1), 0);
+    const unsigned char* sm1 = stage_at(smem, 0);
+    u_c = vload(reinterpret_cast<const T*>(stage_at(smem, 1) + L.oU) + iU);
     u_lo = u_c;
     w0_prev = vsplat<T>((T)0);
     if (c.has_zlo(a.g, j)) {
@@ -2799,18 +2807,20 @@ struct KFusedJ1T {
   TVDK_DEV void step(const Args& a, unsigned char* smem) {
     const Scalars<T>& sc = a.k.sc;
     const int slot = (j - c.z0) & 1;
-    wait(smem, j + 1);  // (every issued plane is waited for, also when its data ends up unused)
+    const bool wrap = sr + 1 == NS;
+    const int sr1 = wrap ? 0 : sr + 1;  // stage of plane j + 1
+    mbar_wait(bar_at(smem, sr1), (unsigned)((kq + (wrap ? 1 : 0)) & 1));  // (every issued plane is waited for, also when unused)
     const bool have_row = (j < c.z1) || c.plane_ok(a.g, j);
     Vec<T> up = vsplat<T>((T)0), u_hi = u_c;
     Vec<T> b_cur[D], w0_cur = w0_prev;
 #pragma unroll
     for (int d = 0; d < D; ++d) b_cur[d] = b_prev[d];
     if (have_row) {
-      const unsigned char* sj = stage(smem, j);
+      const unsigned char* sj = stage_at(smem, sr);
       const T* U = reinterpret_cast<const T*>(sj + L.oU);
       const T* T1 = reinterpret_cast<const T*>(sj + L.oT1);
       const T* T2 = reinterpret_cast<const T*>(sj + L.oT2);
-      if (c.has_zhi(a.g, j)) u_hi = vload(reinterpret_cast<const T*>(stage(smem, j + 1) + L.oU) + iU);
+      if (c.has_zhi(a.g, j)) u_hi = vload(reinterpret_cast<const T*>(stage_at(smem, sr1) + L.oU) + iU);
       const Vec<T> f = vload(reinterpret_cast<const T*>(sj + L.oF) + iF);
       const Vec<T> t0 = vload(reinterpret_cast<const T*>(sj + L.oT0) + iF);
       const Vec<T> t1 = vload(T1 + iT1), t1m = vload(T1 + iT1 - L.pF);
@@ -2892,8 +2902,12 @@ struct KFusedJ1T {
   // after the barrier: stage(j) (and, on the first step, the stage of plane z0 - 1) is free again
   TVDK_DEV void post(const Args& a, unsigned char* smem) {
     if (leader) {
-      if (j == c.z0 && pstart + NS <= c.z1 + 1) issue(a, smem, pstart + NS);
-      if (j + NS <= c.z1 + 1) issue(a, smem, j + NS);
+      if (j == c.z0 && j - 1 + NS <= c.z1 + 1) issue(a, smem, j - 1 + NS, 0);
+      if (j + NS <= c.z1 + 1) issue(a, smem, j + NS, sr);
+    }
+    if (++sr == NS) {
+      sr = 0;
+      ++kq;
     }
     c.cur += c.s0b;
     ++j;

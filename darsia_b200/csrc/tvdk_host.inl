@@ -122,6 +122,14 @@ struct KernelNtx3<K, std::void_t<decltype(K::NTX3D)>> {
   static constexpr int value = K::NTX3D;
 };
 template <class K, typename = void>
+struct KernelNty3 {
+  static int get(bool big_tile) { return big_tile ? 16 : 8; }
+};
+template <class K>
+struct KernelNty3<K, std::void_t<decltype(K::NTY3D)>> {
+  static int get(bool) { return K::NTY3D; }
+};
+template <class K, typename = void>
 struct KernelIsTma : std::false_type {};
 template <class K>
 struct KernelIsTma<K, std::void_t<decltype(K::TMA)>> : std::bool_constant<K::TMA> {};
@@ -232,7 +240,7 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     int ntx = tune.tile_x > 0 ? tune.tile_x : KernelNtx3<K>::value;
     ntx = std::min(ntx, round_up(need_x, 8));
     ntx = std::max(ntx, 8);
-    int nty = tune.tile_y > 0 ? tune.tile_y : (big_tile ? 16 : 8);
+    int nty = tune.tile_y > 0 ? tune.tile_y : KernelNty3<K>::get(big_tile);
     const int halo_y = K::LH + K::RH;
     nty = std::min(nty, round_up(g.ny + halo_y, 4));
     nty = std::max(nty, halo_y + 1);

@@ -22,6 +22,15 @@ def tma_cases():
         ((9, 5, 6), (), (0, 0, 2), f8, 6),
         ((5, 16, 64), (), (0, 0, 1), f8, 4),
         ((7, 15, 62), (), (0, 0, 0), f8, 4),
+        # the halo row / vector of an interior tile IS the last image row / column (ny = k * ih + 1, nx = x0 + ntx * V)
+        ((6, 31, 126), (), (0, 0, 0), f8, 4),
+        ((6, 46, 125), (), (0, 0, 0), f8, 4),
+        ((6, 31, 124), (), (0, 0, 0), f4, 4),
+        ((6, 29, 62), (), (0, 0, 0), f8, 4),
+        ((6, 22, 92), (), (0, 0, 0), f8, 4),
+        ((6, 34, 124), (), (0, 0, 0), f4, 4),
+        ((7, 16, 30), (), (8, 6, 3), f8, 4),
+        ((7, 16, 46), (), (8, 6, 3), f4, 4),
     ]
 
 
