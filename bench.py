@@ -55,6 +55,10 @@ WORKLOADS = {
                                 solver=("jacobi", 1, None), outer=50, hetero=False, slab=True),
     "cfg5_3d_slab_j1_f64": dict(shape=(2048, 2048, 512), nb=1, dtype="float64", iso=False,
                                 solver=("jacobi", 1, None), outer=50, hetero=False, slab=True),
+    # BASELINE configs[2] as specified: 512 frames, per-pixel mu / omega, sharded by frames over the ranks (strong scaling);
+    # device-resident value on sub-batches of 8 frames, e2e through the streaming pipeline (tvd_series_stream)
+    "cfg3_series512": dict(shape=(4000, 7000), nb=8, dtype="float64", iso=False, solver=("jacobi", 1, None), outer=100,
+                           hetero=True, series=512),
     "small": dict(shape=(512, 768), nb=3, dtype="float64", iso=True, solver=("cg", 10, 0.0), outer=10, hetero=False),
 }
 DEFAULT_WORKLOAD = "cfg2_2d_iso_cg10"
@@ -837,6 +841,127 @@ def run_slab_nccl(args, w, wname, rank, world, local, dev, barrier):
                       "roofline": {"frac": gbs / world / peak, "peak": peak, "per_gpu": True}}))
 
 
+def run_series(args, w, wname):
+    """BASELINE configs[2]: a time series of frames, heterogeneous (per-pixel) weight / omega, frame-sharded over the
+    ranks with no collective.  Strong scaling: the series has w["series"] frames in total, every rank takes its block.
+    value: device-resident (the rank's frames solved in resident sub-batches of nb frames); e2e: host frames in, host
+    frames out through the three-stage streaming pipeline (pageable frames, pinned rings, copies overlapped)."""
+    import torch
+    import torch.distributed as dist
+
+    import darsia_b200 as da
+    from darsia_b200 import _cabi
+    from darsia_b200.engine import Engine, SolverSpec
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local])
+        torch.cuda.synchronize(dev)
+
+    def reduce_max(x):
+        tx = torch.tensor([x], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tx, op=dist.ReduceOp.MAX)
+        return float(tx.item())
+
+    T = int(args.frames or w["series"])
+    s, e = da.frame_range(T, rank, world)
+    mine = e - s
+    B = w["nb"]
+    shape = tuple(w["shape"])
+    kind, m, tol = w["solver"]
+    spec = SolverSpec(kind=_cabi.TVDK_SOLVER_JACOBI, maxiter=m, tol=tol)
+    np_dtype = np.dtype(w["dtype"])
+    outer = w["outer"]
+    fvox = int(np.prod(shape))
+    mu_h, om_h = hetero_maps(w, seed=3)
+    pool = [phantom_np(shape, 3 + 100 * rank + k, w["dtype"]) for k in range(4)]  # distinct pageable host frames, cycled
+    eng = Engine(shape, nb=B, dtype=np_dtype, device=dev)
+    mu_f, om_f = eng.coef(mu_h)[1], eng.coef(om_h)[1]
+    f = eng.upload(np.stack([pool[k % 4] for k in range(B)], axis=-1))
+    u, t = eng.empty_fields(1), eng.empty_fields(2)
+    nsub = (mine + B - 1) // B
+
+    def device_pass():
+        for _ in range(nsub):
+            u.copy_(f)
+            t.zero_()
+            eng.solve(f, u, t, mu_f, om_f, ELL, False, spec, outer, None, sync=False)
+
+    for _ in range(max(1, args.warmup)):
+        eng.solve(f, u.copy_(f), t.zero_(), mu_f, om_f, ELL, False, spec, outer, None, sync=False)
+    lib = _cabi.get_library()
+    lib.launch_count(1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        device_pass()
+    ev1.record()
+    barrier()
+    launches = int(lib.launch_count(1))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = reduce_max(ev0.elapsed_time(ev1)) / args.steps
+    # (every rank solved nsub full sub-batches; count the frames of the series, not the padding of the last one)
+    value = T * fvox * outer / (ms_per_step * 1e-3) / 1e6
+    W = np_dtype.itemsize
+    words = algo_words_per_voxel_iter(2, w["solver"], 2)
+    peak, peak_src = measured_peak()
+    gbs = words * W * nsub * B * fvox * outer / (ms_per_step * 1e-3) / 1e9
+    # ---- e2e: the streaming pipeline on pageable host frames ----
+    kw = dict(dim=2, batch=B, mu=mu_h, omega=om_h, ell=ELL, isotropic=False, max_num_iter=outer, solver=da.Jacobi(maxiter=1),
+              device=dev, rank=rank, world=world)
+    got = {}
+
+    def sink(k, fr):
+        if k == s:
+            got["first"] = fr.copy()
+
+    da.tvd_series_stream(lambda k: pool[k % 4], n_frames=min(T, 2 * B * world), sink=lambda k, fr: None, **kw)  # allocator warm-up
+    barrier()
+    t0 = time.perf_counter()
+    da.tvd_series_stream(lambda k: pool[k % 4], n_frames=T, sink=sink, **kw)
+    torch.cuda.synchronize(dev)
+    te = reduce_max(time.perf_counter() - t0)
+    # the streamed result of the first frame == the resident solve of the same frame
+    chk = da.split_bregman_tvd(pool[s % 4], mu=mu_h, omega=om_h, ell=ELL, dim=2, max_num_iter=outer, solver=da.Jacobi(maxiter=1),
+                               device=dev)
+    same = bool(np.array_equal(chk, got["first"]))
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {
+        "metric": "tvd_mvoxel_iter_per_s", "value": value, "unit": "Mvoxel*iter/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f64" if W == 8 else "f32", "data": "synthetic (4 distinct seeded frames per rank, cycled; per-pixel mu / omega maps)",
+        "config": dict(config_of(w, wname), frames=T, frames_per_rank=mine, sub_batch=B,
+                       sharding="contiguous blocks of frames per rank, no collective"),
+        "roofline": {"bound": "hbm", "kernel": "whole step (fused Jacobi-1 iterations with per-pixel maps)", "achieved": gbs,
+                     "peak": peak, "unit": "GB/s", "frac": gbs / peak, "traffic": None, "peak_source": peak_src,
+                     "algo_words_per_voxel_iter": words, "per_gpu": True},
+        "cpu_baseline": None,
+        "e2e": {"value": T * fvox * outer / te / 1e6, "unit": "Mvoxel*iter/s", "s_per_step": te,
+                "h2d_bytes_per_step": int(mine * fvox * W), "d2h_bytes_per_step": int(mine * fvox * W),
+                "input": "pageable ndarray frames from a generator (tvd_series_stream: pinned staging rings, H2D / solve / D2H overlapped)",
+                "matches_resident_result": same},
+        "gpu_launches": launches, "clocks": clocks,
+    }
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -848,12 +973,15 @@ def main():
     ap.add_argument("--no-slab", action="store_true", help="skip the slab-decomposed sub-record of the default workload")
     ap.add_argument("--transport", default="p2p", choices=["p2p", "nccl"], help="slab workloads: tvdk_solve_slab or the NCCL driver")
     ap.add_argument("--shape", type=int, nargs="+", default=None, help="override the workload's spatial shape")
+    ap.add_argument("--frames", type=int, default=None, help="series workloads: total number of frames (default: the workload's)")
     args = ap.parse_args()
     w = WORKLOADS[args.workload]
     if args.shape:
         w = dict(w, shape=tuple(args.shape))
     if args.impl == "reference":
         run_reference_arm(args, w, args.workload)
+    elif w.get("series"):
+        run_series(args, w, args.workload)
     elif w.get("slab"):
         run_slab(args, w, args.workload)
     else:

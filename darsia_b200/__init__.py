@@ -12,7 +12,8 @@ from .restoration.split_bregman_tvd import split_bregman_tvd  # noqa: F401
 from .restoration.tvd import TVD, tvd  # noqa: F401
 from .restoration.h1_regularization import H1_regularization  # noqa: F401
 from .engine import Engine, SolveInfo, SolverSpec  # noqa: F401
-from .series import frame_range, tvd_series  # noqa: F401
+from .series import frame_range, tvd_series, tvd_series_stream  # noqa: F401
 from .slab import slab_range, split_bregman_tvd_slab  # noqa: F401
+from .slab_p2p import SlabGroup, split_bregman_tvd_slab_p2p  # noqa: F401
 
 __version__ = "0.1.0"

@@ -78,6 +78,8 @@ class Stat(C.Structure):
         ("e_prev", C.c_double),
         ("rho_pred", C.c_double),
         ("cg_pred_dev", C.c_double),
+        ("nonfinite", C.c_int32),
+        ("pad_", C.c_int32),
     ]
 
 

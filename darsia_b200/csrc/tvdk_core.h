@@ -261,13 +261,20 @@ TVDK_DEV void finalize_fin(const Fin& f, int nred, int b, const double* tot) {
       s.jac_sel = 0;
       s.cg_stop = 0;
       if (f.history) f.history[(long long)f.iter * f.nb + b] = inc;
-      if (f.eps >= 0.0 && inc < f.eps) {
+      const bool bad = !(inc <= 1.7976931348623157e308);  // NaN or +Inf
+      if (bad) s.nonfinite = 1;
+      if ((f.eps >= 0.0 && inc < f.eps) || bad) {
         s.done = 1;
         if (f.ndone) atomic_inc(f.ndone);
       }
     } break;
     case FIN_OUTER2: {  // two iterations of :161 (no eps: the host only fuses pairs when eps is None)
       const double i1 = sqrt(tot[0]) / s.nrm_f, i2 = sqrt(tot[1]) / s.nrm_f;
+      if (!(i1 <= 1.7976931348623157e308) || !(i2 <= 1.7976931348623157e308)) {
+        s.nonfinite = 1;
+        s.done = 1;
+        if (f.ndone) atomic_inc(f.ndone);
+      }
       s.inc = i2;
       s.iters += 2;
       s.cur_buf = f.buf_id;
@@ -1962,6 +1969,7 @@ struct KShrink {
     int use_sel;
     const T* axpy_p;   // optional: u+ = unew[0] + alpha * axpy_p (last x-update of the single-pass CG route)
     DRef axpy_alpha;
+    int cg_mode;       // the inner solver was CG: a zero right-hand side makes the iterate ZERO (scipy cg returns b)
     const T* u_old;    // pointwise
     T* u_out;          // may alias u_old (pointwise) or be nullptr
     const T* t_in;     // nullptr: explicit warm-start b in xb
@@ -1977,8 +1985,10 @@ struct KShrink {
   const T* un;
   const T* ap;
   T aalpha;
+  bool zero_up;
   Vec<T> up_c, up_hi, nx_up;
   TVDK_DEV Vec<T> load_up(long long o) const {
+    if (zero_up) return vsplat<T>((T)0);
     Vec<T> x = ldo(un, o);
     if (ap) {
       const Vec<T> pv = ldo(ap, o);
@@ -2006,6 +2016,7 @@ struct KShrink {
     red[0] = 0.0;
     un = a.unew[a.use_sel ? a.skip[lc.bz].jac_sel : 0];
     ap = (a.axpy_p && !(a.skip && a.skip[lc.bz].cg_stop)) ? a.axpy_p : nullptr;
+    zero_up = a.cg_mode && a.skip && a.skip[lc.bz].bnrm == 0.0;
     aalpha = ap ? (T)a.axpy_alpha.at(lc.bz) : (T)0;
     j = c.z0;
     const long long o = c.at(a.g, j);

@@ -600,6 +600,7 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
       memset(&a, 0, sizeof a);
       a.k = k; a.unew[0] = u0; a.unew[1] = u1; a.unew[2] = u2; a.use_sel = use_sel;
       a.axpy_p = axpy_p; a.axpy_alpha.p = &st[0].alpha; a.axpy_alpha.stride = stat_dstride;
+      a.cg_mode = fp.cg ? 1 : 0;
       a.u_old = ubuf[cur]; a.u_out = ubuf[cur];
       a.t_in = expl_now ? nullptr : tbuf[cur]; a.t_out = tbuf[cur]; a.tcs = tcs[cur];
       a.xb = xb_cur; a.xcs = xcs_cur;

@@ -337,6 +337,7 @@ static int solve_slab_impl(int nlocal, const tvdk_problem_t* const* problems, co
         a.k = r.k;
         a.unew[0] = unew(r, 0); a.unew[1] = unew(r, 1); a.unew[2] = unew(r, 2);
         a.use_sel = use_sel ? 1 : 0;
+        a.cg_mode = cg ? 1 : 0;
         a.u_old = r.ubuf[0]; a.u_out = r.ubuf[0];
         a.t_in = r.tbuf[0]; a.t_out = r.tbuf[0]; a.tcs = r.tcs[0];
         a.skip = r.st; a.fin = local_fin(r);

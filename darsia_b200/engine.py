@@ -41,6 +41,7 @@ class SolveInfo:
     energy: Optional[np.ndarray]  # (max_num_iter, nb) energies when verbose
     launched: int  # outer iterations enqueued by the host
     cg_pred_dev: Optional[np.ndarray] = None  # single-pass CG: largest relative deviation of the predicted rho
+    nonfinite: Optional[np.ndarray] = None  # a relative increment came out NaN / Inf (the problem was frozen there)
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -311,4 +312,5 @@ class Engine:
             energy=None if ehist is None else ehist.cpu().numpy().reshape(-1, self.nb),
             launched=int(launched.value),
             cg_pred_dev=np.array([r.cg_pred_dev for r in recs]),
+            nonfinite=np.array([bool(r.nonfinite) for r in recs]),
         )

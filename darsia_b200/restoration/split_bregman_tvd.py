@@ -6,7 +6,7 @@ outer loop) and brings the result back; there is no CPU fallback.
 
 Policy on the reference's quirks:
   Q2  a fresh solver state per call;  Q3  isotropic works for any dim / dtype / per-voxel mu;
-  Q5/Q6  axes beyond ``dim`` are independent problems;  Q10  integer images raise TypeError;
+  Q5/Q6  axes beyond ``dim`` are independent problems;  Q10  integer images are rescaled like ``img_as_float`` and converted back like ``convert_dtype``;
   Q11 ``verbose=0`` is silent;  Q12  non-positive ``ell`` raises ValueError.
 """
 
@@ -109,10 +109,23 @@ def split_bregman_tvd(
     if not isinstance(img, np.ndarray) and not on_device:
         raise TypeError(f"Input type {type(img)} not supported.")
     img_dtype = _np_dtype(img)
+    if img_dtype in _INT_RANGE:
+        # Integer images (what cv2 / skimage hand to darsia.tvd for a jpg): the reference converts the iterate with
+        # skimage.img_as_float (split_bregman_tvd.py:94,99) and the result back with convert_dtype (:177,
+        # utils/dtype.py:9-30).  (It also keeps using the RAW integers in its right-hand side and integer d / b
+        # arrays -- SURVEY Q10, an accident; here the whole solve runs on the rescaled image, in fp64.)
+        if return_state:
+            raise NotImplementedError("return_state with an integer image (the state is a float quantity)")
+        lo, hi = _INT_RANGE[img_dtype]
+        scaled = _int_to_float(img, lo, hi)
+        res = split_bregman_tvd(scaled, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic, verbose, solver, adaptive,
+                                precision=precision, device=device, return_info=return_info, return_state=return_state, fused=fused,
+                                tile=tile)
+        out, info = res if return_info else (res, None)
+        out = _float_to_int(out, img_dtype, lo, hi)
+        return (out, info) if return_info else out
     if img_dtype not in (np.float32, np.float64):
-        raise TypeError(
-            f"float32/float64 images only, got {img.dtype} (the reference mixes rescaled and raw integers, SURVEY Q10)"
-        )
+        raise TypeError(f"float32/float64 (or uint8 / uint16) images only, got {img.dtype}")
     if on_device:
         if device is None and img.is_cuda:
             device = img.device
@@ -205,8 +218,17 @@ def split_bregman_tvd(
         x0_db=x0_db, verbose_every=verbose_every, record_history=return_info, fused=fused,
         full_shape=shape, adaptive_mask=adaptive_mask,
     )
+    if info is not None and info.nonfinite is not None and bool(np.any(info.nonfinite)):
+        import warnings
+
+        bad = [int(i) for i in np.nonzero(info.nonfinite)[0]]
+        warnings.warn(f"split_bregman_tvd: the relative increment became NaN/Inf for problem(s) {bad[:8]} "
+                      f"(non-finite input or coefficients); they were stopped at that iteration", RuntimeWarning)
     if verbose_every:
-        _print_verbose(info, verbose_every)
+        e_img = None
+        if x0 is not None:  # the reference prints _functional(img), not the energy of the warm start (:103-104)
+            e_img = _energy_of(eng, f, mu, omega, shape)
+        _print_verbose(info, verbose_every, e_img)
     if timing:
         t_solve = time.perf_counter()
     # convert_dtype, split_bregman_tvd.py:177
@@ -314,6 +336,34 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
     return out, info
 
 
+# skimage.util.dtype ranges: unsigned integers map [0, max] <-> [0, 1], signed ones [min, max] <-> [-1, 1]
+# (the two integer types convert_dtype can return, utils/dtype.py:20-23)
+_INT_RANGE = {np.dtype(np.uint8): (0, 255), np.dtype(np.uint16): (0, 65535)}
+
+
+def _int_to_float(img, lo, hi):
+    """``skimage.img_as_float`` of an integer image (fp64): ``x / max`` (unsigned), ``(x - min) * 2 / (max - min) - 1`` (signed)."""
+    if _is_tensor(img):
+        import torch
+
+        x = img.to(torch.float64)
+        return x / hi if lo == 0 else (x - lo) * (2.0 / (hi - lo)) - 1.0
+    x = img.astype(np.float64)
+    return x / hi if lo == 0 else (x - lo) * (2.0 / (hi - lo)) - 1.0
+
+
+def _float_to_int(x, dtype, lo, hi):
+    """``convert_dtype`` (utils/dtype.py:9-30 -> ``skimage.img_as_ubyte`` / ``img_as_uint``): scale, round to nearest, clip."""
+    if _is_tensor(x):
+        import torch
+
+        y = x * hi if lo == 0 else (x + 1.0) * ((hi - lo) / 2.0) + lo
+        tdt = {np.dtype(np.uint8): torch.uint8, np.dtype(np.uint16): torch.uint16}[np.dtype(dtype)]
+        return torch.clamp(torch.round(y), lo, hi).to(tdt)
+    y = x * hi if lo == 0 else (x + 1.0) * ((hi - lo) / 2.0) + lo
+    return np.clip(np.rint(y), lo, hi).astype(dtype)
+
+
 def _is_tensor(x) -> bool:
     import torch
 
@@ -324,7 +374,8 @@ def _np_dtype(x) -> np.dtype:
     if _is_tensor(x):
         import torch
 
-        return {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64)}.get(x.dtype, np.dtype(object))
+        return {torch.float32: np.dtype(np.float32), torch.float64: np.dtype(np.float64), torch.uint8: np.dtype(np.uint8),
+                torch.uint16: np.dtype(np.uint16)}.get(x.dtype, np.dtype(object))
     return np.dtype(x.dtype)
 
 
@@ -351,7 +402,27 @@ def _sync(eng: Engine) -> None:
         torch.cuda.synchronize(eng.device)
 
 
-def _print_verbose(info: SolveInfo, every: int) -> None:
+def _energy_of(eng: Engine, field, mu, omega, full_shape):
+    """``_functional`` (split_bregman_tvd.py:71-77) of a resident field, per problem (``tvdk_energy``)."""
+    import ctypes as C
+
+    import torch
+
+    from .._runtime import device_guard
+
+    muc, k1 = eng.coef(mu, full_shape, "mu")
+    omc, k2 = eng.coef(omega, full_shape, "omega")
+    ws = eng.op_workspace()
+    out = torch.zeros(2 * eng.nb, dtype=torch.float64, device=eng.device)
+    with device_guard(eng.device):
+        rc = eng.lib.energy(C.byref(eng.geom), C.byref(muc), C.byref(omc), field.data_ptr(), field.data_ptr(), out.data_ptr(),
+                            ws.data_ptr(), ws.numel(), eng.stream())
+    eng.lib.check(rc, "tvdk_energy")
+    tot = out.cpu().numpy().reshape(eng.nb, 2)
+    return 0.5 * tot[:, 0] + tot[:, 1]
+
+
+def _print_verbose(info: SolveInfo, every: int, e_img=None) -> None:
     """The reference's progress lines (split_bregman_tvd.py:103-104, 162-167), printed after
     the device-resident loop has finished (one line per problem when batched)."""
     hist, en = info.history, info.energy
@@ -361,7 +432,7 @@ def _print_verbose(info: SolveInfo, every: int) -> None:
     for b in range(nb):
         tag = f"[problem {b}] " if nb > 1 else ""
         if info.iters[b] > 0 or hist.shape[0] > 0:
-            print(f"{tag}The energy functional starts at {en[0, b]}")
+            print(f"{tag}The energy functional starts at {en[0, b] if e_img is None else e_img[b]}")
         for it in range(int(info.iters[b])):
             if it % every == 0:
                 print(

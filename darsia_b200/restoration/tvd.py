@@ -1,10 +1,12 @@
-"""``darsia.TVD`` / ``darsia.tvd`` with the heterogeneous split-Bregman method on the GPU.
+"""``darsia.TVD`` / ``darsia.tvd`` on the GPU (reference: ``restoration/tvd.py:15-163``).
 
-Reference: ``restoration/tvd.py:15-163``.  Only ``method="heterogeneous bregman"`` is
-implemented here (the path BASELINE.json names); the skimage-backed methods ("chambolle",
-"anisotropic bregman", "isotropic bregman", ``tvd.py:77-101``) are a different algorithm and
-stay with DarSIA/scikit-image -- asking for them raises ``NotImplementedError`` rather than
-silently running something else.
+``method="heterogeneous bregman"`` (``tvd.py:103-112``) is the path BASELINE.json names: ``split_bregman_tvd``, pinned
+against the reference's own outputs.  ``method="chambolle"`` (``tvd.py:77-83``, the default of ``tvd()``) runs a GPU
+restatement of ``skimage.restoration.denoise_tv_chambolle`` whose PARITY IS UNPINNED -- scikit-image is a third-party
+dependency that is neither vendored by the reference nor installed in the build image, so there is no output of the
+real function to pin it against; the first use warns about it once.  ``"anisotropic bregman"`` / ``"isotropic bregman"``
+(``tvd.py:85-101``) are scikit-image's Cython Gauss-Seidel scheme and raise ``NotImplementedError`` rather than silently
+running something else.
 """
 
 from __future__ import annotations
@@ -15,6 +17,9 @@ import numpy as np
 
 from ..image import is_image_like
 from .split_bregman_tvd import split_bregman_tvd
+
+
+_CHAMBOLLE_WARNED = False
 
 
 def _is_device_tensor(x) -> bool:
@@ -65,6 +70,14 @@ class TVD:
             # third-party algorithm restated without scikit-image at hand: parity unpinned (chambolle.py)
             from .chambolle import denoise_tv_chambolle
 
+            global _CHAMBOLLE_WARNED
+            if not _CHAMBOLLE_WARNED:
+                import warnings
+
+                warnings.warn("darsia_b200: method='chambolle' is a restatement of skimage.restoration.denoise_tv_chambolle whose "
+                              "parity is unpinned (scikit-image is not available to compare with); use method='heterogeneous bregman' "
+                              "for the reference-pinned path", UserWarning, stacklevel=3)
+                _CHAMBOLLE_WARNED = True
             return denoise_tv_chambolle(img, weight=self.weight, max_num_iter=self.max_num_iter, eps=self.eps)
         elif self.method in ("anisotropic bregman", "isotropic bregman"):
             raise NotImplementedError(

@@ -301,7 +301,10 @@ class SlabSolver:
                     rho.copy_(sums[1:2])
                     stop = False
                     if spec.tol > 0.0 or self.iters == 0:  # host check only when a tolerance can fire
-                        stop = bool((bnrm == 0).item()) or bool((torch.sqrt(rho) < atol).item())
+                        zero_rhs = bool((bnrm == 0).item())
+                        if zero_rhs:  # scipy cg returns b (all zeros) for a zero right-hand side
+                            x.zero_()
+                        stop = zero_rhs or bool((torch.sqrt(rho) < atol).item())
                     updated = False
                     for i in range(spec.maxiter):
                         if stop:

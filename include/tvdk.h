@@ -94,6 +94,10 @@ typedef struct tvdk_stat {
   /* single-pass CG (K7): the predicted rho of the next iteration, and the largest relative deviation
    * |rho_predicted - rho_summed| / rho_summed seen during the solve (diagnostic: ~1e-15 on well-conditioned systems) */
   double rho_pred, cg_pred_dev;
+  /* 1 once a relative increment came out NaN / Inf (the reference would silently carry it on); the problem is
+   * marked done so that the remaining iterations leave the last finite-input state alone */
+  int32_t nonfinite;
+  int32_t pad_;
 } tvdk_stat_t;
 
 /* One call of darsia.split_bregman_tvd (restoration/split_bregman_tvd.py:14-27). */

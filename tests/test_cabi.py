@@ -39,7 +39,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     # sizes the C side computes with sizeof(tvdk_stat_t)/sizeof(double|int)
-    assert ctypes.sizeof(_cabi.Stat) == 12 * 8 + 8 * 4 + 4 * 8
+    assert ctypes.sizeof(_cabi.Stat) == 12 * 8 + 8 * 4 + 4 * 8 + 2 * 4  # (+ nonfinite, pad)
+    assert ctypes.sizeof(_cabi.SlabComm) == 8 + 16 * 4 + 16 * 8 + 8 + 8 + 8
     assert ctypes.sizeof(_cabi.Geom) == 11 * 4
     assert ctypes.sizeof(_cabi.Coef) == 24
 

@@ -320,3 +320,34 @@ def test_tma_staged_fused_jacobi1_3d(da, shape, batch, tile, dtype, nit):
     assert list(info.iters) == [nit] * nb
     np.testing.assert_allclose(info.history[:nit].reshape(-1), np.array(hist).reshape(nb, nit).T.reshape(-1),
                                rtol=1e-9 if dtype == np.float64 else 1e-3)
+
+
+def test_series_streaming_pipeline(da):
+    """tvd_series_stream: frames from a callable / an iterator through the staging rings == frame-by-frame oracle; partial
+    last sub-batch, colour channels, shared per-pixel maps, sink delivery in order."""
+    from golden.generate_golden import coeff_field, phantom
+
+    shape = (180, 250)
+    frames = [phantom(shape, 40 + k) for k in range(7)]
+    mu = 0.1 * coeff_field(shape, 5, 0.5, 1.0, 0.1)
+    om = coeff_field(shape, 6, 0.5, 2.0)
+    got, rng = da.tvd_series_stream(lambda k: frames[k], n_frames=7, dim=2, batch=3, mu=mu, omega=om, ell=1.0, max_num_iter=6,
+                                    solver=da.Jacobi(maxiter=1))
+    assert rng == (0, 7) and len(got) == 7
+    for k in range(7):
+        ref = oracle.split_bregman_tvd(frames[k], mu=mu, omega=om, ell=1.0, dim=2, max_num_iter=6, solver=oracle.Jacobi(maxiter=1))
+        assert rel_l2(got[k], ref) <= 1e-13
+    # this rank's block of a sharded series
+    got1, rng1 = da.tvd_series_stream(lambda k: frames[k], n_frames=7, dim=2, batch=2, rank=1, world=2, mu=mu, omega=om, ell=1.0,
+                                      max_num_iter=6, solver=da.Jacobi(maxiter=1))
+    assert rng1 == da.frame_range(7, 1, 2) and all(np.array_equal(a, b) for a, b in zip(got1, got[rng1[0]:rng1[1]]))
+    rgb = [phantom(shape + (3,), 50 + k) for k in range(4)]
+    seen = []
+    da.tvd_series_stream(iter(rgb), dim=2, batch=2, sink=lambda k, f: seen.append((k, f.copy())), mu=0.1, ell=1.0, isotropic=True,
+                         max_num_iter=4, solver=da.CG(maxiter=3, tol=0.0))
+    assert [k for k, _ in seen] == [0, 1, 2, 3]
+    for k, f in seen:
+        ref = oracle.split_bregman_tvd(rgb[k], mu=0.1, ell=1.0, dim=2, isotropic=True, max_num_iter=4, solver=oracle.CG(maxiter=3, tol=0.0))
+        assert rel_l2(f, ref) <= 1e-13
+    with pytest.raises(AssertionError):
+        da.tvd_series_stream(iter([frames[0], np.zeros((5, 5))]), dim=2, mu=0.1, ell=1.0, max_num_iter=1)

@@ -71,7 +71,7 @@ def test_errors(img):
     with pytest.raises(NotImplementedError):
         da.tvd(img, method="anisotropic bregman")  # scikit-image's sequential Gauss-Seidel scheme
     with pytest.raises(TypeError):
-        da.split_bregman_tvd((img * 255).astype(np.uint8))
+        da.split_bregman_tvd((img * 255).astype(np.int32))  # convert_dtype returns uint8 / uint16 / floats only
     with pytest.raises(TypeError):
         da.split_bregman_tvd(img, solver=da.CG(maxiter=3))  # tol=None is not a tolerance (Q4)
     with pytest.raises(NotImplementedError):
@@ -140,3 +140,33 @@ def test_reference_example_script_runs(tmp_path, capsys):
         sys.argv = argv
     out = capsys.readouterr().out
     assert "TVD" in out and "H1" in out
+
+
+@pytest.mark.parametrize("dtype,top", [(np.uint8, 255), (np.uint16, 65535)])
+def test_integer_images_follow_img_as_float_and_convert_dtype(img, dtype, top):
+    """uint8 / uint16 in (what tvd(jpg_array) gets): skimage.img_as_float on the way in (split_bregman_tvd.py:94,99),
+    convert_dtype = img_as_ubyte / img_as_uint on the way out (:177, utils/dtype.py:9-30); the solve runs in fp64."""
+    raw = np.rint(img * top).astype(dtype)
+    out = da.split_bregman_tvd(raw, mu=0.1, ell=1.0, max_num_iter=6)
+    assert out.dtype == dtype and out.shape == raw.shape
+    ref = oracle.split_bregman_tvd(raw.astype(np.float64) / top, mu=0.1, ell=1.0, max_num_iter=6)
+    want = np.clip(np.rint(ref * top), 0, top).astype(dtype)
+    assert int(np.max(np.abs(out.astype(np.int64) - want.astype(np.int64)))) <= 1  # a rounding tie at most
+    assert np.mean(out != want) < 1e-3
+    out2 = da.tvd(raw, method="heterogeneous bregman", weight=0.1, max_num_iter=3, eps=None)
+    assert out2.dtype == dtype
+
+
+def test_zero_image_with_warm_start_and_cg_returns_zero(img):
+    """scipy cg returns b when ||b|| = 0 (cg.py:50-56 -> scipy): with a zero image every right-hand side is zero, so the
+    iterate becomes zero whatever the warm start was."""
+    z = np.zeros_like(img)
+    x0 = (img.copy(), np.zeros(img.shape + (2,)), np.zeros(img.shape + (2,)))
+    ref = oracle.split_bregman_tvd(z, mu=0.1, ell=1.0, max_num_iter=2, solver=oracle.CG(maxiter=3, tol=0.0), x0=x0)
+    with np.errstate(all="ignore"):
+        import warnings
+
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            out = da.split_bregman_tvd(z, mu=0.1, ell=1.0, max_num_iter=2, solver=da.CG(maxiter=3, tol=0.0), x0=x0)
+    assert np.array_equal(ref, np.zeros_like(ref)) and np.array_equal(out, ref)
