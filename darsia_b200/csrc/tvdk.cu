@@ -10,6 +10,16 @@
 
 #include "tvdk_core.h"
 
+// NVTX ranges around the solves (header-only NVTX3: a no-op unless a profiler is attached)
+#include <nvtx3/nvToolsExt.h>
+namespace tvdk {
+struct NvtxRange {
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace tvdk
+#define TVDK_RANGE(name) ::tvdk::NvtxRange tvdk_nvtx_range_(name)
+
 namespace tvdk {
 
 constexpr int kMaxThreads = 512;
@@ -40,6 +50,13 @@ __device__ __forceinline__ void block_sum(double (&val)[NRED], double (*wsum)[NR
   __syncthreads();
 }
 
+// Which axis-0 chunk this thread block works on.  Blocks are dispatched in ascending blockIdx order; with g.rev the
+// chunks are taken from the far end first, so that a launch starts on the planes its predecessor wrote LAST -- for
+// images of a few L2 sizes (BASELINE config 1: 7 fields x 45 MB vs 126 MB of L2) those are still resident.
+__device__ __forceinline__ int chunk_index(const Geom& g) {
+  return g.rev ? (int)(gridDim.y - 1 - blockIdx.y) : (int)blockIdx.y;
+}
+
 template <class K, typename = void>
 struct has_unroll2 : std::false_type {};
 template <class K>
@@ -59,7 +76,7 @@ __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel(const typen
   extern __shared__ __align__(16) unsigned char smem[];
   LaunchCtx lc;
   lc.tx = threadIdx.x; lc.ty = threadIdx.y; lc.ntx = blockDim.x; lc.nty = blockDim.y;
-  lc.bx = blockIdx.x; lc.by = blockIdx.y; lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
+  lc.bx = blockIdx.x; lc.by = chunk_index(a.g); lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
   K k;
   if (!k.init(a, lc, smem)) return;  // block-uniform (whole problems are skipped)
   if constexpr (has_unroll2<K>::value) {
@@ -87,7 +104,7 @@ __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel(const typen
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y;
     const unsigned nblk = gridDim.x * gridDim.y;
-    const unsigned blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned blk = lc.by * gridDim.x + blockIdx.x;  // (logical chunk: the order of the sums does not depend on g.rev)
     const int b = blockIdx.z;
     double v[NR];
 #pragma unroll
@@ -142,7 +159,7 @@ __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel_tma(const _
   extern __shared__ __align__(128) unsigned char smem_tma[];
   LaunchCtx lc;
   lc.tx = threadIdx.x; lc.ty = threadIdx.y; lc.ntx = blockDim.x; lc.nty = blockDim.y;
-  lc.bx = blockIdx.x; lc.by = blockIdx.y; lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
+  lc.bx = blockIdx.x; lc.by = chunk_index(a.g); lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
   if (K::skipped(a, lc)) return;  // block-uniform (whole problems are skipped)
   K::bar_init(a, lc, smem_tma);
   __syncthreads();
@@ -160,7 +177,7 @@ __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel_tma(const _
     const int tid = threadIdx.y * blockDim.x + threadIdx.x;
     const int nthreads = blockDim.x * blockDim.y;
     const unsigned nblk = gridDim.x * gridDim.y;
-    const unsigned blk = blockIdx.y * gridDim.x + blockIdx.x;
+    const unsigned blk = lc.by * gridDim.x + blockIdx.x;  // (logical chunk: the order of the sums does not depend on g.rev)
     const int b = blockIdx.z;
     double v[NR];
 #pragma unroll

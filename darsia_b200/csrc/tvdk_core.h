@@ -162,6 +162,7 @@ struct Geom {
   int xtiles, ytiles;  // in-plane tiling (depends on the kernel's halo widths)
   int pf;              // L2 prefetch distance in planes (0 = off)
   int pfsub;           // 1: one thread per 128-byte line issues the prefetch, 0: every thread
+  int rev;             // 1: thread blocks take the axis-0 chunks in DESCENDING order (see tvdk_host.inl: run)
 };
 
 template <typename T>

@@ -159,6 +159,7 @@ static Geom make_geom(const tvdk_geom_t& g) {
   r.xtiles = r.ytiles = 1;
   r.pf = 0;
   r.pfsub = prefetch_sub();
+  r.rev = 0;
   return r;
 }
 
@@ -210,6 +211,21 @@ struct LaunchCfg {
 };
 
 static thread_local Tune g_tune = {0, 0, 0};
+// Inside a solve consecutive march launches alternate the direction in which their thread blocks walk the axis-0 chunks
+// (Geom::rev): every kernel reads what its predecessor wrote, and starts where that one ended -- on lines still in L2.
+// TVDK_ALTERNATE=0 switches it off (A/B runs).  The results do not depend on it (same per-voxel arithmetic, reductions
+// summed by logical chunk index).
+static thread_local int g_alternate = 0;  // 0: off ; 1 / 2: next launch ascending / descending
+static bool alternate_enabled() {
+  static const int v = env_int("TVDK_ALTERNATE", 1);
+  return v != 0;
+}
+static int next_direction() {
+  if (!g_alternate) return 0;
+  const int rev = g_alternate == 2 ? 1 : 0;
+  g_alternate = 3 - g_alternate;
+  return rev;
+}
 
 
 static Tune merge_tune(int tx, int ty, int zc) {
@@ -344,6 +360,7 @@ static int run(typename K::Args& a, const Geom& g, const Tune& tune, bool big_ti
                void* stream) {
   LaunchCfg L = plan_launch<K, T, D>(g, tune, big_tile);
   a.g = L.g;
+  a.g.rev = next_direction();
   a.g.pf = prefetch_override() >= 0 ? prefetch_override() : KernelPf<K>::get(D);
   if (K::NRED > 0 && (size_t)L.gx * L.gy * L.gz * K::NRED > sc.partial_cap)
     return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
@@ -375,6 +392,7 @@ static int run_fj1_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const
   typename K::Args a;
   memset(&a, 0, sizeof a);
   a.g = L.g;
+  a.g.rev = next_direction();
   a.k = k;
   a.u_out = u_out;
   a.t_out = t_out;
@@ -984,7 +1002,10 @@ int tvdk_solve(const tvdk_problem_t* p, void* stream, int* iters_launched) {
   if (p->solver_kind != TVDK_SOLVER_JACOBI && p->solver_kind != TVDK_SOLVER_CG)
     return fail(TVDK_ERR_UNSUPPORTED, "unknown solver kind %d (Jacobi and CG only)", p->solver_kind);
   int rc = 0;
+  TVDK_RANGE("tvdk_solve");
+  g_alternate = alternate_enabled() ? 1 : 0;
   TVDK_DISPATCH(p->geom, rc = (solve_impl<T, D>(p, stream, iters_launched)));
+  g_alternate = 0;
   return rc;
 }
 
@@ -1565,6 +1586,7 @@ int tvdk_chambolle(const tvdk_chambolle_t* c, void* stream, int* iters_launched)
   if (c->geom.z_begin != 0 || c->geom.z_end != c->geom.n[0] || c->geom.g0_off != 0 || c->geom.g0_n != c->geom.n[0])
     return fail(TVDK_ERR_INVALID, "tvdk_chambolle works on whole images");
   int rc = 0;
+  TVDK_RANGE("tvdk_chambolle");
   TVDK_DISPATCH(c->geom, rc = (chambolle_impl<T, D>(c, stream, iters_launched)));
   return rc;
 }

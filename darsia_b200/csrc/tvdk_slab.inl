@@ -173,11 +173,29 @@ static int comm_step(std::vector<SlabRank<T>>& R, const std::vector<std::vector<
 
 enum { SKIP_DONE = 1, SKIP_CG = 2, SKIP_JAC = 4 };
 
+// The workspace layout must not depend on the rank (peers address each other's fields by arena offset): size the
+// scratch for the LARGEST slab -- every rank's array has GL + max nown + GH planes.
+static Geom capacity_geom(Geom g) {
+  g.z_begin = TVDK_SLAB_GL;
+  g.z_end = g.n0 - TVDK_SLAB_GH;
+  g.zchunk = g.z_end - g.z_begin;
+  return g;
+}
+// ... and for the launch shape with the MOST thread blocks any rank can get (the planner picks 8..64 planes per block
+// depending on how many planes a rank owns; 8 is its minimum), so that every rank carves the same scratch
+template <typename T, int D>
+static size_t slab_partial_capacity(const Geom& g, const Tune& tune) {
+  const Geom cg = capacity_geom(g);
+  Tune fine = tune;
+  if (fine.zchunk == 0) fine.zchunk = 8;
+  return std::max(partial_capacity<T, D>(cg, tune), partial_capacity<T, D>(cg, fine));
+}
+
 template <typename T, int D>
 static size_t slab_workspace_bytes_impl(const tvdk_problem_t* p) {
-  Geom g = make_geom(p->geom);
+  Geom g = capacity_geom(make_geom(p->geom));
   Tune tune = merge_tune(p->tile_x, p->tile_y, p->zchunk);
-  const size_t cap = partial_capacity<T, D>(g, tune);
+  const size_t cap = slab_partial_capacity<T, D>(g, tune);
   const bool cg = p->solver_kind == TVDK_SOLVER_CG;
   const bool fusedj1 = !cg && p->solver_maxiter == 1 && p->solver_tol < 0.0;
   const int n_fields = fusedj1 ? 1 + D : (cg ? 4 : 3);
@@ -210,7 +228,7 @@ static int solve_slab_impl(int nlocal, const tvdk_problem_t* const* problems, co
     r.stream = streams ? streams[i] : nullptr;
     r.device = devices ? devices[i] : -1;
     r.g = make_geom(p->geom);
-    const size_t cap = partial_capacity<T, D>(r.g, tune);
+    const size_t cap = slab_partial_capacity<T, D>(r.g, tune);
     r.sc = carve_scratch(p->workspace, cap, r.g.nb);
     r.hdr = reinterpret_cast<SlabHeader*>(comms[i]->arena[comms[i]->rank]);
     r.k = make_coefs<T>(&p->mu, &p->omega, &p->ell, D);
@@ -546,6 +564,8 @@ int tvdk_solve_slab(int nlocal, const tvdk_problem_t* const* problems, const tvd
     if (problems[i]->max_num_iter < 0) return fail(TVDK_ERR_INVALID, "max_num_iter must be >= 0");
   }
   int rc = 0;
+  TVDK_RANGE("tvdk_solve_slab");
+  g_alternate = 0;  // (several ranks share this thread's toggle: every rank must see the same direction per launch)
   TVDK_DISPATCH(problems[0]->geom, rc = (solve_slab_impl<T, D>(nlocal, problems, comms, streams, devices, iters_launched)));
   return rc;
 }

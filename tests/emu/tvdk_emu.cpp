@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "../../darsia_b200/csrc/tvdk_core.h"
+#define TVDK_RANGE(name) (void)0
 
 namespace tvdk {
 namespace backend {
@@ -50,7 +51,7 @@ int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, 
         for (int t = 0; t < nthreads; ++t) {
           LaunchCtx lc;
           lc.tx = t % ntx; lc.ty = t / ntx; lc.ntx = ntx; lc.nty = nty;
-          lc.bx = bx; lc.by = by; lc.bz = bz; lc.nbx = gx; lc.nby = gy;
+          lc.bx = bx; lc.by = a.g.rev ? gy - 1 - by : by; lc.bz = bz; lc.nbx = gx; lc.nby = gy;
           alive += th[t].init(a, lc, smem) ? 1 : 0;
         }
         if (alive == 0) continue;

@@ -46,6 +46,9 @@ CASES = [
     (5, (27, 6, 12), "float64", True, "cg4", 3, None, False),
     (4, (23, 6, 12), "float64", False, "j1", 4, None, True),
     (1, (9, 7, 12), "float64", True, "cg4", 3, None, False),
+    # uneven slabs whose launch shapes differ (49 / 48 planes): the workspace layout must still be rank-independent
+    (2, (97, 6, 10), "float64", False, "j1", 3, None, False),
+    (3, (100, 5, 8), "float64", True, "cg4", 2, None, False),
 ]
 
 
