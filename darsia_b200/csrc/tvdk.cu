@@ -165,6 +165,7 @@ __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel_tma(const _
   __syncthreads();
   K k;
   k.init(a, lc, smem_tma);
+  if constexpr (K::SYNC_AFTER_INIT) __syncthreads();  // (what init published in shared memory is read by the first step)
   while (k.more()) {
     k.pre(a, smem_tma);
     __syncthreads();

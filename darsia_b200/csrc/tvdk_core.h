@@ -546,14 +546,20 @@ TVDK_DEV Vec<T> syp(const T* row, const C& c) {
 //   anisotropic: d = sign(t) max(|t| - kappa, 0); b = t - d   (split_bregman_tvd.py:80-81,142-146)
 //   isotropic:   s = sqrt(sum t^2); phi = max(s - kappa, 0)/(s + 1e-18); d = t phi; b = t (1 - phi)
 //                                                           (split_bregman_tvd.py:116-126)
+// the isotropic shrinkage factor phi = max(s - kappa, 0) / (s + 1e-18), s = |t|_2   (split_bregman_tvd.py:117-126)
+template <typename T, int D, bool ISO>
+TVDK_DEV T iso_phi_of(const T (&t)[D], T kappa) {
+  T s = t[0] * t[0];
+#pragma unroll
+  for (int a = 1; a < D; ++a) s = s + t[a] * t[a];
+  s = tsqrt(s);
+  return tdiv(tmax(s - kappa, (T)0), s + (T)1e-18);
+}
+
 template <typename T, int D, bool ISO>
 TVDK_DEV void bw_from_t(const T (&t)[D], T kappa, T ell, T (&b)[D], T (&w)[D]) {
   if (ISO) {
-    T s = t[0] * t[0];
-#pragma unroll
-    for (int a = 1; a < D; ++a) s = s + t[a] * t[a];
-    s = tsqrt(s);
-    const T phi = tdiv(tmax(s - kappa, (T)0), s + (T)1e-18);
+    const T phi = iso_phi_of<T, D, true>(t, kappa);
 #pragma unroll
     for (int a = 0; a < D; ++a) {
       const T d = t[a] * phi;
@@ -2658,31 +2664,36 @@ TVDK_DEV void tma_load_3d(void* dst, const TmaMap* m, int x, int y, int z, unsig
 #endif
 
 // ==========================================================================================
-// K1-TMA  fused outer iteration for Jacobi(maxiter=1), 3-D, ANISOTROPIC, scalar coefficients
+// K1-TMA  fused outer iteration for Jacobi(maxiter=1), 3-D, scalar coefficients
 //     (BASELINE config 5; same arithmetic as K1: split_bregman_tvd.py:84-89 rhs, jacobi.py:101-114 sweep,
-//      :142-146 shrink + Bregman update, :161 increment)
+//      :136-146 shrink + Bregman update, :161 increment)
 //   All inputs of a plane arrive as TMA boxes (tile + halo) in a ring of NS shared-memory stages, issued by
 //   one thread NS - 1 planes ahead: no halo threads for u or t, no register prefetch, no per-thread load
-//   addresses.  The anisotropic w_a = ell (b_a - d_a) is a pointwise function of t_a alone, so the values the
-//   divergence needs at y - 1 and x - 1 are re-derived from the staged t instead of being published by halo
-//   threads: the only halo left is the one row / one vector on the high side where u+ is recomputed.
-//   Per step j (one barrier):  A: u+(j) from stage(j) (+ u(j+1) from stage(j+1)) -> ring[j & 1]
+//   addresses.  The only halo threads left are the one row / one vector on the high side where u+ is recomputed.
+//   What the divergence needs of w_a = ell (b_a - d_a) at y - 1 and x - 1 is re-derived from the staged t:
+//     anisotropic: w_a is a pointwise function of t_a alone (:80-81, :142-146) -- recomputed on the spot;
+//     isotropic:   w_a = ell (t_a (1 - phi) - t_a phi) with the shrinkage factor phi of :117-126, which costs a
+//                  square root and a division: phi of plane j + 1 is formed ONE STEP AHEAD by the threads (own
+//                  voxels, plus the row y0 - 1 and the column x0 - 1 dealt out one voxel per thread) and published
+//                  in a shared ring, so the step keeps its single barrier.
+//   Per step j (one barrier):  A: [iso: phi(j+1) -> phi ring]  u+(j) from stage(j) (+ u(j+1) from stage(j+1)) -> ring[j & 1]
 //                              B: t+(j-1) from ring[(j-1) & 1] and registers, stores of plane j - 1
 //                              barrier ; one thread refills stage(j) with plane j + NS.
-//   Stage layout (elements): U (ntx+2)V x (nty+2) | F | T0 (ntx V x nty each) | T1 ntx V x (nty+1) | T2 (ntx+1)V x nty.
+//   Stage layout: U (ntx+2)V x (nty+2) | F ntx V x nty | aniso: T0 ntx V x nty, T1 ntx V x (nty+1), T2 (ntx+1)V x nty
+//                                                      | iso:   T0, T1, T2 (ntx+1)V x (nty+1) each (origin x0 - V, y0 - 1).
 // ==========================================================================================
-template <typename T>
+#ifndef TVDK_TMA_NS
+#define TVDK_TMA_NS 3
+#endif
+template <typename T, bool ISO>
 struct KFusedJ1T {
   static constexpr int D = 3;
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 0, RH = 1, NRED = 1;
-#ifndef TVDK_TMA_NS
-#define TVDK_TMA_NS 3
-#endif
   static constexpr int NS = TVDK_TMA_NS;
   static constexpr int ZC3D = 64;
-  // launch shape (profiles/r2_tma_tiles.txt, 512^3): small CTAs win -- 16 x 8 threads (fp64: 0.92 of the HBM peak vs
-  // 0.82 with 32 x 16; five CTAs of 40 KB per SM instead of one of 148 KB), 16 x 12 for fp32 (0.91 vs 0.86)
+  // launch shape (profiles/r2_tma_ab_and_tiles.txt, 512^3): small CTAs win -- 16 x 8 threads (fp64: 0.91 of the HBM peak
+  // vs 0.82 with 32 x 16; five CTAs of 40 KB per SM instead of one of 148 KB), 16 x 12 for fp32 (0.91 vs 0.86)
   static constexpr int NTX3D = 16;
   static constexpr int NTY3D = sizeof(T) == 4 ? 12 : 8;
   static constexpr bool TMA = true;
@@ -2699,29 +2710,41 @@ struct KFusedJ1T {
   };
   // shared-memory layout for a thread block of ntx x nty threads (byte offsets; every buffer 128-byte aligned)
   struct Lay {
-    int pU, pF, pT2;          // row pitches in elements (T0, T1 share pF)
+    int pU, pF, pT0, pT1, pT2;  // row pitches in elements
     int oU, oF, oT0, oT1, oT2;  // byte offsets inside one stage
-    int stage_bytes, ring_bytes, ring_off, stage_off, total;
-    unsigned tx_bytes;        // bytes one plane's five boxes deliver
+    int stage_bytes, ring_bytes, ring_off, phi_bytes, phi_off, stage_off, total;
+    unsigned tx_bytes;          // bytes one plane's five boxes deliver
   };
   static TVDK_HD int a128(int x) { return (x + 127) / 128 * 128; }
+  // box shapes (elements x rows) -- the host encodes the tensor maps with the same numbers
+  static TVDK_HD int box_w(int which, int ntx) {  // 0: U, 1: F, 2..4: T0..T2
+    return which == 0 ? (ntx + 2) * V : which == 1 ? ntx * V : ISO ? (ntx + 1) * V : (which == 4 ? (ntx + 1) * V : ntx * V);
+  }
+  static TVDK_HD int box_h(int which, int nty) {
+    return which == 0 ? nty + 2 : which == 1 ? nty : ISO ? nty + 1 : (which == 3 ? nty + 1 : nty);
+  }
   static TVDK_HD Lay layout(int ntx, int nty) {
     Lay L;
     const int W = (int)sizeof(T);
-    L.pU = (ntx + 2) * V;
-    L.pF = ntx * V;
-    L.pT2 = (ntx + 1) * V;
-    const int bU = L.pU * (nty + 2) * W, bF = L.pF * nty * W, bT1 = L.pF * (nty + 1) * W, bT2 = L.pT2 * nty * W;
+    L.pU = box_w(0, ntx);
+    L.pF = box_w(1, ntx);
+    L.pT0 = box_w(2, ntx);
+    L.pT1 = box_w(3, ntx);
+    L.pT2 = box_w(4, ntx);
+    int b[5];
+    for (int i = 0; i < 5; ++i) b[i] = box_w(i, ntx) * box_h(i, nty) * W;
     L.oU = 0;
-    L.oF = L.oU + a128(bU);
-    L.oT0 = L.oF + a128(bF);
-    L.oT1 = L.oT0 + a128(bF);
-    L.oT2 = L.oT1 + a128(bT1);
-    L.stage_bytes = L.oT2 + a128(bT2);
-    L.tx_bytes = (unsigned)(bU + bF + bF + bT1 + bT2);
+    L.oF = L.oU + a128(b[0]);
+    L.oT0 = L.oF + a128(b[1]);
+    L.oT1 = L.oT0 + a128(b[2]);
+    L.oT2 = L.oT1 + a128(b[3]);
+    L.stage_bytes = L.oT2 + a128(b[4]);
+    L.tx_bytes = (unsigned)(b[0] + b[1] + b[2] + b[3] + b[4]);
     L.ring_bytes = a128((L.pF * (nty + 1) + V) * W);  // one row + one vector of slack for the halo threads' reads
     L.ring_off = 128;                                 // [0, 128): the NS mbarriers
-    L.stage_off = L.ring_off + 2 * L.ring_bytes;
+    L.phi_bytes = ISO ? a128(L.pT0 * (nty + 1) * W) : 0;
+    L.phi_off = L.ring_off + 2 * L.ring_bytes;
+    L.stage_off = L.phi_off + 2 * L.phi_bytes;
     L.total = L.stage_off + NS * L.stage_bytes;
     return L;
   }
@@ -2731,9 +2754,11 @@ struct KFusedJ1T {
   Lay L;
   int j, x0b, y0b, zb;  // march plane; box origin of the tile; plane offset of the problem
   int sr, kq;           // stage of plane j and how many times that stage has been used before it
-  int iU, iF, iT1, iT2;         // element offsets of the thread's vector inside the stage buffers (iT0 = iR = iF)
-  Vec<T> u_lo, u_c;             // u(j-1), u(j)
+  int iU, iF, iT0, iT1, iT2;  // element offsets of the thread's vector inside the stage buffers (ring: iF)
+  int tid, nthr, txt;   // linear thread index, threads per block, tile width in elements (iso: halo phi dealing)
+  Vec<T> u_lo, u_c;     // u(j-1), u(j)
   Vec<T> w0_prev, up_prev, b_prev[D];
+  Vec<T> phi_c;         // iso: phi of the own voxels of plane j (formed one step ahead)
   bool leader;
   double red[NRED];
 
@@ -2749,6 +2774,7 @@ struct KFusedJ1T {
   TVDK_DEV unsigned long long* bar_at(unsigned char* smem, int idx) const { return reinterpret_cast<unsigned long long*>(smem) + idx; }
   TVDK_DEV unsigned char* stage_at(unsigned char* smem, int idx) const { return smem + L.stage_off + idx * L.stage_bytes; }
   TVDK_DEV T* ring(unsigned char* smem, int slot) const { return reinterpret_cast<T*>(smem + L.ring_off + slot * L.ring_bytes); }
+  TVDK_DEV T* phiring(unsigned char* smem, int slot) const { return reinterpret_cast<T*>(smem + L.phi_off + slot * L.phi_bytes); }
   TVDK_DEV void issue(const Args& a, unsigned char* smem, int p, int idx) const {  // one thread: plane p -> stage idx
     unsigned long long* b = bar_at(smem, idx);
     unsigned char* s = stage_at(smem, idx);
@@ -2756,17 +2782,53 @@ struct KFusedJ1T {
     const int z = zb + p;
     tma_load_3d(s + L.oU, &a.tm_u, x0b - V, y0b - 1, z, b);
     tma_load_3d(s + L.oF, &a.tm_f, x0b, y0b, z, b);
-    tma_load_3d(s + L.oT0, &a.tm_t0, x0b, y0b, z, b);
-    tma_load_3d(s + L.oT1, &a.tm_t1, x0b, y0b - 1, z, b);
-    tma_load_3d(s + L.oT2, &a.tm_t2, x0b - V, y0b, z, b);
+    if (ISO) {
+      tma_load_3d(s + L.oT0, &a.tm_t0, x0b - V, y0b - 1, z, b);
+      tma_load_3d(s + L.oT1, &a.tm_t1, x0b - V, y0b - 1, z, b);
+      tma_load_3d(s + L.oT2, &a.tm_t2, x0b - V, y0b - 1, z, b);
+    } else {
+      tma_load_3d(s + L.oT0, &a.tm_t0, x0b, y0b, z, b);
+      tma_load_3d(s + L.oT1, &a.tm_t1, x0b, y0b - 1, z, b);
+      tma_load_3d(s + L.oT2, &a.tm_t2, x0b - V, y0b, z, b);
+    }
   }
 
-  // w = ell (b - d), b of one component from its t (split_bregman_tvd.py:80-81, :142-146)
+  // w = ell (b - d), b of one component from its t (anisotropic: split_bregman_tvd.py:80-81, :142-146)
   static TVDK_DEV void bw1(T t, const Scalars<T>& sc, T& b, T& w) {
     T tt[1] = {t}, bb[1], ww[1];
     bw_from_t<T, 1, false>(tt, sc.kappa, sc.ell, bb, ww);
     b = bb[0];
     w = ww[0];
+  }
+  // ... and of one component given the voxel's isotropic shrinkage factor (:117-126): d = t phi, b = t (1 - phi)
+  static TVDK_DEV void bwphi(T t, T phi, const Scalars<T>& sc, T& b, T& w) {
+    const T d = t * phi;
+    b = t * ((T)1 - phi);
+    w = sc.ell * (b - d);
+  }
+  static TVDK_DEV T phi3(T t0, T t1, T t2, const Scalars<T>& sc) {
+    const T tt[3] = {t0, t1, t2};
+    return iso_phi_of<T, 3, true>(tt, sc.kappa);
+  }
+  // iso: phi of plane p (staged in stage idx) -> phi ring slot: own voxels (returned) + the dealt halo voxels
+  TVDK_DEV Vec<T> make_phi(const Args& a, unsigned char* smem, int idx, int slot) const {
+    const unsigned char* sp = stage_at(smem, idx);
+    const T* T0 = reinterpret_cast<const T*>(sp + L.oT0);
+    const T* T1 = reinterpret_cast<const T*>(sp + L.oT1);
+    const T* T2 = reinterpret_cast<const T*>(sp + L.oT2);
+    T* P = phiring(smem, slot);
+    const Vec<T> t0 = vload(T0 + iT0), t1 = vload(T1 + iT0), t2 = vload(T2 + iT0);
+    Vec<T> ph;
+#pragma unroll
+    for (int v = 0; v < V; ++v) ph.v[v] = phi3(t0.v[v], t1.v[v], t2.v[v], a.k.sc);
+    vstore(P + iT0, ph);
+    // row y0 - 1 (box row 0, elements V .. V + txt) and column x0 - 1 (box column V - 1, rows 1 .. nty)
+    const int nty = nthr / (txt / V);
+    for (int h = tid; h < txt + nty; h += nthr) {
+      const int e = h < txt ? V + h : (h - txt + 1) * L.pT0 + V - 1;
+      P[e] = phi3(T0[e], T1[e], T2[e], a.k.sc);
+    }
+    return ph;
   }
 
   TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char* smem) {
@@ -2774,6 +2836,9 @@ struct KFusedJ1T {
     L = layout(lc.ntx, lc.nty);
     red[0] = 0.0;
     leader = lc.tx == 0 && lc.ty == 0;
+    tid = lc.ty * lc.ntx + lc.tx;
+    nthr = lc.ntx * lc.nty;
+    txt = lc.ntx * V;
     const int xt = lc.bx % a.g.xtiles, yt = lc.bx / a.g.xtiles;
     x0b = xt * C::iw(lc.ntx);
     y0b = yt * C::ih(lc.nty);
@@ -2784,8 +2849,13 @@ struct KFusedJ1T {
     c.edge = c.edge || x0b == 0 || y0b == 0 || x0b + lc.ntx * V >= a.g.nx || y0b + lc.nty >= a.g.ny;
     iU = (lc.ty + 1) * L.pU + (lc.tx + 1) * V;
     iF = lc.ty * L.pF + lc.tx * V;
-    iT1 = (lc.ty + 1) * L.pF + lc.tx * V;
-    iT2 = lc.ty * L.pT2 + (lc.tx + 1) * V;
+    if (ISO) {
+      iT0 = iT1 = iT2 = (lc.ty + 1) * L.pT0 + (lc.tx + 1) * V;
+    } else {
+      iT0 = iF;
+      iT1 = (lc.ty + 1) * L.pT1 + lc.tx * V;
+      iT2 = lc.ty * L.pT2 + (lc.tx + 1) * V;
+    }
     j = c.z0;
     sr = 1;  // plane z0 - 1 sits in stage 0, plane z0 in stage 1, ...
     kq = 0;
@@ -2801,18 +2871,31 @@ struct KFusedJ1T {
     w0_prev = vsplat<T>((T)0);
     if (c.has_zlo(a.g, j)) {
       u_lo = vload(reinterpret_cast<const T*>(sm1 + L.oU) + iU);
-      const Vec<T> t0 = vload(reinterpret_cast<const T*>(sm1 + L.oT0) + iF);
+      const Vec<T> t0 = vload(reinterpret_cast<const T*>(sm1 + L.oT0) + iT0);
+      if (ISO) {
+        const Vec<T> t1 = vload(reinterpret_cast<const T*>(sm1 + L.oT1) + iT0), t2 = vload(reinterpret_cast<const T*>(sm1 + L.oT2) + iT0);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        T b;
-        bw1(t0.v[v], a.k.sc, b, w0_prev.v[v]);
+        for (int v = 0; v < V; ++v) {
+          T b;
+          bwphi(t0.v[v], phi3(t0.v[v], t1.v[v], t2.v[v], a.k.sc), a.k.sc, b, w0_prev.v[v]);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          T b;
+          bw1(t0.v[v], a.k.sc, b, w0_prev.v[v]);
+        }
       }
     }
+    phi_c = vsplat<T>((T)0);
+    if (ISO) phi_c = make_phi(a, smem, 1, 0);  // phi of plane z0 -> slot 0 (published by the barrier of pre_sync)
     up_prev = vsplat<T>((T)0);
 #pragma unroll
     for (int d = 0; d < D; ++d) b_prev[d] = vsplat<T>((T)0);
     return true;
   }
+  // iso: the phi ring slot filled in init() must be visible to the whole block before the first step reads it
+  static constexpr bool SYNC_AFTER_INIT = ISO;
   TVDK_DEV bool more() const { return j <= c.z1; }
 
   template <bool E>
@@ -2827,6 +2910,8 @@ struct KFusedJ1T {
     Vec<T> b_cur[D], w0_cur = w0_prev;
 #pragma unroll
     for (int d = 0; d < D; ++d) b_cur[d] = b_prev[d];
+    Vec<T> phi_n = phi_c;
+    if (ISO && j < c.z1) phi_n = make_phi(a, smem, sr1, slot ^ 1);  // phi of plane j + 1, read after the next barrier
     if (have_row) {
       const unsigned char* sj = stage_at(smem, sr);
       const T* U = reinterpret_cast<const T*>(sj + L.oU);
@@ -2834,21 +2919,34 @@ struct KFusedJ1T {
       const T* T2 = reinterpret_cast<const T*>(sj + L.oT2);
       if (c.has_zhi(a.g, j)) u_hi = vload(reinterpret_cast<const T*>(stage_at(smem, sr1) + L.oU) + iU);
       const Vec<T> f = vload(reinterpret_cast<const T*>(sj + L.oF) + iF);
-      const Vec<T> t0 = vload(reinterpret_cast<const T*>(sj + L.oT0) + iF);
-      const Vec<T> t1 = vload(T1 + iT1), t1m = vload(T1 + iT1 - L.pF);
+      const Vec<T> t0 = vload(reinterpret_cast<const T*>(sj + L.oT0) + iT0);
+      const Vec<T> t1 = vload(T1 + iT1), t1m = vload(T1 + iT1 - L.pT1);
       const Vec<T> t2 = vload(T2 + iT2);
       const T t2l = T2[iT2 - 1];
       const Vec<T> ym = vload(U + iU - L.pU), yp = vload(U + iU + L.pU);
       const T xl = U[iU - 1], xr = U[iU + V];
       Vec<T> w1, w2, w1m;
       T w2l, bdummy;
-      bw1(t2l, sc, bdummy, w2l);
+      if (ISO) {
+        const T* P = phiring(smem, slot);
+        const Vec<T> phm = vload(P + iT0 - L.pT0);
+        bwphi(t2l, P[iT0 - 1], sc, bdummy, w2l);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        bw1(t0.v[v], sc, b_cur[0].v[v], w0_cur.v[v]);
-        bw1(t1.v[v], sc, b_cur[1].v[v], w1.v[v]);
-        bw1(t2.v[v], sc, b_cur[2].v[v], w2.v[v]);
-        bw1(t1m.v[v], sc, bdummy, w1m.v[v]);
+        for (int v = 0; v < V; ++v) {
+          bwphi(t0.v[v], phi_c.v[v], sc, b_cur[0].v[v], w0_cur.v[v]);
+          bwphi(t1.v[v], phi_c.v[v], sc, b_cur[1].v[v], w1.v[v]);
+          bwphi(t2.v[v], phi_c.v[v], sc, b_cur[2].v[v], w2.v[v]);
+          bwphi(t1m.v[v], phm.v[v], sc, bdummy, w1m.v[v]);
+        }
+      } else {
+        bw1(t2l, sc, bdummy, w2l);
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          bw1(t0.v[v], sc, b_cur[0].v[v], w0_cur.v[v]);
+          bw1(t1.v[v], sc, b_cur[1].v[v], w1.v[v]);
+          bw1(t2.v[v], sc, b_cur[2].v[v], w2.v[v]);
+          bw1(t1m.v[v], sc, bdummy, w1m.v[v]);
+        }
       }
       // rhs = omega f + H_0 w_0 + H_1 w_1 + H_2 w_2 in the reference's order (:84-89), then the sweep (jacobi.py:112-114)
       const bool zlo = c.template ZLO<E>(a.g, j);
@@ -2871,7 +2969,7 @@ struct KFusedJ1T {
       vstore(ring(smem, slot) + iF, up);
     }
     if (j > c.z0) {
-      // outputs of plane j-1: t_new = G u+ + b, u_out = u+, increment (:142-146, :161)
+      // outputs of plane j-1: t_new = G u+ + b, u_out = u+, increment (:136-146, :161)
       const int zo = j - 1;
       const long long oo = c.cur - c.s0b;
       const T* R = ring(smem, slot ^ 1);
@@ -2902,6 +3000,7 @@ struct KFusedJ1T {
     u_c = u_hi;
     w0_prev = w0_cur;
     up_prev = up;
+    phi_c = phi_n;
 #pragma unroll
     for (int d = 0; d < D; ++d) b_prev[d] = b_cur[d];
   }

@@ -325,7 +325,7 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   LaunchCfg ch = plan_launch<KChamb<T, D, 0>, T, D>(g, tune, true);
   size_t m = (size_t)ch.gx * ch.gy * ch.gz * 2;
   if constexpr (D == 3) {
-    LaunchCfg tm = plan_launch<KFusedJ1T<T>, T, D>(g, tune, true);
+    LaunchCfg tm = plan_launch<KFusedJ1T<T, false>, T, D>(g, tune, true);
     m = std::max(m, (size_t)tm.gx * tm.gy * tm.gz * 2);
   }
   if constexpr (D == 2) {
@@ -381,13 +381,12 @@ static int field_map(TmaMap* m, const T* base, const Geom& g, int bx, int by) {
                              g.s0 * (long long)sizeof(T), bx, by);
 }
 
-// K1 for 3-D anisotropic problems with scalar coefficients: the TMA-staged kernel
-template <typename T>
+// K1 for 3-D problems with scalar coefficients: the TMA-staged kernel
+template <typename T, bool ISO>
 static int run_fj1_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const T* f, const T* u_in, T* u_out, const T* t_in,
                        T* t_out, long long tcs_in, long long tcs_out, const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc,
                        void* stream) {
-  typedef KFusedJ1T<T> K;
-  constexpr int V = Vec<T>::N;
+  typedef KFusedJ1T<T, ISO> K;
   LaunchCfg L = plan_launch<K, T, 3>(g, tune, true);
   typename K::Args a;
   memset(&a, 0, sizeof a);
@@ -399,12 +398,11 @@ static int run_fj1_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const
   a.tcs_out = tcs_out;
   a.skip = skip;
   a.fin = fin;
-  const int tx = L.ntx * V, ty = L.nty;
-  TVDK_TRY(field_map(&a.tm_u, u_in, L.g, tx + 2 * V, ty + 2));
-  TVDK_TRY(field_map(&a.tm_f, f, L.g, tx, ty));
-  TVDK_TRY(field_map(&a.tm_t0, t_in, L.g, tx, ty));
-  TVDK_TRY(field_map(&a.tm_t1, t_in + tcs_in, L.g, tx, ty + 1));
-  TVDK_TRY(field_map(&a.tm_t2, t_in + 2 * tcs_in, L.g, tx + V, ty));
+  TVDK_TRY(field_map(&a.tm_u, u_in, L.g, K::box_w(0, L.ntx), K::box_h(0, L.nty)));
+  TVDK_TRY(field_map(&a.tm_f, f, L.g, K::box_w(1, L.ntx), K::box_h(1, L.nty)));
+  TVDK_TRY(field_map(&a.tm_t0, t_in, L.g, K::box_w(2, L.ntx), K::box_h(2, L.nty)));
+  TVDK_TRY(field_map(&a.tm_t1, t_in + tcs_in, L.g, K::box_w(3, L.ntx), K::box_h(3, L.nty)));
+  TVDK_TRY(field_map(&a.tm_t2, t_in + 2 * tcs_in, L.g, K::box_w(4, L.ntx), K::box_h(4, L.nty)));
   if ((size_t)L.gx * L.gy * L.gz * K::NRED > sc.partial_cap) return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
   ++g_launches;
   return backend::launch_tma<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
@@ -441,9 +439,11 @@ static int run_fj1(bool iso, bool het, const Geom& g, const Tune& tune, const Co
                    const Scratch& sc, void* stream) {
   if constexpr (D == 3) {
     // (a TMA box holds at most 256 elements per axis: wider forced tiles stay on the march kernel)
-    const LaunchCfg probe = plan_launch<KFusedJ1T<T>, T, 3>(g, tune, true);
-    if (!iso && !het && tma_enabled() && (probe.ntx + 2) * Vec<T>::N <= 256 && probe.nty + 2 <= 256)
-      return run_fj1_tma<T>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
+    const LaunchCfg probe = plan_launch<KFusedJ1T<T, false>, T, 3>(g, tune, true);
+    if (!het && tma_enabled() && (probe.ntx + 2) * Vec<T>::N <= 256 && probe.nty + 2 <= 256) {
+      if (iso) return run_fj1_tma<T, true>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
+      return run_fj1_tma<T, false>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
+    }
   }
   return dispatch2(iso, het, [&](auto I, auto H) {
     typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;

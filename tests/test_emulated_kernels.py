@@ -239,10 +239,11 @@ def test_single_pass_cg_predicted_rho_diagnostic():
     assert rel_l2(out, ref) <= 1e-13
 
 
+@pytest.mark.parametrize("iso", [False, True])
 @pytest.mark.parametrize("shape,batch,tile,dtype,nit", tma_cases())
-def test_tma_staged_fused_jacobi1_3d(shape, batch, tile, dtype, nit):
+def test_tma_staged_fused_jacobi1_3d(shape, batch, tile, dtype, nit, iso):
     """KFusedJ1T (3-D anisotropic Jacobi(1), scalar coefficients): the TMA boxes are emulated by a zero-filling copy."""
-    out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit)
+    out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit, iso)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
     nb = max(1, int(np.prod(batch, dtype=int)))
     assert list(info.iters) == [nit] * nb

@@ -312,9 +312,10 @@ def test_single_pass_cg_predicted_rho_diagnostic(da):
 
 @pytest.mark.parametrize("shape,batch,tile,dtype,nit", tma_cases() + [((70, 90, 200), (), (0, 0, 0), np.float64, 8),
                                                                          ((130, 61, 257), (), (0, 0, 0), np.float32, 8)])
-def test_tma_staged_fused_jacobi1_3d(da, shape, batch, tile, dtype, nit):
+@pytest.mark.parametrize("iso", [False, True])
+def test_tma_staged_fused_jacobi1_3d(da, shape, batch, tile, dtype, nit, iso):
     """KFusedJ1T on the B200: cp.async.bulk.tensor boxes + mbarrier ring against the oracle (and the march kernel's bar)."""
-    out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit)
+    out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit, iso)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
     nb = max(1, int(np.prod(batch, dtype=int)))
     assert list(info.iters) == [nit] * nb

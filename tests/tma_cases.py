@@ -34,9 +34,9 @@ def tma_cases():
     ]
 
 
-def run_tma_case(da, oracle, shape, batch, tile, dtype, nit):
+def run_tma_case(da, oracle, shape, batch, tile, dtype, nit, iso=False):
     img = phantom(tuple(shape) + tuple(batch), 13, dtype)
-    kw = dict(mu=0.1, omega=1.3, ell=0.9, dim=3, max_num_iter=nit, isotropic=False)
+    kw = dict(mu=0.1, omega=1.3, ell=0.9, dim=3, max_num_iter=nit, isotropic=iso)
     hist = []
     ref = oracle.split_bregman_tvd(img, solver=oracle.Jacobi(maxiter=1), history=hist, **kw)
     out, info = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=1), tile=tile, return_info=True, **kw)
