@@ -215,6 +215,11 @@ namespace backend {
 
 static int cuda_fail(cudaError_t e, const char* what);
 
+template <class K, typename = void>
+struct is_tma_kernel : std::false_type {};
+template <class K>
+struct is_tma_kernel<K, std::void_t<decltype(K::TMA)>> : std::bool_constant<K::TMA> {};
+
 constexpr int kMaxDevices = 64;
 static int current_device() {
   int dev = -1;
@@ -264,6 +269,38 @@ int launch_tma(const typename K::Args& a, int gx, int gy, int gz, int ntx, int n
 // no swizzle, no interleave, zero fill outside the tensor
 static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long long ny, long long nz, long long row_bytes,
                       long long plane_bytes, int bx, int by);
+
+// resident thread blocks per SM of a kernel at a launch shape (cached: the planner asks on every launch)
+template <class K>
+int occupancy(int threads, size_t smem) {
+  struct Entry {
+    int threads;
+    size_t smem;
+    int blocks;
+  };
+  static thread_local Entry cache[8] = {};
+  static thread_local int used = 0;
+  for (int i = 0; i < used; ++i)
+    if (cache[i].threads == threads && cache[i].smem == smem) return cache[i].blocks;
+  int blocks = 0;
+  cudaError_t e;
+  if (smem > 48 * 1024) {  // the opt-in has to be in place for the query to count the launch as valid
+    if constexpr (is_tma_kernel<K>::value)
+      cudaFuncSetAttribute(tvdk_kernel_tma<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else
+      cudaFuncSetAttribute(tvdk_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
+  if constexpr (is_tma_kernel<K>::value)
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tvdk_kernel_tma<K>, threads, smem);
+  else
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, tvdk_kernel<K>, threads, smem);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    blocks = 4;
+  }
+  if (used < 8) cache[used++] = Entry{threads, smem, blocks};
+  return blocks;
+}
 
 static int memset_async(void* p, int value, size_t bytes, void* stream) {
   cudaError_t e = cudaMemsetAsync(p, value, bytes, (cudaStream_t)stream);

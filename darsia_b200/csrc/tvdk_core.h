@@ -3027,6 +3027,210 @@ struct KFusedJ1T {
 };
 
 // ==========================================================================================
+// K5-TMA / K4-TMA  one stencil field staged by TMA, 3-D, scalar coefficients -- no halo threads at all:
+//   MODE TS_PQ     p_out = first ? r : beta p + r ;  reduce p_out . (A p_out)        (K5: scipy cg via cg.py:50-56)
+//                  p_out of the six neighbours is re-derived from the staged p and r (one FMA each)
+//   MODE TS_SWEEP  x_out = rhs / diag + N(x) / (diag / ell)                           (K4: jacobi.py:101-114)
+//   Boxes per plane: A = p / x with a one-cell halo (ntx V + 2V) x (nty + 2); B = r with the same halo (PQ) or the
+//   bare tile (SWEEP).  The z-neighbours are carried in registers; the step's only barrier recycles the stage.
+// ==========================================================================================
+enum { TS_PQ = 0, TS_SWEEP = 1 };
+
+template <typename T, int MODE>
+struct KStencilT {
+  static constexpr int D = 3;
+  static constexpr int V = Vec<T>::N;
+  static constexpr int LH = 0, RH = 0, NRED = MODE == TS_PQ ? 1 : 0;
+  static constexpr int NS = TVDK_TMA_NS;
+  static constexpr int ZC3D = 64;
+  static constexpr int NTX3D = 16;
+  static constexpr int NTY3D = sizeof(T) == 4 ? 12 : 8;
+  static constexpr bool TMA = true;
+  static constexpr bool SYNC_AFTER_INIT = false;
+  typedef Col<T, D, 0, 0, 0, 0> C;
+  struct Args {
+    Geom g;
+    Coefs<T> k;
+    T* out;        // PQ: p_out ; SWEEP: x_out
+    DRef coef;     // PQ: beta
+    IRef first;    // PQ: first spin (p = r), per problem
+    int first_all;
+    const tvdk_stat_t* skip;  // done ; PQ: cg_stop ; SWEEP: jac_stop
+    Fin fin;
+    TmaMap tm_a, tm_b;
+  };
+  struct Lay {
+    int pA, pB, oA, oB, stage_bytes, stage_off, total;
+    unsigned bytesA, bytesB;
+  };
+  static TVDK_HD int a128(int x) { return (x + 127) / 128 * 128; }
+  static TVDK_HD int box_w(int which, int ntx) { return (which == 0 || MODE == TS_PQ) ? (ntx + 2) * V : ntx * V; }
+  static TVDK_HD int box_h(int which, int nty) { return (which == 0 || MODE == TS_PQ) ? nty + 2 : nty; }
+  static TVDK_HD Lay layout(int ntx, int nty) {
+    Lay L;
+    const int W = (int)sizeof(T);
+    L.pA = box_w(0, ntx);
+    L.pB = box_w(1, ntx);
+    L.bytesA = (unsigned)(L.pA * box_h(0, nty) * W);
+    L.bytesB = (unsigned)(L.pB * box_h(1, nty) * W);
+    L.oA = 0;
+    L.oB = a128((int)L.bytesA);
+    L.stage_bytes = L.oB + a128((int)L.bytesB);
+    L.stage_off = 128;
+    L.total = L.stage_off + NS * L.stage_bytes;
+    return L;
+  }
+  static TVDK_HD size_t smem_bytes(int ntx, int nty) { return (size_t)layout(ntx, nty).total; }
+
+  C c;
+  Lay L;
+  int j, x0b, y0b, zb, sr, kq, iA, iB;
+  T beta;
+  bool first, leader;
+  Vec<T> p_lo, p_c;
+  double red[NRED > 0 ? NRED : 1];
+
+  static TVDK_DEV bool skipped(const Args& a, const LaunchCtx& lc) {
+    if (!a.skip) return false;
+    const tvdk_stat_t& s = a.skip[lc.bz];
+    return s.done || (MODE == TS_PQ ? s.cg_stop : s.jac_stop);
+  }
+  static TVDK_DEV void bar_init(const Args&, const LaunchCtx& lc, unsigned char* smem) {
+    if (lc.tx == 0 && lc.ty == 0) {
+      unsigned long long* bars = reinterpret_cast<unsigned long long*>(smem);
+      for (int s = 0; s < NS; ++s) mbar_init(bars + s, 1);
+      mbar_init_fence();
+    }
+  }
+  TVDK_DEV unsigned long long* bar_at(unsigned char* smem, int idx) const { return reinterpret_cast<unsigned long long*>(smem) + idx; }
+  TVDK_DEV unsigned char* stage_at(unsigned char* smem, int idx) const { return smem + L.stage_off + idx * L.stage_bytes; }
+  TVDK_DEV void issue(const Args& a, unsigned char* smem, int p, int idx) const {
+    unsigned long long* b = bar_at(smem, idx);
+    unsigned char* s = stage_at(smem, idx);
+    const bool needA = !(MODE == TS_PQ && first);  // first CG spin: p = r, the old p is never read
+    mbar_expect_tx(b, (needA ? L.bytesA : 0u) + L.bytesB);
+    const int z = zb + p;
+    if (needA) tma_load_3d(s + L.oA, &a.tm_a, x0b - V, y0b - 1, z, b);
+    if (MODE == TS_PQ)
+      tma_load_3d(s + L.oB, &a.tm_b, x0b - V, y0b - 1, z, b);
+    else
+      tma_load_3d(s + L.oB, &a.tm_b, x0b, y0b, z, b);
+  }
+  // the stencil field at box offset `i` of the stage: PQ: p_new = beta p + r (r alone on the first spin); SWEEP: x
+  TVDK_DEV Vec<T> fieldv(const unsigned char* s, int i) const {
+    if (MODE == TS_SWEEP) return vload(reinterpret_cast<const T*>(s + L.oA) + i);
+    const Vec<T> r = vload(reinterpret_cast<const T*>(s + L.oB) + i);
+    if (first) return r;
+    const Vec<T> p = vload(reinterpret_cast<const T*>(s + L.oA) + i);
+    Vec<T> o;
+#pragma unroll
+    for (int v = 0; v < V; ++v) o.v[v] = beta * p.v[v] + r.v[v];  // p *= beta; p += r
+    return o;
+  }
+  TVDK_DEV T field1(const unsigned char* s, int i) const {
+    if (MODE == TS_SWEEP) return reinterpret_cast<const T*>(s + L.oA)[i];
+    const T r = reinterpret_cast<const T*>(s + L.oB)[i];
+    if (first) return r;
+    return beta * reinterpret_cast<const T*>(s + L.oA)[i] + r;
+  }
+
+  TVDK_DEV bool init(const Args& a, const LaunchCtx& lc, unsigned char* smem) {
+    c.setup(a.g, lc);
+    L = layout(lc.ntx, lc.nty);
+    if (NRED > 0) red[0] = 0.0;
+    leader = lc.tx == 0 && lc.ty == 0;
+    const int xt = lc.bx % a.g.xtiles, yt = lc.bx / a.g.xtiles;
+    x0b = xt * C::iw(lc.ntx);
+    y0b = yt * C::ih(lc.nty);
+    zb = c.b * a.g.n0;
+    c.edge = x0b == 0 || y0b == 0 || x0b + lc.ntx * V >= a.g.nx || y0b + lc.nty >= a.g.ny;
+    iA = (lc.ty + 1) * L.pA + (lc.tx + 1) * V;
+    iB = MODE == TS_PQ ? iA : lc.ty * L.pB + lc.tx * V;
+    beta = (MODE == TS_PQ && a.coef.p) ? (T)a.coef.at(c.b) : (T)0;
+    first = MODE == TS_PQ && (a.first_all || a.first.at(c.b));
+    j = c.z0;
+    sr = 1;
+    kq = 0;
+    if (leader) {
+      for (int i = 0; i < NS && c.z0 - 1 + i <= c.z1; ++i) issue(a, smem, c.z0 - 1 + i, i);
+    }
+    mbar_wait(bar_at(smem, 0), 0);
+    mbar_wait(bar_at(smem, 1), 0);
+    p_c = fieldv(stage_at(smem, 1), iA);
+    p_lo = c.has_zlo(a.g, j) ? fieldv(stage_at(smem, 0), iA) : p_c;
+    return true;
+  }
+  TVDK_DEV bool more() const { return j < c.z1; }
+
+  template <bool E>
+  TVDK_DEV void step(const Args& a, unsigned char* smem) {
+    const Scalars<T>& sc = a.k.sc;
+    const bool wrap = sr + 1 == NS;
+    const int sr1 = wrap ? 0 : sr + 1;
+    mbar_wait(bar_at(smem, sr1), (unsigned)((kq + (wrap ? 1 : 0)) & 1));
+    const unsigned char* sj = stage_at(smem, sr);
+    const Vec<T> p_hi = c.has_zhi(a.g, j) ? fieldv(stage_at(smem, sr1), iA) : p_c;
+    const Vec<T> ym = fieldv(sj, iA - L.pA), yp = fieldv(sj, iA + L.pA);
+    const T xl = field1(sj, iA - 1), xr = field1(sj, iA + V);
+    const bool zlo = c.template ZLO<E>(a.g, j), zhi = c.template ZHI<E>(a.g, j);
+    Vec<T> o;
+    if (MODE == TS_PQ) {  // q = omega p - L_ell p with the half-weight boundary rows (derivatives.py:88-104), as apply_A
+      const T l = a.k.ell.val;
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        T s = lap_axis(p_lo.v[v], p_c.v[v], p_hi.v[v], zlo, zhi, l, l, l);
+        s = s + lap_axis(ym.v[v], p_c.v[v], yp.v[v], c.template YLO<E>(), c.template YHI<E>(), l, l, l);
+        const T left = v > 0 ? p_c.v[v > 0 ? v - 1 : 0] : xl;
+        const T right = v < V - 1 ? p_c.v[v < V - 1 ? v + 1 : 0] : xr;
+        s = s + lap_axis(left, p_c.v[v], right, c.template HL<E>(v), c.template HR<E>(v), l, l, l);
+        o.v[v] = sc.omega * p_c.v[v] - s;
+      }
+      sto(c, a.out, c.cur, p_c);
+      if (c.st) {
+#pragma unroll
+        for (int v = 0; v < V; ++v)
+          if (c.template OK<E>(v)) red[0] += (double)p_c.v[v] * (double)o.v[v];
+      }
+    } else {  // N(x) in the reference's order (jacobi.py:40-55), as nsum
+      const Vec<T> rhs = vload(reinterpret_cast<const T*>(sj + L.oB) + iB);
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        T s = (zlo ? p_lo.v[v] : p_c.v[v]) + (zhi ? p_hi.v[v] : p_c.v[v]);
+        s += c.template YLO<E>() ? ym.v[v] : p_c.v[v];
+        s += c.template YHI<E>() ? yp.v[v] : p_c.v[v];
+        const T left = v > 0 ? p_c.v[v > 0 ? v - 1 : 0] : xl;
+        const T right = v < V - 1 ? p_c.v[v < V - 1 ? v + 1 : 0] : xr;
+        s += c.template HL<E>(v) ? left : p_c.v[v];
+        s += c.template HR<E>(v) ? right : p_c.v[v];
+        o.v[v] = rhs.v[v] * sc.inv_diag + s * sc.c_nb;
+      }
+      sto(c, a.out, c.cur, o);
+    }
+    p_lo = p_c;
+    p_c = p_hi;
+  }
+  TVDK_DEV void pre(const Args& a, unsigned char* smem) {
+    if (c.edge || c.zedge(a.g, j))
+      step<true>(a, smem);
+    else
+      step<false>(a, smem);
+  }
+  TVDK_DEV void post(const Args& a, unsigned char* smem) {
+    if (leader) {
+      if (j == c.z0 && j - 1 + NS <= c.z1) issue(a, smem, j - 1 + NS, 0);
+      if (j + NS <= c.z1) issue(a, smem, j + NS, sr);
+    }
+    if (++sr == NS) {
+      sr = 0;
+      ++kq;
+    }
+    c.cur += c.s0b;
+    ++j;
+  }
+  static TVDK_DEV void finalize(const Args& a, int b, const double* tot) { finalize_fin(a.fin, NRED > 0 ? NRED : 1, b, tot); }
+};
+
+// ==========================================================================================
 // Slab decomposition: halo exchange + all-reduce over peer memory (tvdk_slab.inl; include/tvdk.h)
 //   Every rank's arena starts with a SlabHeader.  slot[parity][s] is the mailbox rank s writes into
 //   (on EVERY rank, its own included): up to 8 partial sums, then -- after a system-wide fence --

@@ -216,6 +216,7 @@ static thread_local Tune g_tune = {0, 0, 0};
 // TVDK_ALTERNATE=0 switches it off (A/B runs).  The results do not depend on it (same per-voxel arithmetic, reductions
 // summed by logical chunk index).
 static thread_local int g_alternate = 0;  // 0: off ; 1 / 2: next launch ascending / descending
+static thread_local int g_force_variants = 0;  // tvdk_problem_t.fused >= 2: take every implemented kernel variant
 static bool alternate_enabled() {
   static const int v = env_int("TVDK_ALTERNATE", 1);
   return v != 0;
@@ -237,6 +238,10 @@ static Tune merge_tune(int tx, int ty, int zc) {
 }
 
 static int round_up(int a, int b) { return (a + b - 1) / b * b; }
+static bool wave_aware_enabled() {
+  static const int v = env_int("TVDK_WAVES", 1);
+  return v != 0;
+}
 
 template <class K, typename T, int D>
 static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
@@ -288,6 +293,27 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
     // as a problem alone still fills the GPU several times over
     const int pref = D == 2 ? KernelZc<K>::get(D) : KernelZc3<K>::value;
     if (pref > zc && tiles * ((nz + pref - 1) / pref) >= 148LL * 8) zc = pref;
+    // Small problems (BASELINE config 1: a 1788 x 3180 image is 13 tiles x 224 chunks of 8 rows = 2.5 waves of resident
+    // thread blocks): pick the chunk length whose block count fills WHOLE waves.  Cost model: waves x (planes per block
+    // + 3 planes of prologue); measured on that image (profiles/r2_cfg1_chunks.txt): 20 rows per block = one full wave,
+    // 0.068 ms per launch against 0.074 with 8.  Still a function of the problem alone, not of nb.
+    if (wave_aware_enabled() && tiles * ((nz + 7) / 8) <= 6LL * 148 * 8) {
+      size_t smem_k = 0;
+      if constexpr (KernelIsTma<K>::value)
+        smem_k = K::smem_bytes(L.ntx, L.nty);
+      else
+        smem_k = (size_t)K::NROWS * C::row_elems(L.ntx, L.nty) * sizeof(T);
+      const long long slots = 148LL * std::max(1, backend::occupancy<K>(L.ntx * L.nty, smem_k));
+      long long best_cost = -1;
+      for (int cand = 8; cand <= std::min(64, std::max(8, nz)); ++cand) {
+        const long long blocks = tiles * ((nz + cand - 1) / cand);
+        const long long cost = ((blocks + slots - 1) / slots) * (cand + 3);
+        if (best_cost < 0 || cost < best_cost) {
+          best_cost = cost;
+          zc = cand;
+        }
+      }
+    }
   }
   zc = std::min(zc, nz);
   g.zchunk = zc;
@@ -327,6 +353,8 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   if constexpr (D == 3) {
     LaunchCfg tm = plan_launch<KFusedJ1T<T, false>, T, D>(g, tune, true);
     m = std::max(m, (size_t)tm.gx * tm.gy * tm.gz * 2);
+    LaunchCfg ts = plan_launch<KStencilT<T, TS_PQ>, T, D>(g, tune, true);
+    m = std::max(m, (size_t)ts.gx * ts.gy * ts.gz * 2);
   }
   if constexpr (D == 2) {
     LaunchCfg x2 = plan_launch<KFusedJ1x2<T, false, false>, T, D>(g, tune, true);
@@ -441,8 +469,13 @@ static int run_fj1(bool iso, bool het, const Geom& g, const Tune& tune, const Co
     // (a TMA box holds at most 256 elements per axis: wider forced tiles stay on the march kernel)
     const LaunchCfg probe = plan_launch<KFusedJ1T<T, false>, T, 3>(g, tune, true);
     if (!het && tma_enabled() && (probe.ntx + 2) * Vec<T>::N <= 256 && probe.nty + 2 <= 256) {
-      if (iso) return run_fj1_tma<T, true>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
-      return run_fj1_tma<T, false>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
+      // The isotropic variant measured SLOWER than the march kernel (profiles/r2_tma_iso.txt, 512^3: fp64 0.80 vs 0.83 of
+      // the HBM peak, fp32 0.66 vs 0.78: forming phi one plane ahead costs more than the halo rows it removes), so it only
+      // runs when every variant is forced (fused = 2: tests) or TVDK_TMA_ISO=1.
+      static const int iso_env = env_int("TVDK_TMA_ISO", 0);
+      if (iso && (g_force_variants || iso_env))
+        return run_fj1_tma<T, true>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
+      if (!iso) return run_fj1_tma<T, false>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
     }
   }
   return dispatch2(iso, het, [&](auto I, auto H) {
@@ -453,6 +486,82 @@ static int run_fj1(bool iso, bool het, const Geom& g, const Tune& tune, const Co
     a.t_in = t_in; a.t_out = t_out; a.tcs_in = tcs_in; a.tcs_out = tcs_out;
     a.skip = skip; a.fin = fin;
     return run<K, T, D>(a, g, tune, true, sc, stream);
+  });
+}
+
+// K5 / K4 in 3-D with scalar coefficients: the TMA-staged single-field stencil kernel
+template <typename T, int MODE>
+static int run_stencil_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const T* a_in, const T* b_in, T* out, DRef coef,
+                           IRef first, int first_all, const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc, void* stream) {
+  typedef KStencilT<T, MODE> K;
+  LaunchCfg L = plan_launch<K, T, 3>(g, tune, true);
+  typename K::Args a;
+  memset(&a, 0, sizeof a);
+  a.g = L.g;
+  a.g.rev = next_direction();
+  a.k = k;
+  a.out = out;
+  a.coef = coef;
+  a.first = first;
+  a.first_all = first_all;
+  a.skip = skip;
+  a.fin = fin;
+  // (on the first CG spin the old p is never read; its map still has to be a valid descriptor)
+  TVDK_TRY(field_map(&a.tm_a, a_in ? a_in : b_in, L.g, K::box_w(0, L.ntx), K::box_h(0, L.nty)));
+  TVDK_TRY(field_map(&a.tm_b, b_in, L.g, K::box_w(1, L.ntx), K::box_h(1, L.nty)));
+  if (K::NRED > 0 && (size_t)L.gx * L.gy * L.gz * K::NRED > sc.partial_cap)
+    return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
+  ++g_launches;
+  return backend::launch_tma<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
+}
+
+template <typename T>
+static bool stencil_tma_ok(const Geom& g, const Tune& tune) {
+  if (!tma_enabled()) return false;
+  const LaunchCfg probe = plan_launch<KStencilT<T, TS_PQ>, T, 3>(g, tune, true);
+  return (probe.ntx + 2) * Vec<T>::N <= 256 && probe.nty + 2 <= 256;
+}
+
+// K5: p_out = first ? r : beta p_in + r ; p_out . (A p_out)
+template <typename T, int D>
+static int run_cgpq(bool het, const Geom& g, const Tune& tune, const Coefs<T>& k, const T* p_in, const T* r_in, T* p_out, DRef beta,
+                    IRef first, int first_all, const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc, void* stream) {
+  if constexpr (D == 3) {
+    if (!het && stencil_tma_ok<T>(g, tune))
+      return run_stencil_tma<T, TS_PQ>(g, tune, k, p_in, r_in, p_out, beta, first, first_all, skip, fin, sc, stream);
+  }
+  return dispatch2(het, false, [&](auto H, auto) {
+    typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.p_in = p_in; a.r_in = r_in; a.p_out = p_out;
+    a.coef = beta; a.first = first; a.first_all = first_all;
+    a.skip = skip; a.fin = fin;
+    return run<K, T, D>(a, g, tune, false, sc, stream);
+  });
+}
+
+// K4: one Jacobi sweep (the TMA kernel has no tol-branch sums: fin must be empty for it)
+template <typename T, int D>
+static int run_sweep(bool het, const Geom& g, const Tune& tune, const Coefs<T>& k, const T* x_in, const T* rhs, T* x_out,
+                     const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc, void* stream) {
+  if constexpr (D == 3) {
+    if (!het && fin.kind == FIN_NONE && !fin.sum_out && stencil_tma_ok<T>(g, tune)) {
+      DRef none;
+      none.p = nullptr;
+      none.stride = 0;
+      IRef nof;
+      nof.p = nullptr;
+      nof.stride = 0;
+      return run_stencil_tma<T, TS_SWEEP>(g, tune, k, x_in, rhs, x_out, none, nof, 0, skip, fin, sc, stream);
+    }
+  }
+  return dispatch2(het, false, [&](auto H, auto) {
+    typedef KSweep<T, D, decltype(H)::value> K;
+    typename K::Args a;
+    memset(&a, 0, sizeof a);
+    a.k = k; a.x_in = x_in; a.rhs = rhs; a.x_out = x_out; a.skip = skip; a.fin = fin;
+    return run<K, T, D>(a, g, tune, true, sc, stream);  // 3-D: 16-row tiles (profiles/r1_tile3d.txt)
   });
 }
 
@@ -748,16 +857,15 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
         TVDK_TRY(launch_shrink(it, cur, X, nullptr, nullptr, 0, expl_now, p_last));
       } else {
       for (int i = 0; i < p->solver_maxiter; ++i) {
-        TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
-          typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
-          typename K::Args a;
-          memset(&a, 0, sizeof a);
-          a.k = k; a.p_in = P[(i & 1) ^ 1]; a.r_in = RB; a.p_out = P[i & 1];
-          a.coef.p = &st[0].beta; a.coef.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
-          a.first.p = &st[0].cg_first; a.first.stride = (int)(sizeof(tvdk_stat_t) / sizeof(int));
-          a.skip = st; a.fin = no_fin(); a.fin.kind = FIN_CGPQ; a.fin.stats = st;
-          return run<K, T, D>(a, g, tune, false, sc, stream);
-        }));
+        {
+          DRef beta;
+          beta.p = &st[0].beta; beta.stride = (int)(sizeof(tvdk_stat_t) / sizeof(double));
+          IRef frst;
+          frst.p = &st[0].cg_first; frst.stride = (int)(sizeof(tvdk_stat_t) / sizeof(int));
+          Fin fq = no_fin();
+          fq.kind = FIN_CGPQ; fq.stats = st;
+          TVDK_TRY((run_cgpq<T, D>(het, g, tune, k, P[(i & 1) ^ 1], RB, P[i & 1], beta, frst, 0, st, fq, sc, stream)));
+        }
         TVDK_TRY(dispatch2(het, false, [&](auto H, auto) {
           typedef KCg<T, D, CG_UPDATE, decltype(H)::value> K;
           typename K::Args b;
@@ -813,17 +921,14 @@ static int solve_impl(const tvdk_problem_t* p, void* stream, int* iters_launched
             continue;
           }
         }
-        TVDK_TRY(dispatch2(het0, false, [&](auto H, auto) {
-          typedef KSweep<T, D, decltype(H)::value> K;
-          typename K::Args a;
-          memset(&a, 0, sizeof a);
-          a.k = k0; a.x_in = xin; a.rhs = RB; a.x_out = xout; a.skip = st; a.fin = no_fin();
+        {
+          Fin fs = no_fin();
           if (tolmode) {
-            a.fin.kind = FIN_JTOL; a.fin.stats = st; a.fin.tol = p->solver_tol; a.fin.buf_id = out_id;
-            a.fin.first_sweep = (s == 1);
+            fs.kind = FIN_JTOL; fs.stats = st; fs.tol = p->solver_tol; fs.buf_id = out_id;
+            fs.first_sweep = (s == 1);
           }
-          return run<K, T, D>(a, g, tune, true, sc, stream);  // 3-D: 16-row tiles (profiles/r1_tile3d.txt)
-        }));
+          TVDK_TRY((run_sweep<T, D>(het0, g, tune, k0, xin, RB, xout, st, fs, sc, stream)));
+        }
         if (s == 1) {
           xin = XA;
           xout = XB;
@@ -1004,8 +1109,10 @@ int tvdk_solve(const tvdk_problem_t* p, void* stream, int* iters_launched) {
   int rc = 0;
   TVDK_RANGE("tvdk_solve");
   g_alternate = alternate_enabled() ? 1 : 0;
+  g_force_variants = p->fused >= 2 ? 1 : 0;
   TVDK_DISPATCH(p->geom, rc = (solve_impl<T, D>(p, stream, iters_launched)));
   g_alternate = 0;
+  g_force_variants = 0;
   return rc;
 }
 
@@ -1096,13 +1203,7 @@ static int sweep_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_c
   OpCtx<T, D> o;
   TVDK_TRY(o.init(gg, ws, wsb, stream));
   const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
-  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
-    typedef KSweep<T, D, decltype(H)::value> K;
-    typename K::Args a;
-    memset(&a, 0, sizeof a);
-    a.k = k; a.x_in = (const T*)x_in; a.rhs = (const T*)rhs; a.x_out = (T*)x_out; a.fin = no_fin();
-    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
-  });
+  return run_sweep<T, D>(k.sc.hetero != 0, o.g, o.tune, k, (const T*)x_in, (const T*)rhs, (T*)x_out, nullptr, no_fin(), o.sc, stream);
 }
 
 template <typename T, int D>
@@ -1234,14 +1335,12 @@ static int cgpq_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_co
   OpCtx<T, D> o;
   TVDK_TRY(o.init(gg, ws, wsb, stream));
   const Coefs<T> k = make_coefs<T>(nullptr, om, el, D);
-  return dispatch2(k.sc.hetero != 0, false, [&](auto H, auto) {
-    typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
-    typename K::Args a;
-    memset(&a, 0, sizeof a);
-    a.k = k; a.p_in = (const T*)p_in; a.r_in = (const T*)r; a.p_out = (T*)p_out;
-    a.coef.p = beta; a.coef.stride = 1; a.first_all = first; a.fin = sum_fin(sum_out);
-    return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
-  });
+  DRef b;
+  b.p = beta; b.stride = 1;
+  IRef nof;
+  nof.p = nullptr; nof.stride = 0;
+  return run_cgpq<T, D>(k.sc.hetero != 0, o.g, o.tune, k, (const T*)p_in, (const T*)r, (T*)p_out, b, nof, first, nullptr, sum_fin(sum_out),
+                        o.sc, stream);
 }
 
 template <typename T, int D>

@@ -406,16 +406,11 @@ static int solve_slab_impl(int nlocal, const tvdk_problem_t* const* problems, co
       const int sd = (int)(sizeof(tvdk_stat_t) / sizeof(double)), si = (int)(sizeof(tvdk_stat_t) / sizeof(int));
       for (int i = 0; i < m; ++i) {
         TVDK_TRY(each([&](SlabRank<T>& r) {
-          return dispatch2(het, false, [&](auto H, auto) {
-            typedef KCg<T, D, CG_PQ, decltype(H)::value> K;
-            typename K::Args a;
-            memset(&a, 0, sizeof a);
-            a.k = r.k; a.p_in = r.P[(i & 1) ^ 1]; a.r_in = r.RB; a.p_out = r.P[i & 1];
-            a.coef.p = &r.st[0].beta; a.coef.stride = sd;
-            a.first.p = &r.st[0].cg_first; a.first.stride = si;
-            a.skip = r.st; a.fin = local_fin(r);
-            return run<K, T, D>(a, r.g, tune, false, r.sc, r.stream);
-          });
+          DRef beta;
+          beta.p = &r.st[0].beta; beta.stride = sd;
+          IRef frst;
+          frst.p = &r.st[0].cg_first; frst.stride = si;
+          return run_cgpq<T, D>(het, r.g, tune, r.k, r.P[(i & 1) ^ 1], r.RB, r.P[i & 1], beta, frst, 0, r.st, local_fin(r), r.sc, r.stream);
         }));
         TVDK_TRY(comm_step(R, field_halo([&](SlabRank<T>& r) { return r.P[i & 1]; }, 1, 1), 1, plain_fin(FIN_CGPQ),
                            SKIP_DONE | SKIP_CG));
@@ -462,14 +457,9 @@ static int solve_slab_impl(int nlocal, const tvdk_problem_t* const* problems, co
       for (int s = 2; s <= m; ++s) {
         const int out_id = in_a ? 2 : 1;
         TVDK_TRY(each([&](SlabRank<T>& r) {
-          return dispatch2(het0, false, [&](auto H, auto) {
-            typedef KSweep<T, D, decltype(H)::value> K;
-            typename K::Args a;
-            memset(&a, 0, sizeof a);
-            a.k = r.k; a.x_in = in_a ? r.XA : r.XB; a.rhs = r.RB; a.x_out = in_a ? r.XB : r.XA;
-            a.skip = r.st; a.fin = local_fin(r);
-            return run<K, T, D>(a, r.g, tune, true, r.sc, r.stream);
-          });
+          // (the sums of the tol branch are only formed when a tolerance is set)
+          return run_sweep<T, D>(het0, r.g, tune, r.k, in_a ? r.XA : r.XB, r.RB, in_a ? r.XB : r.XA, r.st,
+                                 tolmode ? local_fin(r) : no_fin(), r.sc, r.stream);
         }));
         std::vector<Fin> sf = plain_fin(tolmode ? FIN_JTOL : FIN_NONE, p0->solver_tol);
         for (auto& f : sf) {

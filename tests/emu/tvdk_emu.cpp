@@ -90,6 +90,11 @@ static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long
   return 0;
 }
 
+template <class K>
+int occupancy(int, size_t) {
+  return 8;
+}
+
 static int memset_async(void* p, int value, size_t bytes, void*) {
   memset(p, value, bytes);
   return 0;

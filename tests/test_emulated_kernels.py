@@ -16,7 +16,7 @@ from parity_cases import (adaptive_cases, cg_fixed_count_cases, chambolle_cases,
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
-from tma_cases import run_tma_case, tma_cases
+from tma_cases import run_stencil_case, run_tma_case, stencil_cases, tma_cases
 
 import darsia_b200 as da
 
@@ -280,3 +280,11 @@ def test_series_streaming_pipeline():
         assert rel_l2(f, ref) <= 1e-13
     with pytest.raises(AssertionError):
         da.tvd_series_stream(iter([frames[0], np.zeros((5, 5))]), dim=2, mu=0.1, ell=1.0, max_num_iter=1)
+
+
+@pytest.mark.parametrize("solver", ["cg", "j3"])
+@pytest.mark.parametrize("shape,tile,dtype", stencil_cases())
+def test_tma_staged_stencil_3d(shape, tile, dtype, solver):
+    """KStencilT (3-D cg_pq / Jacobi sweep with scalar coefficients) against the oracle."""
+    out, ref = run_stencil_case(da, oracle, shape, tile, dtype, solver)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)

@@ -39,5 +39,26 @@ def run_tma_case(da, oracle, shape, batch, tile, dtype, nit, iso=False):
     kw = dict(mu=0.1, omega=1.3, ell=0.9, dim=3, max_num_iter=nit, isotropic=iso)
     hist = []
     ref = oracle.split_bregman_tvd(img, solver=oracle.Jacobi(maxiter=1), history=hist, **kw)
-    out, info = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=1), tile=tile, return_info=True, **kw)
+    # (fused = 2 forces the isotropic TMA variant, which is not the default route: the march kernel measured faster)
+    out, info = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=1), tile=tile, return_info=True, fused=2 if iso else True, **kw)
     return out, ref, info, hist
+
+
+def stencil_cases():
+    """3-D CG / Jacobi(K) through the TMA-staged single-field stencil kernel (KStencilT: tiles WITHOUT halo threads, so the
+    tile edges coincide with the image edges for exact multiples): shape, tile, dtype."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((6, 16, 64), (0, 0, 0), f8), ((6, 17, 65), (0, 0, 0), f8), ((7, 24, 97), (0, 0, 0), f8), ((6, 24, 128), (0, 0, 0), f4),
+        ((6, 25, 129), (0, 0, 0), f4), ((11, 19, 70), (8, 6, 3), f8), ((11, 19, 70), (8, 6, 3), f4), ((2, 1, 7), (0, 0, 0), f8),
+        ((9, 5, 6), (0, 0, 2), f8), ((5, 13, 40), (0, 0, 1), f8),
+    ]
+
+
+def run_stencil_case(da, oracle, shape, tile, dtype, solver):
+    img = phantom(tuple(shape), 17, dtype)
+    kw = dict(mu=0.1, omega=1.2, ell=0.8, dim=3, max_num_iter=4, isotropic=(solver == "cg"))
+    mk = (lambda m: m.CG(maxiter=4, tol=0.0)) if solver == "cg" else (lambda m: m.Jacobi(maxiter=3))
+    ref = oracle.split_bregman_tvd(img, solver=mk(oracle), **kw)
+    out = da.split_bregman_tvd(img, solver=mk(da), tile=tile, **kw)
+    return out, ref
