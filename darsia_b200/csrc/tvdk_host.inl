@@ -546,7 +546,9 @@ template <typename T, int D>
 static int run_sweep(bool het, const Geom& g, const Tune& tune, const Coefs<T>& k, const T* x_in, const T* rhs, T* x_out,
                      const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc, void* stream) {
   if constexpr (D == 3) {
-    if (!het && fin.kind == FIN_NONE && !fin.sum_out && stencil_tma_ok<T>(g, tune)) {
+    // (fp32 only: 0.92 vs 0.78 of the HBM peak at 512^3; in fp64 the march kernel's 0.95 beats the staged 0.93,
+    //  profiles/r2_stencil_ab.txt)
+    if (sizeof(T) == 4 && !het && fin.kind == FIN_NONE && !fin.sum_out && stencil_tma_ok<T>(g, tune)) {
       DRef none;
       none.p = nullptr;
       none.stride = 0;
