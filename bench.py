@@ -731,7 +731,7 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
         del g2, parts, mine
         torch.cuda.empty_cache()
         if want_e2e:
-            owned = phantom_np((e - s,) + shape[1:], 4 + rank, w["dtype"])
+            owned = torch.from_numpy(phantom_np((e - s,) + shape[1:], 4 + rank, w["dtype"])).pin_memory().numpy()
             g3 = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
             g3.setup([owned])
             g3.solve(outer)
@@ -745,7 +745,7 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
             te = reduce_max(time.perf_counter() - t0)
             rec["e2e"] = {"value": nvox * outer / te / 1e6, "unit": "Mvoxel*iter/s", "s_per_step": te,
                           "h2d_bytes_per_step": int(owned.nbytes), "d2h_bytes_per_step": int(out.nbytes),
-                          "input": "pageable ndarray of the owned planes"}
+                          "input": "owned planes in pinned host memory"}
             del g3, owned, out
             torch.cuda.empty_cache()
     return rec
@@ -885,6 +885,7 @@ def run_series(args, w, wname):
     fvox = int(np.prod(shape))
     mu_h, om_h = hetero_maps(w, seed=3)
     pool = [phantom_np(shape, 3 + 100 * rank + k, w["dtype"]) for k in range(4)]  # distinct pageable host frames, cycled
+    pool_pinned = [torch.from_numpy(a).pin_memory().numpy() for a in pool]  # the same frames page-locked (the e2e contract)
     eng = Engine(shape, nb=B, dtype=np_dtype, device=dev)
     mu_f, om_f = eng.coef(mu_h)[1], eng.coef(om_h)[1]
     f = eng.upload(np.stack([pool[k % 4] for k in range(B)], axis=-1))
@@ -932,9 +933,14 @@ def run_series(args, w, wname):
     da.tvd_series_stream(lambda k: pool[k % 4], n_frames=min(T, 2 * B * world), sink=lambda k, fr: None, **kw)  # allocator warm-up
     barrier()
     t0 = time.perf_counter()
-    da.tvd_series_stream(lambda k: pool[k % 4], n_frames=T, sink=sink, **kw)
+    da.tvd_series_stream(lambda k: pool_pinned[k % 4], n_frames=T, sink=sink, **kw)  # frames in pinned host memory
     torch.cuda.synchronize(dev)
     te = reduce_max(time.perf_counter() - t0)
+    barrier()
+    t0 = time.perf_counter()
+    da.tvd_series_stream(lambda k: pool[k % 4], n_frames=T, sink=lambda k, fr: None, **kw)  # pageable frames: + one staging memcpy each
+    torch.cuda.synchronize(dev)
+    te_pageable = reduce_max(time.perf_counter() - t0)
     # the streamed result of the first frame == the resident solve of the same frame
     chk = da.split_bregman_tvd(pool[s % 4], mu=mu_h, omega=om_h, ell=ELL, dim=2, max_num_iter=outer, solver=da.Jacobi(maxiter=1),
                                device=dev)
@@ -955,8 +961,10 @@ def run_series(args, w, wname):
         "cpu_baseline": None,
         "e2e": {"value": T * fvox * outer / te / 1e6, "unit": "Mvoxel*iter/s", "s_per_step": te,
                 "h2d_bytes_per_step": int(mine * fvox * W), "d2h_bytes_per_step": int(mine * fvox * W),
-                "input": "pageable ndarray frames from a generator (tvd_series_stream: pinned staging rings, H2D / solve / D2H overlapped)",
-                "matches_resident_result": same},
+                "input": "frames in pinned host memory from a generator (tvd_series_stream: H2D / solve / D2H overlapped, results into pinned rings)",
+                "matches_resident_result": same,
+                "pageable_input": {"value": T * fvox * outer / te_pageable / 1e6, "s_per_step": te_pageable,
+                                   "note": "pageable frames: one extra staging memcpy per frame on the host (a loader thread per rank)"}},
         "gpu_launches": launches, "clocks": clocks,
     }
     print(json.dumps(line))

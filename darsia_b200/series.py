@@ -264,21 +264,30 @@ def tvd_series_stream(
     for i in range(NSLOT):
         free_out.put(i)
 
-    def loader():  # host frames -> pinned staging (plain memcpy, releases the GIL)
+    def loader():  # host frames -> pinned staging (plain memcpy, releases the GIL); frames that ARE pinned go as they are
         try:
             k, cur, n, slot = s, first, 0, free_in.get()
+            direct = [None] * B
             while cur is not None:
                 a = np.asarray(cur)
                 if a.shape[:dim] != spatial or a.size != fvox:
                     raise AssertionError(f"frame {k}: shape {a.shape} differs from the first frame's")
-                h_in[slot][n].numpy()[...] = a.reshape(-1)
+                src = None
+                if cuda and a.dtype == first.dtype and a.flags.c_contiguous:
+                    tsrc = torch.from_numpy(a.reshape(-1))
+                    if tsrc.is_pinned():  # page-locked by the caller: DMA straight from it, no staging copy
+                        src = tsrc
+                if src is None:
+                    h_in[slot][n].numpy()[...] = a.reshape(-1)
+                direct[n] = src
                 n += 1
                 k += 1
                 cur = next(source, None)
                 if n == B or cur is None:
-                    ready.put((slot, n, k - n))
+                    ready.put((slot, n, k - n, direct[:n]))
                     if cur is not None:
                         n, slot = 0, free_in.get()
+                        direct = [None] * B
             ready.put(None)
         except BaseException as exc:  # noqa: BLE001
             errors.append(exc)
@@ -314,7 +323,7 @@ def tvd_series_stream(
         item = ready.get()
         if item is None:
             break
-        slot, n, k0 = item
+        slot, n, k0, direct = item
         di = it & 1
         f, u, t = fld[di]
         e_cur = eng if n == B else Engine(spatial, nb=n * chans, dtype=cdtype, device=dev)
@@ -324,7 +333,11 @@ def tvd_series_stream(
                 with torch.cuda.stream(st_in):
                     if ev_free[di] is not None:
                         st_in.wait_event(ev_free[di])
-                    d_in[di][:n].copy_(h_in[slot][:n], non_blocking=True)
+                    if all(t is None for t in direct):
+                        d_in[di][:n].copy_(h_in[slot][:n], non_blocking=True)
+                    else:
+                        for i in range(n):
+                            d_in[di][i].copy_(h_in[slot][i] if direct[i] is None else direct[i], non_blocking=True)
                     ev_in = torch.cuda.Event()
                     ev_in.record(st_in)
                 st_cmp.wait_event(ev_in)

@@ -352,6 +352,13 @@ def test_series_streaming_pipeline(da):
         assert rel_l2(f, ref) <= 1e-13
     with pytest.raises(AssertionError):
         da.tvd_series_stream(iter([frames[0], np.zeros((5, 5))]), dim=2, mu=0.1, ell=1.0, max_num_iter=1)
+    # frames the caller keeps in pinned host memory are DMA'd as they are (no staging copy): same result
+    import torch
+
+    pinned = [torch.from_numpy(fr).pin_memory().numpy() for fr in frames]
+    got_p, _ = da.tvd_series_stream(lambda k: pinned[k], n_frames=7, dim=2, batch=3, mu=mu, omega=om, ell=1.0, max_num_iter=6,
+                                    solver=da.Jacobi(maxiter=1))
+    assert all(np.array_equal(a, b) for a, b in zip(got_p, got))
 
 
 @pytest.mark.parametrize("solver", ["cg", "j3"])
