@@ -730,6 +730,44 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
                                         "shape": list(red), "outer_iterations": outer}
         del g2, parts, mine
         torch.cuda.empty_cache()
+        # SURVEY 8d parity protocol (iii): the decomposed result == the single-GPU result AT FULL SIZE.  Every rank repeats
+        # its solve, the owned planes are gathered on rank 0, which solves the whole volume alone (it fits: 9 fields of
+        # 8.6 GB) from the same seeded slabs and compares on the device.
+        if nvox * W * 11 < 150e9 and len({da.slab_range(shape[0], r, world)[1] - da.slab_range(shape[0], r, world)[0]
+                                          for r in range(world)}) == 1:
+            gfull = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
+            gfull.setup([phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev)])
+            gfull.solve(outer)
+            gfull.check()
+            rk = gfull.ranks[0]
+            mine_f = rk.field("u")[rk.plane_elems * 1:rk.plane_elems * (1 + (e - s))].clone()
+            del gfull, rk
+            torch.cuda.empty_cache()
+            gathered = [torch.empty_like(mine_f) for _ in range(world)] if rank == 0 else None
+            dist.gather(mine_f, gathered, dst=0)
+            del mine_f
+            if rank == 0:
+                whole_in = torch.cat([phantom_torch((da.slab_range(shape[0], r, world)[1] - da.slab_range(shape[0], r, world)[0],)
+                                                    + shape[1:], 4 + r, tdtype, dev) for r in range(world)], dim=0)
+                one = SlabGroup.local(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), world=1, devices=[dev])
+                one.setup([whole_in])
+                del whole_in
+                one.solve(outer)
+                r1 = one.ranks[0]
+                ref_f = r1.field("u")[r1.plane_elems * 1:r1.plane_elems * (1 + shape[0])]
+                num, den = 0.0, 0.0
+                o = 0
+                for part in gathered:  # slab by slab: no second copy of the volume
+                    seg = ref_f[o:o + part.numel()]
+                    num += float(torch.sum((part.double() - seg.double()) ** 2))
+                    den += float(torch.sum(seg.double() ** 2))
+                    o += part.numel()
+                rec["parity_full_size_vs_one_gpu"] = {"rel_l2": float(np.sqrt(num / den)), "shape": list(shape),
+                                                      "outer_iterations": outer}
+                del one, r1, ref_f
+            del gathered
+            torch.cuda.empty_cache()
+            barrier()
         if want_e2e:
             owned = torch.from_numpy(phantom_np((e - s,) + shape[1:], 4 + rank, w["dtype"])).pin_memory().numpy()
             g3 = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
