@@ -318,6 +318,7 @@ def tvd_series_stream(
     in_code = {np.dtype(np.float64): _cabi.TVDK_F64, np.dtype(np.float32): _cabi.TVDK_F32}
     it = 0
     ev_free = [None, None]  # the compute stream is done reading d_in[i]
+    ev_dout = [None, None]  # the copy-out stream is done reading d_out[i]
     total = 0
     while True:
         item = ready.get()
@@ -357,6 +358,8 @@ def tvd_series_stream(
             tview.zero_()
             e_cur.solve(f[:nfe], u[:nfe], tview, coefs[0], coefs[1], coefs[2], isotropic, spec, max_num_iter, eps, fused=fused,
                         sync=False)
+            if cuda and ev_dout[di] is not None:
+                st_cmp.wait_event(ev_dout[di])  # the D2H copy of sub-batch k - 2 has drained d_out[di]
             for i in range(n):
                 rc = eng1.lib.unpack(C.byref(eng1.geom), in_code[odtype], u[i * chans * eng.field_elems:].data_ptr(),
                                      d_out[di][i].data_ptr(), eng1.stream())
@@ -370,8 +373,7 @@ def tvd_series_stream(
                     h_out[oslot][:n].copy_(d_out[di][:n], non_blocking=True)
                     ev_out = torch.cuda.Event()
                     ev_out.record(st_out)
-                # d_out[di] is rewritten two sub-batches later: by then the compute stream must wait for this copy
-                st_cmp.wait_event(ev_out)
+                ev_dout[di] = ev_out  # (d_out[di] is rewritten two sub-batches later: the wait sits there, not here)
                 done.put((oslot, n, k0, ev_out))
             else:
                 h_out[oslot][:n].copy_(d_out[di][:n])

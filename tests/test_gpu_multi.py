@@ -157,3 +157,28 @@ def test_slab_p2p_one_process_all_gpus_equals_single_gpu(case):
     grp.check()
     out = np.concatenate(grp.results(), axis=0)
     assert rel_l2(out, ref) <= (1e-12 if vol.dtype == np.float64 else 2e-6)
+
+
+@pytest.mark.skipif(_ngpu() < 2, reason="needs >= 2 GPUs")
+def test_two_devices_from_one_host_thread():
+    """per-device launch state.  The isotropic 3-D fused kernel needs the > 48 KB shared-memory opt-in (a
+    per-DEVICE function attribute) and ``eps`` uses the polling events (created on one device): both must work when
+    the same host thread solves on cuda:0 and then on cuda:1."""
+    import torch
+
+    import bench
+    import darsia_b200 as da
+    from conftest import rel_l2
+
+    vol = bench.phantom_np((40, 48, 96), 7, np.float64)
+    kw = dict(mu=0.1, omega=1.0, ell=1.0, dim=3, isotropic=True, max_num_iter=40, eps=1e-3, solver=da.Jacobi(maxiter=1))
+    a, ia = da.split_bregman_tvd(vol, device=0, return_info=True, **kw)
+    b, ib = da.split_bregman_tvd(vol, device=1, return_info=True, **kw)
+    c, ic = da.split_bregman_tvd(vol, device=torch.device("cuda", 0), return_info=True, **kw)
+    assert np.array_equal(a, b) and np.array_equal(a, c)
+    assert int(ia.iters[0]) == int(ib.iters[0]) == int(ic.iters[0]) < 40
+    vol2 = bench.phantom_np((64, 48, 96), 8, np.float64)  # another shape (another launch configuration) on device 1 first
+    kw2 = dict(mu=0.1, omega=1.0, ell=1.0, dim=3, isotropic=False, max_num_iter=5, solver=da.CG(maxiter=3, tol=0.0))
+    d1 = da.split_bregman_tvd(vol2, device=1, **kw2)
+    d0 = da.split_bregman_tvd(vol2, device=0, **kw2)
+    assert rel_l2(d1, d0) == 0.0
