@@ -769,7 +769,11 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
             torch.cuda.empty_cache()
             barrier()
         if want_e2e:
-            owned = torch.from_numpy(phantom_np((e - s,) + shape[1:], 4 + rank, w["dtype"])).pin_memory().numpy()
+            # (host planes = the device phantom copied out once: numpy takes ~30 s to synthesise 0.5 G voxels)
+            owned_t = torch.empty((e - s,) + shape[1:], dtype=tdtype, pin_memory=True)
+            owned_t.copy_(phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev))
+            torch.cuda.synchronize(dev)
+            owned = owned_t.numpy()
             g3 = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
             g3.setup([owned])
             g3.solve(outer)
@@ -784,7 +788,7 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
             rec["e2e"] = {"value": nvox * outer / te / 1e6, "unit": "Mvoxel*iter/s", "s_per_step": te,
                           "h2d_bytes_per_step": int(owned.nbytes), "d2h_bytes_per_step": int(out.nbytes),
                           "input": "owned planes in pinned host memory"}
-            del g3, owned, out
+            del g3, owned, owned_t, out
             torch.cuda.empty_cache()
     return rec
 
