@@ -671,6 +671,20 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
         barrier()
         return reduce_max(ev0.elapsed_time(ev1)) / n
 
+    def everyone_has(nbytes, what):
+        """True when EVERY rank has `nbytes` of device memory free (the same answer on all ranks, so that a stage is
+        skipped by all of them or by none: a rank that ran out of memory alone would leave the others in a barrier)."""
+        free = torch.cuda.mem_get_info(dev)[0]
+        ok = torch.tensor([1.0 if free > nbytes + (2 << 30) else 0.0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if not bool(ok.item()):
+            skipped.append(f"{what}: needs {nbytes / 2**30:.1f} GiB free on every GPU")
+        return bool(ok.item())
+
+    skipped = []
+    slab_field = (e - s + 3) * int(np.prod(shape[1:])) * W  # one field of this rank's slab incl. ghost planes
+    n_fields = 2 + dim + (5 if kind == "cg" else 2)  # f, u, t + the solver's workspace (upper bound)
     grp = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
     owned_dev = phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev)
     grp.setup([owned_dev])
@@ -698,6 +712,7 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
     rec["comm_steps_per_solve"] = 2 + per_it * outer
     if world > 1:
         # the same slab without neighbours (kernels + the same tiny launches, no peer traffic, no waiting on anybody)
+        grp.close()
         del grp
         torch.cuda.empty_cache()
         alone = SlabGroup.local((e - s,) + shape[1:], dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), world=1, devices=[dev])
@@ -705,6 +720,7 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
         alone.reset()
         alone.solve(outer)
         ms_alone = timed(alone, steps)
+        alone.close()
         del alone
         torch.cuda.empty_cache()
         rec["breakdown_ms"] = {"total": ms_per_step, "own_slab_without_neighbours": ms_alone,
@@ -728,19 +744,21 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
                                           solver=mk(), device=dev)
             rec["parity_vs_one_gpu"] = {"rel_l2": float(np.linalg.norm(whole - single) / np.linalg.norm(single)),
                                         "shape": list(red), "outer_iterations": outer}
+        g2.close()
         del g2, parts, mine
         torch.cuda.empty_cache()
         # SURVEY 8d parity protocol (iii): the decomposed result == the single-GPU result AT FULL SIZE.  Every rank repeats
         # its solve, the owned planes are gathered on rank 0, which solves the whole volume alone (it fits: 9 fields of
         # 8.6 GB) from the same seeded slabs and compares on the device.
-        if nvox * W * 11 < 150e9 and len({da.slab_range(shape[0], r, world)[1] - da.slab_range(shape[0], r, world)[0]
-                                          for r in range(world)}) == 1:
+        equal_slabs = len({da.slab_range(shape[0], r, world)[1] - da.slab_range(shape[0], r, world)[0] for r in range(world)}) == 1
+        if equal_slabs and everyone_has((n_fields + 2) * nvox * W if rank == 0 else (n_fields + 1) * slab_field, "full-size parity"):
             gfull = SlabGroup.distributed(shape, dim, np_dtype, MU, OMEGA, ELL, w["iso"], mk(), device=dev)
             gfull.setup([phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev)])
             gfull.solve(outer)
             gfull.check()
             rk = gfull.ranks[0]
             mine_f = rk.field("u")[rk.plane_elems * 1:rk.plane_elems * (1 + (e - s))].clone()
+            gfull.close()
             del gfull, rk
             torch.cuda.empty_cache()
             gathered = [torch.empty_like(mine_f) for _ in range(world)] if rank == 0 else None
@@ -764,11 +782,12 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
                     o += part.numel()
                 rec["parity_full_size_vs_one_gpu"] = {"rel_l2": float(np.sqrt(num / den)), "shape": list(shape),
                                                       "outer_iterations": outer}
-                del one, r1, ref_f
+                one.close()
+                del one, r1, ref_f, seg, part  # (seg is a view of one's arena: it alone would keep 9 fields alive)
             del gathered
             torch.cuda.empty_cache()
             barrier()
-        if want_e2e:
+        if want_e2e and everyone_has((n_fields + 2) * slab_field, "e2e"):
             # (host planes = the device phantom copied out once: numpy takes ~30 s to synthesise 0.5 G voxels)
             owned_t = torch.empty((e - s,) + shape[1:], dtype=tdtype, pin_memory=True)
             owned_t.copy_(phantom_torch((e - s,) + shape[1:], 4 + rank, tdtype, dev))
@@ -788,8 +807,13 @@ def slab_measure(w, wname, rank, world, local, dev, steps, warmup, want_e2e, bar
             rec["e2e"] = {"value": nvox * outer / te / 1e6, "unit": "Mvoxel*iter/s", "s_per_step": te,
                           "h2d_bytes_per_step": int(owned.nbytes), "d2h_bytes_per_step": int(out.nbytes),
                           "input": "owned planes in pinned host memory"}
+            g3.close()
             del g3, owned, owned_t, out
             torch.cuda.empty_cache()
+    else:
+        grp.close()
+    if skipped:
+        rec["skipped"] = skipped
     return rec
 
 

@@ -207,6 +207,7 @@ SIGNATURES = {
                                      _I, _I, C.POINTER(_VP), C.POINTER(C.c_int)]),
     "tvdk_ipc_export": (C.c_int, [_VP, C.POINTER(C.c_ubyte * 64), C.POINTER(_I64)]),
     "tvdk_ipc_open": (C.c_int, [C.POINTER(C.c_ubyte * 64), _I64, C.POINTER(_VP)]),
+    "tvdk_ipc_close": (C.c_int, [_VP, _I64]),
     "tvdk_enable_peer": (C.c_int, [_I]),
 }
 

@@ -607,6 +607,14 @@ int tvdk_ipc_open(const unsigned char handle[64], int64_t offset, void** ptr_out
   return 0;
 }
 
+int tvdk_ipc_close(void* ptr, int64_t offset) {
+  using namespace tvdk;
+  if (!ptr) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  // (the exporting device keeps the allocation alive for as long as any process still maps it)
+  cudaError_t e = cudaIpcCloseMemHandle(reinterpret_cast<unsigned char*>(ptr) - offset);
+  return e == cudaSuccess ? 0 : backend::cuda_fail(e, "cudaIpcCloseMemHandle");
+}
+
 int tvdk_enable_peer(int peer_device) {
   using namespace tvdk;
   int dev = -1;

@@ -199,6 +199,8 @@ class SlabGroup:
             rk.comm.seq = C.pointer(self.seq)
             self.ranks.append(rk)
         self.eps = eps
+        self._peer_maps = []  # (pointer, offset) of every arena opened over CUDA IPC
+        self._closed = False
         self._map_arenas()
         for rk in self.ranks:  # scalar coefficients / pointers of the maps
             for k, v in self.coefs.items():
@@ -250,7 +252,6 @@ class SlabGroup:
         mine = (bytes(handle), int(off.value), int(rk.arena_bytes))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, mine, group=self.group)
-        self._peer_keep = []
         for r, (h, o, nbytes) in enumerate(everyone):
             if nbytes != rk.arena_bytes:
                 raise RuntimeError("ranks disagree on the arena layout")
@@ -262,7 +263,40 @@ class SlabGroup:
             with device_guard(rk.device):
                 lib.check(lib.ipc_open(C.byref(hb), o, C.byref(ptr)), "tvdk_ipc_open")
             rk.comm.arena[r] = ptr.value
+            self._peer_maps.append((ptr.value, o))
         dist.barrier(group=self.group)  # every header is zero and mapped before the first flag is written
+
+    def close(self) -> None:
+        """Unmap the peers' arenas and release this process' own (collective for ``distributed`` groups: every
+        rank calls it).  An arena exported over CUDA IPC stays allocated on ITS device until every importer has
+        closed the mapping, so dropping the last Python reference alone does not give the memory back."""
+        if self._closed:
+            return
+        self._closed = True
+        self._ready = False
+        for rk in self.ranks:
+            if rk.device.type == "cuda":
+                torch.cuda.synchronize(rk.device)
+        if self._peer_maps:
+            import torch.distributed as dist
+
+            dist.barrier(group=self.group)  # nobody still pushes into an arena that is about to be unmapped
+            rk = self.ranks[0]
+            with device_guard(rk.device):
+                for ptr, o in self._peer_maps:
+                    self.lib.check(self.lib.ipc_close(ptr, o), "tvdk_ipc_close")
+            self._peer_maps = []
+            dist.barrier(group=self.group)
+        for rk in self.ranks:
+            rk.arena = None
+            rk._keep = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+        return False
 
     # -- data ----------------------------------------------------------------------------------------
     def _arrays(self):
@@ -359,9 +393,10 @@ def split_bregman_tvd_slab_p2p(img_owned, global_shape, mu=1.0, omega=1.0, ell=N
     if not isinstance(img_owned, np.ndarray) or img_owned.dtype not in (np.float32, np.float64):
         raise TypeError("float32/float64 ndarray expected")
     cdtype = img_owned.dtype if precision is None else np.dtype({"fp64": np.float64, "fp32": np.float32}[precision])
-    grp = SlabGroup.distributed(global_shape, dim, cdtype, mu, omega, ell, isotropic, solver, eps=eps, group=group, device=device)
-    grp.setup([img_owned])
-    grp.solve(max_num_iter)
-    out = grp.results(img_owned.dtype)[0]
-    grp.check()
-    return (out, grp.history()) if return_info else out
+    with SlabGroup.distributed(global_shape, dim, cdtype, mu, omega, ell, isotropic, solver, eps=eps, group=group, device=device) as grp:
+        grp.setup([img_owned])
+        grp.solve(max_num_iter)
+        out = grp.results(img_owned.dtype)[0]
+        grp.check()
+        hist = grp.history() if return_info else None
+    return (out, hist) if return_info else out

@@ -362,10 +362,12 @@ int tvdk_slab_exchange(int nlocal, const tvdk_geom_t* const* geoms, const tvdk_s
 
 /* Peer mapping helpers for one-process-per-GPU runs (CUDA IPC; thin wrappers so that callers need no CUDA
  * bindings): export a 64-byte handle + offset for a device pointer / open one exported by another process
- * of the same node (returns the pointer mapped in this process; never freed before exit) / enable peer access
- * from the current device to `peer_device`. */
+ * of the same node (returns the pointer mapped in this process) / unmap it again (`ptr` and `offset` as
+ * tvdk_ipc_open returned / took them; the exporter's memory stays allocated on ITS device until every
+ * importer has closed the mapping) / enable peer access from the current device to `peer_device`. */
 int tvdk_ipc_export(const void* device_ptr, unsigned char handle_out[64], int64_t* offset_out);
 int tvdk_ipc_open(const unsigned char handle[64], int64_t offset, void** ptr_out);
+int tvdk_ipc_close(void* ptr, int64_t offset);
 int tvdk_enable_peer(int peer_device);
 
 #ifdef __cplusplus

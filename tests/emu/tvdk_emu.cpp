@@ -164,6 +164,7 @@ int tvdk_ipc_open(const unsigned char h[64], int64_t off, void** out) {
   *out = reinterpret_cast<unsigned char*>(p) + off;
   return 0;
 }
+int tvdk_ipc_close(void*, int64_t) { return 0; }
 int tvdk_enable_peer(int) { return 0; }
 
 extern "C" int tvdk_is_emulator(void) { return 1; }
