@@ -182,6 +182,8 @@ SIGNATURES = {
     "tvdk_jacobi_sweep": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_cg_matvec": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_shrink": (C.c_int, [_PG, _I, _PC, _PC, _VP, _VP, _VP, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
+    "tvdk_rhs_explicit": (C.c_int, [_PG, _PC, _PC, _VP, _VP, _VP, _I64, _VP, _VP, _SZ, _VP]),
+    "tvdk_shrink_explicit": (C.c_int, [_PG, _I, _PC, _PC, _VP, _VP, _VP, _VP, _I64, _VP, _I64, _VP, _VP, _SZ, _VP]),
     "tvdk_expand_state": (C.c_int, [_PG, _I, _PC, _PC, _VP, _I64, _VP, _VP, _I64, _VP]),
     "tvdk_dot": (C.c_int, [_PG, _VP, _VP, _VP, _VP, _SZ, _VP]),
     "tvdk_norm_diff2": (C.c_int, [_PG, _VP, _VP, _VP, _VP, _SZ, _VP]),
@@ -205,6 +207,8 @@ SIGNATURES = {
     "tvdk_slab_error": (C.c_int, [_VP, _VP, C.POINTER(_I64)]),
     "tvdk_slab_exchange": (C.c_int, [_I, C.POINTER(_PG), C.POINTER(C.POINTER(SlabComm)), _I, C.POINTER(C.POINTER(_VP)),
                                      _I, _I, C.POINTER(_VP), C.POINTER(C.c_int)]),
+    "tvdk_profile_arm": (C.c_int, [C.c_char_p]),
+    "tvdk_profile_read": (C.c_int, [C.POINTER(_I64), C.POINTER(C.c_double)]),
     "tvdk_ipc_export": (C.c_int, [_VP, C.POINTER(C.c_ubyte * 64), C.POINTER(_I64)]),
     "tvdk_ipc_open": (C.c_int, [C.POINTER(C.c_ubyte * 64), _I64, C.POINTER(_VP)]),
     "tvdk_ipc_close": (C.c_int, [_VP, _I64]),

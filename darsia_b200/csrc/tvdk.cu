@@ -6,7 +6,15 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <string.h>
+
+#include <atomic>
+#include <mutex>
+#include <string>
 #include <type_traits>
+#include <typeinfo>
+#include <utility>
+#include <vector>
 
 #include "tvdk_core.h"
 
@@ -226,9 +234,45 @@ static int current_device() {
   return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
 }
 
+// ---- optional timing of one kernel family inside a real solve (tvdk_profile_arm / tvdk_profile_read) ----------------
+// While armed, every launch whose kernel type name contains the pattern is bracketed by two CUDA events on its own
+// stream.  Disarmed (the normal state) this costs one load of a flag per launch.
+struct ProfState {
+  std::mutex mu;
+  std::string pattern;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+static std::atomic<bool> g_prof_on{false};
+static ProfState& prof_state() {
+  static ProfState s;
+  return s;
+}
+template <class K>
+struct ProfScope {
+  cudaEvent_t stop = nullptr;
+  cudaStream_t stream;
+  explicit ProfScope(void* st) : stream((cudaStream_t)st) {
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfState& ps = prof_state();
+    std::lock_guard<std::mutex> lk(ps.mu);
+    if (ps.pattern.empty() || !strstr(typeid(K).name(), ps.pattern.c_str()) || ps.events.size() >= (1u << 20)) return;
+    cudaEvent_t start = nullptr;
+    if (cudaEventCreate(&start) != cudaSuccess || cudaEventCreate(&stop) != cudaSuccess) {
+      stop = nullptr;
+      return;
+    }
+    cudaEventRecord(start, stream);
+    ps.events.emplace_back(start, stop);
+  }
+  ~ProfScope() {
+    if (stop) cudaEventRecord(stop, stream);
+  }
+};
+
 template <class K>
 int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem, void* stream,
            double* partials, unsigned* counters) {
+  ProfScope<K> prof(stream);
   // the opt-in above 48 KB is a per-DEVICE function attribute: cache it per (thread, kernel, device)
   static thread_local size_t smem_set[kMaxDevices] = {};
   if (smem > 48 * 1024) {
@@ -249,6 +293,7 @@ int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, 
 template <class K>
 int launch_tma(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem, void* stream,
                double* partials, unsigned* counters) {
+  ProfScope<K> prof(stream);
   static thread_local size_t smem_set[kMaxDevices] = {};
   if (smem > 48 * 1024) {
     const int dev = current_device();
@@ -568,6 +613,44 @@ static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long
 }
 }  // namespace backend
 }  // namespace tvdk
+
+int tvdk_profile_arm(const char* kernel_substring) {
+  using namespace tvdk;
+  backend::ProfState& ps = backend::prof_state();
+  std::lock_guard<std::mutex> lk(ps.mu);
+  for (auto& ev : ps.events) {
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  ps.events.clear();
+  ps.pattern = kernel_substring ? kernel_substring : "";
+  backend::g_prof_on.store(!ps.pattern.empty());
+  return 0;
+}
+
+int tvdk_profile_read(int64_t* launches, double* total_ms) {
+  using namespace tvdk;
+  if (!launches || !total_ms) return fail(TVDK_ERR_INVALID, "NULL pointer");
+  backend::ProfState& ps = backend::prof_state();
+  std::lock_guard<std::mutex> lk(ps.mu);
+  backend::g_prof_on.store(false);
+  double sum = 0.0;
+  cudaError_t bad = cudaSuccess;
+  for (auto& ev : ps.events) {
+    float ms = 0.f;
+    cudaError_t e = cudaEventSynchronize(ev.second);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(&ms, ev.first, ev.second);
+    if (e != cudaSuccess) bad = e;
+    sum += ms;
+    cudaEventDestroy(ev.first);
+    cudaEventDestroy(ev.second);
+  }
+  *launches = (int64_t)ps.events.size();
+  *total_ms = sum;
+  ps.events.clear();
+  ps.pattern.clear();
+  return bad == cudaSuccess ? 0 : backend::cuda_fail(bad, "tvdk_profile_read");
+}
 
 int tvdk_ipc_export(const void* device_ptr, unsigned char handle_out[64], int64_t* offset_out) {
   using namespace tvdk;

@@ -645,7 +645,9 @@ TVDK_DEV Vec<T> nsum(const C& c, const Vec<T>& lo, const Vec<T>& hi, const Vec<T
 // A x = omega x - L_ell x (cg.py:37-44) with x's z-neighbours in registers and its row in smem;
 // `o` is the element offset of the vector (for the per-voxel-ell variant, which loads ell's
 // neighbours straight from global memory: rare path, cg.py:43 / SURVEY Q18).
-template <typename T, int D, bool E, bool HET, typename C>
+// OUT: a per-voxel ell multiplies the unit-coefficient Laplacian from OUTSIDE, `omega x - ell * laplace(x)` -- the
+// multigrid residual operator (mg.py:94-105), unlike CG's `laplace(x, diffusion_coeff=ell)` (cg.py:37-44).
+template <typename T, int D, bool E, bool HET, bool OUT = false, typename C>
 TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, long long o, const Vec<T>& lo, const Vec<T>& xc,
                         const Vec<T>& hi, const T* row, const Vec<T>& om, const Coef<T>& ell) {
   constexpr int V = Vec<T>::N;
@@ -657,8 +659,9 @@ TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, long long o, const Vec
     ym = sym(row, c);
     yp = syp(row, c);
   }
-  if (!HET || !ell.p) {
-    const T l = ell.val;
+  const bool outside = OUT && HET && ell.p;
+  if (!HET || !ell.p || outside) {
+    const T l = outside ? (T)1 : ell.val;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
       T s = lap_axis(lo.v[v], xc.v[v], hi.v[v], zlo, zhi, l, l, l);
@@ -690,6 +693,12 @@ TVDK_DEV Vec<T> apply_A(const C& c, const Geom& g, int z, long long o, const Vec
     }
   }
   Vec<T> y;
+  if (outside) {
+    const Vec<T> el = ldcoef<HET>(c, ell, o);
+#pragma unroll
+    for (int v = 0; v < V; ++v) y.v[v] = om.v[v] * xc.v[v] - el.v[v] * lap.v[v];
+    return y;
+  }
 #pragma unroll
   for (int v = 0; v < V; ++v) y.v[v] = om.v[v] * xc.v[v] - lap.v[v];
   return y;
@@ -1753,7 +1762,8 @@ struct KCg {
   template <bool E>
   TVDK_DEV void post_t(const Args& a, unsigned char* smem) {
     const Vec<T> om = ldcoef<HET>(c, a.k.omega, c.cur);
-    const Vec<T> q = apply_A<T, D, E, HET>(c, a.g, j, c.cur, p_lo, p_c, p_hi, srow<T>(smem, j & 1, rowe), om, a.k.ell);
+    const Vec<T> q = apply_A<T, D, E, HET, MODE == CG_RESID>(c, a.g, j, c.cur, p_lo, p_c, p_hi, srow<T>(smem, j & 1, rowe), om,
+                                                            a.k.ell);
     if (MODE == CG_PQ) {
       sto(c, a.p_out, c.cur, p_c);
       if (c.st) {

@@ -1186,7 +1186,7 @@ struct OpCtx {
 template <typename T, int D>
 static int rhs_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* om,
                     const tvdk_coef_t* el, const void* f, const void* t, int64_t tcs, void* rhs, void* ws,
-                    size_t wsb, void* stream) {
+                    size_t wsb, void* stream, const void* xd = nullptr, const void* xb = nullptr, int64_t xcs = 0) {
   OpCtx<T, D> o;
   TVDK_TRY(o.init(gg, ws, wsb, stream));
   const Coefs<T> k = make_coefs<T>(mu, om, el, D);
@@ -1195,6 +1195,7 @@ static int rhs_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const
     typename K::Args a;
     memset(&a, 0, sizeof a);
     a.k = k; a.f = (const T*)f; a.t = (const T*)t; a.tcs = tcs; a.rhs = (T*)rhs; a.fin = no_fin();
+    a.xd = (const T*)xd; a.xb = (const T*)xb; a.xcs = xcs;  // (t == nullptr: the explicit d, b of a warm start)
     return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
   });
 }
@@ -1226,7 +1227,8 @@ static int matvec_impl(const tvdk_geom_t* gg, const tvdk_coef_t* om, const tvdk_
 template <typename T, int D>
 static int shrink_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, const tvdk_coef_t* el,
                        const void* u_new, const void* u_old, void* u_out, const void* t_in, void* t_out,
-                       int64_t tcs, double* sum_out, void* ws, size_t wsb, void* stream) {
+                       int64_t tcs, double* sum_out, void* ws, size_t wsb, void* stream, const void* xb = nullptr,
+                       int64_t xcs = 0) {
   OpCtx<T, D> o;
   TVDK_TRY(o.init(gg, ws, wsb, stream));
   const Coefs<T> k = make_coefs<T>(mu, nullptr, el, D);
@@ -1236,6 +1238,7 @@ static int shrink_impl(const tvdk_geom_t* gg, int iso, const tvdk_coef_t* mu, co
     memset(&a, 0, sizeof a);
     a.k = k; a.unew[0] = (const T*)u_new; a.u_old = (const T*)u_old; a.u_out = (T*)u_out;
     a.t_in = (const T*)t_in; a.t_out = (T*)t_out; a.tcs = tcs; a.fin = sum_fin(sum_out);
+    a.xb = (const T*)xb; a.xcs = xcs;  // (t_in == nullptr: the explicit b of a warm start)
     return run<K, T, D>(a, o.g, o.tune, false, o.sc, stream);
   });
 }
@@ -1549,6 +1552,14 @@ int tvdk_rhs(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const t
                                   workspace_bytes, stream)))
 }
 
+int tvdk_rhs_explicit(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* f,
+                      const void* d, const void* b, int64_t db_comp_stride, void* rhs, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  if (!d || !b) return fail(TVDK_ERR_INVALID, "tvdk_rhs_explicit needs both d and b");
+  TVDK_C_ENTRY(g, (rhs_impl<T, D>(g, 0, nullptr, omega, ell, f, nullptr, 0, rhs, workspace, workspace_bytes, stream,
+                                  d, b, db_comp_stride)))
+}
+
 int tvdk_jacobi_sweep(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* x_in,
                       const void* rhs, void* x_out, void* workspace, size_t workspace_bytes, void* stream) {
   TVDK_C_ENTRY(g, (sweep_impl<T, D>(g, omega, ell, x_in, rhs, x_out, workspace, workspace_bytes, stream)))
@@ -1565,6 +1576,16 @@ int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, cons
   if (u_out && u_out == u_new) return fail(TVDK_ERR_INVALID, "u_out must not alias u_new (it may alias u_old)");
   TVDK_C_ENTRY(g, (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, u_out, t_in, t_out, t_comp_stride,
                                      sum_out, workspace, workspace_bytes, stream)))
+}
+
+int tvdk_shrink_explicit(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                         const void* u_new, const void* u_old, void* u_out, const void* b_in, int64_t b_comp_stride,
+                         void* t_out, int64_t t_comp_stride, double* sum_out, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+  if (!b_in) return fail(TVDK_ERR_INVALID, "tvdk_shrink_explicit needs b_in");
+  if (u_out && u_out == u_new) return fail(TVDK_ERR_INVALID, "u_out must not alias u_new (it may alias u_old)");
+  TVDK_C_ENTRY(g, (shrink_impl<T, D>(g, isotropic, mu, ell, u_new, u_old, u_out, nullptr, t_out, t_comp_stride,
+                                     sum_out, workspace, workspace_bytes, stream, b_in, b_comp_stride)))
 }
 
 int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,

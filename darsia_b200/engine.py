@@ -8,6 +8,7 @@ It is also what ``bench.py`` times: ``upload`` -> ``solve`` -> ``download``.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -123,18 +124,27 @@ class Engine:
         return self._stage_pageable(t)
 
     _STAGE: dict = {}  # (thread, device index, dtype) -> two pinned chunks, reused by every engine of that thread
+    _STAGE_POOL = None
+    # host threads copying into the pinned chunks / chunk size (tools/h2d_probe.py measures both on a given box)
+    STAGE_THREADS = int(os.environ.get("DARSIA_B200_STAGE_THREADS", "1"))
+    STAGE_CHUNK_MB = int(os.environ.get("DARSIA_B200_STAGE_CHUNK_MB", "16"))
 
     def _stage_pageable(self, t: torch.Tensor) -> torch.Tensor:
         """A large PAGEABLE host array -> device through two pinned chunks: the host memcpy of chunk i + 1 overlaps the
         DMA of chunk i (a plain ``cudaMemcpy`` from pageable memory stages internally without that overlap: measured
         3.7 GB/s on the 672 MB image of BASELINE configs[1])."""
-        chunk = (16 << 20) // t.element_size()
+        chunk = (Engine.STAGE_CHUNK_MB << 20) // t.element_size()
+        nt = max(1, Engine.STAGE_THREADS)
         import threading
 
-        key = (threading.get_ident(), self.device.index, t.dtype)
+        key = (threading.get_ident(), self.device.index, t.dtype, chunk)
         bufs = Engine._STAGE.get(key)
         if bufs is None:
             bufs = Engine._STAGE[key] = [torch.empty(chunk, dtype=t.dtype, pin_memory=True) for _ in range(2)]
+        if nt > 1 and Engine._STAGE_POOL is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            Engine._STAGE_POOL = ThreadPoolExecutor(nt)
         out = torch.empty(t.numel(), dtype=t.dtype, device=self.device)
         src = t.numpy()
         evs = [None, None]
@@ -144,7 +154,14 @@ class Engine:
             b = i & 1
             if evs[b] is not None:
                 evs[b].synchronize()
-            bufs[b].numpy()[:m] = src[off:off + m]
+            dst = bufs[b].numpy()
+            if nt == 1:
+                dst[:m] = src[off:off + m]
+            else:  # (NumPy releases the GIL while it copies)
+                step = (m + nt - 1) // nt
+                list(Engine._STAGE_POOL.map(
+                    lambda k: np.copyto(dst[k * step:min(m, (k + 1) * step)], src[off + k * step:off + min(m, (k + 1) * step)]),
+                    range(nt)))
             out[off:off + m].copy_(bufs[b][:m], non_blocking=True)
             evs[b] = torch.cuda.Event()
             evs[b].record(stream)

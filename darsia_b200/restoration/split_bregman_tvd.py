@@ -260,8 +260,8 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
     from .._runtime import device_guard
     from ..mg import MGHierarchy
 
-    if x0 is not None or adaptive_mask is not None or return_state:
-        raise NotImplementedError("MG as the inner solver: x0, adaptive and return_state are not implemented")
+    if adaptive_mask is not None:
+        raise NotImplementedError("MG as the inner solver: the adaptive ell schedule is not implemented")
     on_device = _is_tensor(img)
     img_dtype = _np_dtype(img)
     shape = tuple(img.shape)
@@ -275,11 +275,27 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
             mu_b = mu
             if not np.isscalar(mu) and tuple(getattr(mu, "shape", ())) == shape:
                 mu_b = mu.reshape(shape[:dim] + (nb,))[..., b]
-            o, inf = _split_bregman_mg(sl, mu_b, omega, ell, dim, max_num_iter, eps, None, isotropic, solver, None, cdtype,
-                                       device, True, False, verbose_every)
+            x0_b = None
+            if x0 is not None:  # (u, d, b) of this problem: the batch axes sit between the spatial and the component axis
+                u0, d0, b0 = x0
+                x0_b = (u0.reshape(shape[:dim] + (nb,))[..., b], d0.reshape(shape[:dim] + (nb, dim))[..., b, :],
+                        b0.reshape(shape[:dim] + (nb, dim))[..., b, :])
+            coefs_b = []
+            for cmap in (omega, ell):  # full-shape maps: this problem's slice
+                if not np.isscalar(cmap) and tuple(getattr(cmap, "shape", ())) == shape and len(shape) > dim:
+                    cmap = cmap.reshape(shape[:dim] + (nb,))[..., b]
+                coefs_b.append(cmap)
+            o, inf = _split_bregman_mg(sl, mu_b, coefs_b[0], coefs_b[1], dim, max_num_iter, eps, x0_b, isotropic, solver, None,
+                                       cdtype, device, True, return_state, verbose_every)
             outs.append(o)
             infos.append(inf)
-        out = (torch.stack(outs, dim=-1) if on_device else np.stack(outs, axis=-1)).reshape(shape)
+        if return_state:
+            stack = (lambda parts, ax: torch.stack(parts, dim=ax)) if on_device else (lambda parts, ax: np.stack(parts, axis=ax))
+            out = (stack([o[0] for o in outs], -1).reshape(shape),
+                   stack([o[1] for o in outs], -2).reshape(shape + (dim,)),
+                   stack([o[2] for o in outs], -2).reshape(shape + (dim,)))
+        else:
+            out = (torch.stack(outs, dim=-1) if on_device else np.stack(outs, axis=-1)).reshape(shape)
         info = SolveInfo(iters=np.concatenate([i.iters for i in infos]), inc=np.concatenate([i.inc for i in infos]),
                          done=np.concatenate([i.done for i in infos]), history=None, energy=None,
                          launched=max(i.launched for i in infos))
@@ -287,9 +303,22 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
 
     eng = Engine(shape[:dim], nb=nb, dtype=cdtype, device=device)
     lib, g = eng.lib, eng.geom
-    hier = MGHierarchy(eng, solver.depth, solver.smoother_iterations, omega, ell)
+    hier = MGHierarchy(eng, solver.depth, solver.smoother_iterations, omega, ell,
+                       heterogeneous=getattr(solver, "heterogeneous", False), full_shape=shape)
     f = eng.upload(img)
-    u = f.clone()
+    x0_db = None
+    if x0 is not None:  # split_bregman_tvd.py:93-97
+        u0, d0, b0 = (v if _is_tensor(v) else np.asarray(v) for v in x0)
+        assert tuple(u0.shape) == shape and tuple(d0.shape) == (*shape, dim) and tuple(b0.shape) == (*shape, dim)
+        u = eng.upload(_cast(u0, img_dtype))
+        d_pl, b_pl = eng.empty_fields(dim), eng.empty_fields(dim)
+        for a in range(dim):
+            sl = slice(a * eng.batch_elems, (a + 1) * eng.batch_elems)
+            d_pl[sl] = eng.upload(_cast(d0[..., a], img_dtype))
+            b_pl[sl] = eng.upload(_cast(b0[..., a], img_dtype))
+        x0_db = (d_pl, b_pl)
+    else:  # :99-101
+        u = f.clone()
     t = eng.zero_fields(dim)
     rhs = eng.empty_fields(1)
     ws = eng.op_workspace()
@@ -310,13 +339,22 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
                 if it == 0:  # split_bregman_tvd.py:103-104 (u = img at this point)
                     for b in range(nb):
                         print(f"The energy functional starts at {energy[b]}")
-            lib.check(lib.rhs(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(omc), C.byref(elc), f.data_ptr(),
-                              t.data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, eng.stream()), "tvdk_rhs")  # :84-89
+            if x0_db is not None and it == 0:  # an arbitrary warm start (d, b) is not the expansion of a compressed state
+                lib.check(lib.rhs_explicit(C.byref(g), C.byref(omc), C.byref(elc), f.data_ptr(), x0_db[0].data_ptr(),
+                                           x0_db[1].data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, eng.stream()), "tvdk_rhs_explicit")
+            else:
+                lib.check(lib.rhs(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(omc), C.byref(elc), f.data_ptr(),
+                                  t.data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, eng.stream()), "tvdk_rhs")  # :84-89
         x = hier.solve(u, rhs, solver.maxiter, solver.tol)  # :133
         with device_guard(eng.device):
-            lib.check(lib.shrink(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(elc), x.data_ptr(), u.data_ptr(),
-                                 u.data_ptr(), t.data_ptr(), t.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, eng.stream()),
-                      "tvdk_shrink")  # :136-146, :161, :170
+            if x0_db is not None and it == 0:
+                lib.check(lib.shrink_explicit(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(elc), x.data_ptr(),
+                                              u.data_ptr(), u.data_ptr(), x0_db[1].data_ptr(), tcs, t.data_ptr(), tcs,
+                                              sums.data_ptr(), wsp, wsn, eng.stream()), "tvdk_shrink_explicit")
+            else:
+                lib.check(lib.shrink(C.byref(g), 1 if isotropic else 0, C.byref(muc), C.byref(elc), x.data_ptr(), u.data_ptr(),
+                                     u.data_ptr(), t.data_ptr(), t.data_ptr(), tcs, sums.data_ptr(), wsp, wsn, eng.stream()),
+                          "tvdk_shrink")  # :136-146, :161, :170
         inc_t = torch.sqrt(sums[:nb]) / nrm_f
         iters += 1
         if eps is not None or return_info or verbose_every:
@@ -328,6 +366,16 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
             if eps is not None and float(inc[0]) < eps:  # :173-175 (nb == 1 whenever eps is given)
                 break
     out = eng.unpack(u, img_dtype).reshape(shape) if on_device else eng.download(u, img_dtype, shape)
+    if return_state:
+        if iters == 0 and x0_db is not None:
+            d_pl, b_pl = x0_db
+        else:
+            d_pl, b_pl = eng.expand_state(t, mu, ell, isotropic, full_shape=shape)
+        d_out = eng.components_to_host_order(d_pl, img_dtype, shape)
+        b_out = eng.components_to_host_order(b_pl, img_dtype, shape)
+        if not on_device:
+            d_out, b_out = d_out.cpu().numpy(), b_out.cpu().numpy()
+        out = (out, d_out, b_out)
     if not return_info:
         return out
     inc = inc_t.cpu().numpy().copy() if iters else np.full(nb, np.nan)

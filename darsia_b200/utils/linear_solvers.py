@@ -184,10 +184,14 @@ TVDK_SOLVER_MG = 2  # host-composed (darsia_b200/mg.py); not a tvdk_solve kind
 
 
 class MG(Solver):
-    """V-cycle multigrid with Jacobi smoothing (``mg.py:13-270``), scalar coefficients.
+    """V-cycle multigrid with Jacobi smoothing (``mg.py:13-270``), scalar or per-voxel coefficients.
 
     Same constructor as the reference (``mg.py:25-35``).  The cycle runs on the GPU (``darsia_b200/mg.py``:
     sweeps, residual, restriction, prolongation are libtvdk kernels; the recursion is host logic).
+    ``heterogeneous`` is decided here, from the constructor's coefficients, and never revisited (``mg.py:70-73``):
+    per-voxel coefficients handed to an ``MG()`` built without arrays raise the reference's ``ValueError``.
+    As in the reference, a heterogeneous solve leaves the block-averaged arrays in ``mass_coeff`` /
+    ``diffusion_coeff`` (``mg.py:134-149, 170-192``).
     """
 
     kind = TVDK_SOLVER_MG
@@ -207,6 +211,7 @@ class MG(Solver):
                          verbose=verbose)
         self.depth = depth
         self.smoother_iterations = smoother_iterations
+        self.heterogeneous = isinstance(mass_coeff, np.ndarray) or isinstance(diffusion_coeff, np.ndarray)
 
     def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
         from ..engine import Engine
@@ -225,8 +230,16 @@ class MG(Solver):
         dtype = np.float32 if x0.dtype == np.float32 else np.float64
         nb = int(np.prod(x0.shape[self.dim:], dtype=np.int64))
         eng = Engine(x0.shape[: self.dim], nb=nb, dtype=dtype)
-        hier = MGHierarchy(eng, self.depth, self.smoother_iterations, self.mass_coeff, self.diffusion_coeff)
+        hier = MGHierarchy(eng, self.depth, self.smoother_iterations, self.mass_coeff, self.diffusion_coeff,
+                           heterogeneous=self.heterogeneous, full_shape=x0.shape)
         x = eng.upload(x0.astype(dtype, copy=False))
         b = eng.upload(rhs.astype(dtype, copy=False))
         res = hier.solve(x, b, self.maxiter, self.tol)
-        return eng.download(res, x0.dtype, x0.shape)
+        out = eng.download(res, x0.dtype, x0.shape)
+        if hier.cycles:  # restrict_parameters / prolongate_parameters overwrote the solver's arrays (mg.py:134-149, 170-192)
+            if "omega" in hier.maps:
+                self.mass_coeff = hier.final_coefficient("omega", np.shape(self.mass_coeff)).astype(np.asarray(self.mass_coeff).dtype)
+            if "ell" in hier.maps:
+                self.diffusion_coeff = hier.final_coefficient("ell", np.shape(self.diffusion_coeff)).astype(
+                    np.asarray(self.diffusion_coeff).dtype)
+        return out

@@ -194,6 +194,19 @@ int tvdk_shrink(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, cons
                 int64_t t_comp_stride, double* sum_out, void* workspace, size_t workspace_bytes,
                 void* stream);
 
+/* The same two operators for the FIRST outer iteration after a warm start x0 = (u, d, b)
+ * (split_bregman_tvd.py:93-97): an arbitrary (d, b) need not be the expansion of any compressed state, so
+ * the right-hand side takes d and b and the shrinkage takes b as planar fields (dim components,
+ * `*_comp_stride` elements apart); t_out is the compressed state the following iterations continue from.
+ * (tvdk_solve does the same internally for x0_d / x0_b; these are for host-composed loops such as MG.) */
+int tvdk_rhs_explicit(const tvdk_geom_t* g, const tvdk_coef_t* omega, const tvdk_coef_t* ell, const void* f,
+                      const void* d, const void* b, int64_t db_comp_stride, void* rhs, void* workspace,
+                      size_t workspace_bytes, void* stream);
+int tvdk_shrink_explicit(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu, const tvdk_coef_t* ell,
+                         const void* u_new, const void* u_old, void* u_out, const void* b_in,
+                         int64_t b_comp_stride, void* t_out, int64_t t_comp_stride, double* sum_out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
 /* Expand the compressed state into the reference's d and b (planar fields, dim each). */
 int tvdk_expand_state(const tvdk_geom_t* g, int isotropic, const tvdk_coef_t* mu,
                       const tvdk_coef_t* ell, const void* t, int64_t t_comp_stride, void* d, void* b,
@@ -290,7 +303,8 @@ int tvdk_chambolle(const tvdk_chambolle_t* c, void* stream, int* iters_launched)
 
 /* Multigrid building blocks (darsia.MG, utils/linear_solvers/mg.py:94-242; the V-cycle itself is
  * host logic over these and tvdk_jacobi_sweep):
- *   tvdk_residual:        r = rhs - (omega x - ell Lap x)        (mg.py:212; pass ell / h^2 for spacing h)
+ *   tvdk_residual:        r = rhs - (omega x - ell Lap x)        (mg.py:212; pass ell / h^2 for spacing h; a
+ *                         per-voxel ell multiplies the unit-coefficient Laplacian from outside, mg.py:104-106)
  *   tvdk_mg_restrict:     coarse = pairwise averages of fine     (mg.py:107-132; coarse extents = fine / 2)
  *   tvdk_mg_prolong_add:  fine += repeat-twice(coarse), edge-padded for odd extents (mg.py:226-239)
  * `fine` and `coarse` describe two grids of the same dim / dtype / nb. */
@@ -359,6 +373,13 @@ int tvdk_slab_error(const void* arena, void* stream, int64_t* seq_out);
 int tvdk_slab_exchange(int nlocal, const tvdk_geom_t* const* geoms, const tvdk_slab_comm_t* const* comms,
                        int nfields, const void* const* const* fields, int n_up, int n_down,
                        void* const* streams, const int* devices);
+
+/* Diagnostics for measurements (bench.py's in-step kernel time): from now on every launch of a kernel whose C++ type
+ * name contains `kernel_substring` (e.g. "KCgFused") is bracketed by a pair of CUDA events on the stream it is launched
+ * on; NULL or "" disarms.  tvdk_profile_read waits for the recorded events, returns their number and summed duration,
+ * frees them and disarms.  Disarmed -- the normal state -- a launch pays one flag load. */
+int tvdk_profile_arm(const char* kernel_substring);
+int tvdk_profile_read(int64_t* launches, double* total_ms);
 
 /* Peer mapping helpers for one-process-per-GPU runs (CUDA IPC; thin wrappers so that callers need no CUDA
  * bindings): export a 64-byte handle + offset for a device pointer / open one exported by another process

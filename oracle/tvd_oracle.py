@@ -277,8 +277,18 @@ class MG(Solver):
     by the same smoother from a zero guess (mg.py:218-219); (iii) odd extents lose their last entry in
     the restriction and get it back by edge padding (mg.py:229-238); (iv) with ``tol`` the PREVIOUS
     iterate is returned on convergence and the increment is normalised by ``||x0||`` (mg.py:257-270).
-    Per-voxel coefficients are not restated: the reference overwrites them with their restricted /
-    prolongated (block-averaged) versions during the first V-cycle (mg.py:134-149, 170-192).
+
+    Per-voxel coefficients (``heterogeneous``, mg.py:70-73: decided ONCE, from the constructor's arguments --
+    ``update_params`` does not revisit it, so an ``MG()`` built without arrays that later receives per-voxel
+    coefficients from ``split_bregman_tvd`` fails on the first coarse grid with NumPy's broadcasting
+    ``ValueError``, restated by ``_check_coefficients``).  With the flag set the reference (v) restricts the
+    coefficient arrays on the way down and prolongates + edge-pads them on the way up, OVERWRITING
+    ``mass_coeff`` / ``diffusion_coeff`` (mg.py:134-149, 170-192, 215-217, 229-232): the presmoother and the
+    residual of the first cycle see the original arrays (and their pairwise averages on the coarse levels),
+    every later step sees block averages; (vi) builds a fresh Jacobi smoother at each of those two points,
+    whose diagonal is cached at the spacing ``h`` of ITS first call -- unlike quirk (i), the coarse smoothers of the
+    heterogeneous cycle do see ``h``; (vii) multiplies a per-voxel ``diffusion_coeff`` AFTER the unit-coefficient
+    Laplacian in the residual operator (mg.py:104-106), unlike CG's ``laplace(x, diffusion_coeff=ell)``.
     """
 
     def __init__(self, depth: int = 2, smoother_iterations: int = 5, maxiter: int = 100, tol: Optional[float] = None,
@@ -288,10 +298,61 @@ class MG(Solver):
                          verbose=verbose)
         self.depth = depth
         self.smoother_iterations = smoother_iterations
+        self.heterogeneous = isinstance(mass_coeff, np.ndarray) or isinstance(diffusion_coeff, np.ndarray)  # mg.py:70-72
+        self._sm_diag = None
 
-    def _check_scalar(self) -> None:
-        if np.ndim(self.mass_coeff) != 0 or np.ndim(self.diffusion_coeff) != 0:
-            raise NotImplementedError("MG: scalar mass / diffusion coefficients only (see the class docstring)")
+    def reset(self) -> None:
+        self._sm_diag = None  # (a fresh MG holds a fresh smoother, mg.py:60-66)
+
+    def _check_coefficients(self) -> None:
+        if not self.heterogeneous and (np.ndim(self.mass_coeff) != 0 or np.ndim(self.diffusion_coeff) != 0):
+            raise ValueError("MG was constructed without per-voxel coefficients (heterogeneous = False, mg.py:70-73) but "
+                             "holds arrays now: the reference fails on the coarse grid (operands could not be broadcast)")
+
+    # -- heterogeneous cycle (mg.py:134-149, 170-192, 194-243 with self.heterogeneous) -------------------------
+    def _new_smoother(self) -> None:
+        """``da.Jacobi(mass_coeff=..., diffusion_coeff=...)`` of mg.py:143-148 / 186-191: nothing cached yet."""
+        self._sm_diag = None
+
+    def _smooth_h(self, x0: np.ndarray, rhs: np.ndarray, h) -> np.ndarray:
+        """``self.smoother(x0, rhs, h=h)`` (jacobi.py:74-116): diag / diag_scaled cached at the first call's ``h``."""
+        if self._sm_diag is None:
+            diag = self.mass_coeff + self.diffusion_coeff * 2 * self.dim / h**2  # jacobi.py:72
+            self._sm_diag = (diag, np.divide(diag, self.diffusion_coeff / h**2))  # :101-106
+        diag, diag_scaled = self._sm_diag
+        rhs_scaled = np.divide(rhs, diag)
+        x = x0
+        for _ in range(self.smoother_iterations):
+            x = rhs_scaled + np.divide(neighbor_accumulation(x), diag_scaled)
+        return x
+
+    def _restrict_parameters(self) -> None:
+        if isinstance(self.mass_coeff, np.ndarray):
+            self.mass_coeff = mg_restriction(self.mass_coeff, self.dim)
+        if isinstance(self.diffusion_coeff, np.ndarray):
+            self.diffusion_coeff = mg_restriction(self.diffusion_coeff, self.dim)
+        self._new_smoother()
+
+    def _prolongate_parameters(self, pad) -> None:
+        if isinstance(self.mass_coeff, np.ndarray):
+            self.mass_coeff = np.pad(mg_prolongation(self.mass_coeff, self.dim), pad, "edge")
+        if isinstance(self.diffusion_coeff, np.ndarray):
+            self.diffusion_coeff = np.pad(mg_prolongation(self.diffusion_coeff, self.dim), pad, "edge")
+        self._new_smoother()
+
+    def v_cycle_hetero(self, x0: np.ndarray, rhs: np.ndarray, depth: int, h=1) -> np.ndarray:
+        x = self._smooth_h(x0, rhs, h)  # mg.py:209
+        r = mg_restriction(rhs - self.operator(x, h), self.dim)  # :212-215
+        self._restrict_parameters()  # :216-217
+        if depth == 0:  # :220-225
+            eps = self._smooth_h(np.zeros_like(r), r, 2 * h)
+        else:
+            eps = self.v_cycle_hetero(np.zeros_like(r), r, depth - 1, 2 * h)
+        eps = mg_prolongation(eps, self.dim)  # :228
+        pad = tuple((0, x.shape[i] - eps.shape[i]) for i in range(self.dim))  # :231
+        self._prolongate_parameters(pad)  # :232-233
+        x = x + np.pad(eps, pad, "edge")  # :234-239
+        return self._smooth_h(x, rhs, h)  # :242
 
     def smooth(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
         omega, ell, dim = self.mass_coeff, self.diffusion_coeff, self.dim
@@ -326,14 +387,15 @@ class MG(Solver):
         return self.smooth(x, rhs)  # :242
 
     def __call__(self, x0: np.ndarray, rhs: np.ndarray) -> np.ndarray:
-        self._check_scalar()
+        self._check_coefficients()
+        cycle = self.v_cycle_hetero if self.heterogeneous else self.v_cycle
         x = x0
         if self.tol is None:  # mg.py:257-259
             for _ in range(self.maxiter):
-                x = self.v_cycle(x, rhs, self.depth)
+                x = cycle(x, rhs, self.depth)
         else:  # :260-269
             for _ in range(self.maxiter):
-                x_new = self.v_cycle(x, rhs, self.depth)
+                x_new = cycle(x, rhs, self.depth)
                 nrm = np.linalg.norm(x_new - x) / np.linalg.norm(x0)
                 if nrm < self.tol:
                     break

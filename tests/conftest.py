@@ -49,6 +49,11 @@ def run_case_with(api, arrays, params):
     has_x0 = p.pop("x0")
     spec = dict(p.pop("solver"))
     kind = spec.pop("kind")
+    if spec.pop("hetero", False):  # MG decides `heterogeneous` from its constructor arguments (mg.py:70-73)
+        if "coef_omega" in arrays:
+            spec["mass_coeff"] = arrays["coef_omega"].copy()
+        if "coef_ell" in arrays:
+            spec["diffusion_coeff"] = arrays["coef_ell"].copy()
     solver = {"jacobi": api.Jacobi, "cg": api.CG, "mg": getattr(api, "MG", None)}[kind](**spec)
     kwargs = dict(p)
     kwargs.pop("parity_tol", None)

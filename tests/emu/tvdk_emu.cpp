@@ -165,6 +165,14 @@ int tvdk_ipc_open(const unsigned char h[64], int64_t off, void** out) {
   return 0;
 }
 int tvdk_ipc_close(void*, int64_t) { return 0; }
+// (no device clock here: nothing is ever recorded)
+int tvdk_profile_arm(const char*) { return 0; }
+int tvdk_profile_read(int64_t* launches, double* total_ms) {
+  if (!launches || !total_ms) return tvdk::fail(TVDK_ERR_INVALID, "NULL pointer");
+  *launches = 0;
+  *total_ms = 0.0;
+  return 0;
+}
 int tvdk_enable_peer(int) { return 0; }
 
 extern "C" int tvdk_is_emulator(void) { return 1; }

@@ -59,9 +59,14 @@ def coeff_field(shape, seed, lo, hi, zero_frac=0.0):
     return c
 
 
-def make_solver(da, spec):
+def make_solver(da, spec, arrays=None):
     kind = spec["kind"]
-    kw = {k: v for k, v in spec.items() if k != "kind"}
+    kw = {k: v for k, v in spec.items() if k not in ("kind", "hetero")}
+    if spec.get("hetero"):  # MG decides `heterogeneous` from its CONSTRUCTOR arguments (mg.py:70-73)
+        if "omega" in arrays:
+            kw["mass_coeff"] = arrays["omega"]
+        if "ell" in arrays:
+            kw["diffusion_coeff"] = arrays["ell"]
     return {"jacobi": da.Jacobi, "cg": da.CG, "mg": da.MG}[kind](**kw)
 
 
@@ -145,6 +150,21 @@ case("aniso3d_mg", (13, 18, 11), 47, mu=0.1, omega=1.0, ell=1.0, dim=3, max_num_
      solver={"kind": "mg", "depth": 1, "smoother_iterations": 2, "maxiter": 1})
 case("aniso2d_mg_f32", (37, 52), 48, dtype="float32", mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=6,
      isotropic=False, solver={"kind": "mg", "depth": 2, "smoother_iterations": 3, "maxiter": 1})
+# MG with per-voxel coefficients (mg.py:134-149, 170-192: restricted on the way down, block averages afterwards),
+# a per-voxel mu with scalar omega / ell, and a warm start
+case("aniso2d_mg_hetero", (37, 52), 60, arrays={"omega": (0.5, 2.0, 0.0), "ell": (0.5, 1.5, 0.0)}, mu=0.1, dim=2,
+     max_num_iter=6, isotropic=False, solver={"kind": "mg", "depth": 2, "smoother_iterations": 3, "maxiter": 2, "hetero": True})
+case("iso2d_mg_hetero_omega", (41, 36), 61, arrays={"omega": (0.5, 2.0, 0.0)}, mu=0.1, ell=1.0, dim=2,
+     max_num_iter=6, isotropic=True, solver={"kind": "mg", "depth": 1, "smoother_iterations": 4, "maxiter": 1, "hetero": True})
+case("aniso3d_mg_hetero", (13, 18, 11), 62, arrays={"omega": (0.5, 2.0, 0.0), "ell": (0.5, 1.5, 0.0)}, mu=0.1, dim=3,
+     max_num_iter=4, isotropic=False, solver={"kind": "mg", "depth": 1, "smoother_iterations": 2, "maxiter": 2, "hetero": True})
+case("aniso2d_mg_hetero_f32", (37, 52), 63, dtype="float32", arrays={"omega": (0.5, 2.0, 0.0), "ell": (0.5, 1.5, 0.0)}, mu=0.1,
+     dim=2, max_num_iter=5, isotropic=False,
+     solver={"kind": "mg", "depth": 1, "smoother_iterations": 3, "maxiter": 1, "hetero": True})
+case("aniso2d_mg_mu_map", (37, 52), 64, arrays={"mu": (0.05, 0.1, 0.1)}, omega=1.0, ell=1.0, dim=2, max_num_iter=6,
+     isotropic=False, solver={"kind": "mg", "depth": 1, "smoother_iterations": 3, "maxiter": 2})
+case("aniso2d_mg_x0", (24, 31), 65, x0=True, mu=0.1, omega=1.0, ell=1.0, dim=2, max_num_iter=5, isotropic=False,
+     solver={"kind": "mg", "depth": 1, "smoother_iterations": 3, "maxiter": 1})
 # --- adaptive ell schedule (split_bregman_tvd.py:149-158) -------------------------------
 # parity_tol: ell = 1/|grad u| amplifies round-off wherever the gradient is tiny -- the reference's
 # own output moves by 2e-7 (Jacobi) / 1e-5 (CG) / 2e-3 (fp32) rel. L2 when its input is perturbed by
@@ -173,7 +193,7 @@ def run_case(da, c):
         arrays[k] = coeff_field(c["shape"], 1000 + c["seed"] * 10 + i, lo, hi, zf).astype(dtype)
     kwargs = dict(params)
     kwargs.pop("parity_tol", None)
-    kwargs["solver"] = make_solver(da, params["solver"])
+    kwargs["solver"] = make_solver(da, params["solver"], arrays)
     every = kwargs.pop("adaptive_every", None)
     if every:
         kwargs["adaptive"] = lambda it, every=every: it % every == every - 1
@@ -230,6 +250,12 @@ def operator_cases(da):
             store[f"{tag}_mg_prolong"] = mg.prolongation(mg.restriction(x))
             store[f"{tag}_mg_operator_h2"] = mg.operator(x, h=2)
             store[f"{tag}_mg2"] = mg(x0=x.copy(), rhs=rhs)
+            om = 0.5 + rng.random(shape)
+            store[f"{tag}_om"] = om
+            mgh = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=om.copy(), diffusion_coeff=ell.copy())
+            store[f"{tag}_mg_operator_h2_hetero"] = mgh.operator(x, h=2)
+            store[f"{tag}_mg2_hetero"] = mgh(x0=x.copy(), rhs=rhs)
+            store[f"{tag}_mg2_hetero_om_after"] = mgh.mass_coeff  # the block averages the solver is left with
     return store
 
 

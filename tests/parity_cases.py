@@ -168,3 +168,50 @@ def chambolle_cases():
         ((2, 1, 7), f8, 0.1, 0.0, 5),
         ((24, 40, 3), f8, 0.2, 2e-4, 1),
     ]
+
+
+def check_mg_standalone(da, tag, dim):
+    """darsia_b200.MG standalone (as H1_regularization would use it) against the reference's MG outputs in
+    operators.npz: scalar coefficients, the refused cases, and per-voxel coefficients given to the constructor
+    (mg.py:70-73: restricted on the way down, block averages afterwards -- which the solver object is left holding,
+    mg.py:134-149, 170-192)."""
+    import os
+
+    import pytest
+
+    golden = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "operators.npz")
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    with np.load(golden) as z:
+        x, rhs, ref = z[f"{tag}_x"], z[f"{tag}_rhs"], z[f"{tag}_mg2"]
+        om, ell, refh, om_after = z[f"{tag}_om"], z[f"{tag}_ell"], z[f"{tag}_mg2_hetero"], z[f"{tag}_mg2_hetero_om_after"]
+    mg = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
+    assert rel(mg(x.copy(), rhs), ref) <= 1e-13
+    with pytest.raises(ValueError):  # a coarse grid would be empty (the reference crashes there)
+        da.MG(depth=3, dim=dim, mass_coeff=1.0, diffusion_coeff=1.0)(x, rhs)
+    mgh = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=om.copy(), diffusion_coeff=ell.copy())
+    assert rel(mgh(x.copy(), rhs), refh) <= 1e-13
+    np.testing.assert_allclose(mgh.mass_coeff, om_after, rtol=0, atol=1e-15)
+    late = da.MG(depth=1, dim=dim)  # heterogeneous was decided at construction: the reference fails on the coarse grid
+    late.update_params(mass_coeff=om, diffusion_coeff=1.0)
+    with pytest.raises(ValueError):
+        late(x, rhs)
+
+
+def check_mg_warm_start(da, oracle):
+    """MG as the inner solver: 7 iterations == 4 iterations, (u, d, b) handed over as x0, 3 more; then batched with a
+    tolerance (one problem at a time) from an arbitrary (not self-consistent) warm start, against the oracle."""
+    rel = lambda a, b: float(np.linalg.norm(a - b) / np.linalg.norm(b))  # noqa: E731
+    img = phantom((24, 31, 2), 3)
+    kw = dict(mu=0.1, omega=0.8, ell=1.0, dim=2, isotropic=True)
+    mk = lambda m, **k: m.MG(depth=1, smoother_iterations=2, maxiter=2, **k)  # noqa: E731
+    ref7 = oracle.split_bregman_tvd(img, max_num_iter=7, solver=mk(oracle), **kw)
+    u4, d4, b4 = da.split_bregman_tvd(img, max_num_iter=4, solver=mk(da), return_state=True, **kw)
+    assert d4.shape == (*img.shape, 2) and b4.shape == (*img.shape, 2)
+    out = da.split_bregman_tvd(img, max_num_iter=3, solver=mk(da), x0=(u4, d4, b4), **kw)
+    assert rel(out, ref7) <= 1e-13
+    rng = np.random.default_rng(1)
+    x0 = (np.clip(img + 0.05 * rng.standard_normal(img.shape), 0, 1), 0.05 * rng.standard_normal((*img.shape, 2)),
+          0.05 * rng.standard_normal((*img.shape, 2)))
+    ref = oracle.split_bregman_tvd(img, max_num_iter=3, solver=mk(oracle, tol=1e-3), x0=tuple(v.copy() for v in x0), **kw)
+    out, d, b = da.split_bregman_tvd(img, max_num_iter=3, solver=mk(da, tol=1e-3), x0=x0, return_state=True, **kw)
+    assert rel(out, ref) <= 1e-13 and d.shape == b.shape == (*img.shape, 2)

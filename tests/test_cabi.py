@@ -107,6 +107,11 @@ def test_argument_validation_needs_no_gpu():
     g = geom()
     assert lib.fused_jacobi1(ctypes.byref(g), 0, None, None, None, 8, 16, 16, 24, 32, 0, None, None, 0, None) == ERR_INVALID
     assert b"out-of-place" in lib.last_error()
+    assert lib.rhs_explicit(ctypes.byref(g), None, None, 8, None, 16, 0, 24, None, 0, None) == ERR_INVALID
+    assert b"both d and b" in lib.last_error()
+    assert lib.shrink_explicit(ctypes.byref(g), 0, None, None, 8, 16, 16, None, 0, 24, 0, None, None, 0, None) == ERR_INVALID
+    assert b"b_in" in lib.last_error()
+    assert lib.ipc_close(None, 0) == ERR_INVALID
     gc = geom(n=(7, 12, 1))  # not fine / 2
     assert lib.mg_restrict(ctypes.byref(g), ctypes.byref(gc), 8, 16, None) == ERR_INVALID and b"coarse extent" in lib.last_error()
     c = _cabi.Chambolle()

@@ -12,7 +12,7 @@ import fuzz_cases
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from emu.harness import emulated
-from parity_cases import (adaptive_cases, cg_fixed_count_cases, chambolle_cases, jacobi1_pair_cases, jacobi_blocked_cases,
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, check_mg_standalone, check_mg_warm_start, chambolle_cases, jacobi1_pair_cases, jacobi_blocked_cases,
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
@@ -137,16 +137,11 @@ from conftest import GOLDEN_DIR  # noqa: E402
 
 @pytest.mark.parametrize("tag,dim", [("2d", 2), ("3d", 3)])
 def test_mg_standalone_and_errors(tag, dim):
-    """darsia_b200.MG standalone (as H1_regularization would use it) against the reference's MG output; the
-    cases the GPU path refuses."""
-    with np.load(f"{GOLDEN_DIR}/operators.npz") as z:
-        x, rhs, ref = z[f"{tag}_x"], z[f"{tag}_rhs"], z[f"{tag}_mg2"]
-    mg = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
-    assert rel_l2(mg(x.copy(), rhs), ref) <= 1e-13
-    with pytest.raises(NotImplementedError):  # per-voxel coefficients (the reference block-averages them)
-        da.MG(dim=dim, mass_coeff=np.ones_like(x), diffusion_coeff=1.0)(x, rhs)
-    with pytest.raises(ValueError):  # a coarse grid would be empty (the reference crashes there)
-        da.MG(depth=3, dim=dim, mass_coeff=1.0, diffusion_coeff=1.0)(x, rhs)
+    check_mg_standalone(da, tag, dim)
+
+
+def test_mg_warm_start_and_state_round_trip():
+    check_mg_warm_start(da, oracle)
 
 
 def test_mg_inner_solver_batched_and_stopping():

@@ -208,16 +208,15 @@ from conftest import GOLDEN_DIR  # noqa: E402
 
 @pytest.mark.parametrize("tag,dim", [("2d", 2), ("3d", 3)])
 def test_mg_standalone_and_errors(da, tag, dim):
-    """darsia_b200.MG standalone (as H1_regularization would use it) against the reference's MG output; the
-    cases the GPU path refuses."""
-    with np.load(f"{GOLDEN_DIR}/operators.npz") as z:
-        x, rhs, ref = z[f"{tag}_x"], z[f"{tag}_rhs"], z[f"{tag}_mg2"]
-    mg = da.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
-    assert rel_l2(mg(x.copy(), rhs), ref) <= 1e-13
-    with pytest.raises(NotImplementedError):  # per-voxel coefficients (the reference block-averages them)
-        da.MG(dim=dim, mass_coeff=np.ones_like(x), diffusion_coeff=1.0)(x, rhs)
-    with pytest.raises(ValueError):  # a coarse grid would be empty (the reference crashes there)
-        da.MG(depth=3, dim=dim, mass_coeff=1.0, diffusion_coeff=1.0)(x, rhs)
+    from parity_cases import check_mg_standalone
+
+    check_mg_standalone(da, tag, dim)
+
+
+def test_mg_warm_start_and_state_round_trip(da):
+    from parity_cases import check_mg_warm_start
+
+    check_mg_warm_start(da, oracle)
 
 
 def test_mg_inner_solver_batched_and_stopping(da):

@@ -74,8 +74,17 @@ def test_mg_operator_level(ops, tag, dim):
     mg = oracle.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=1.3, diffusion_coeff=0.7)
     np.testing.assert_allclose(mg.operator(x, 2), ops[f"{tag}_mg_operator_h2"], rtol=0, atol=1e-15)
     assert rel_l2(mg(x.copy(), rhs), ops[f"{tag}_mg2"]) < 1e-14
-    with pytest.raises(NotImplementedError):
-        oracle.MG(dim=dim, mass_coeff=np.ones_like(x), diffusion_coeff=1.0)(x, rhs)
+    # per-voxel coefficients: ell multiplies the Laplacian from outside, the solver is left with block averages
+    om, ell = ops[f"{tag}_om"], ops[f"{tag}_ell"]
+    mgh = oracle.MG(depth=1, smoother_iterations=2, maxiter=2, dim=dim, mass_coeff=om.copy(), diffusion_coeff=ell.copy())
+    np.testing.assert_allclose(mgh.operator(x, 2), ops[f"{tag}_mg_operator_h2_hetero"], rtol=0, atol=1e-15)
+    assert rel_l2(mgh(x.copy(), rhs), ops[f"{tag}_mg2_hetero"]) < 1e-14
+    np.testing.assert_array_equal(mgh.mass_coeff, ops[f"{tag}_mg2_hetero_om_after"])
+    # an MG built without arrays that holds arrays later fails like the reference does (on the first coarse grid)
+    late = oracle.MG(depth=1, dim=dim)
+    late.update_params(mass_coeff=om, diffusion_coeff=1.0)
+    with pytest.raises(ValueError):
+        late(x, rhs)
 
 
 def test_oracle_cg_is_scipy_recurrence():
