@@ -126,13 +126,16 @@ class Engine:
     _STAGE: dict = {}  # (thread, device index, dtype) -> two pinned chunks, reused by every engine of that thread
     _STAGE_POOL = None
     # host threads copying into the pinned chunks / chunk size (tools/h2d_probe.py measures both on a given box)
-    STAGE_THREADS = int(os.environ.get("DARSIA_B200_STAGE_THREADS", "1"))
+    # (B200 box, 672 MB fp64: 1 thread 12 GB/s, 4 threads 34 GB/s, pinned source 55 GB/s -- profiles/r2_h2d_probe.txt;
+    #  the default leaves two cores per rank of a one-process-per-GPU job)
+    STAGE_THREADS = int(os.environ.get("DARSIA_B200_STAGE_THREADS", "0")) or max(
+        1, min(4, (os.cpu_count() or 1) // (2 * max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))))
     STAGE_CHUNK_MB = int(os.environ.get("DARSIA_B200_STAGE_CHUNK_MB", "16"))
 
     def _stage_pageable(self, t: torch.Tensor) -> torch.Tensor:
         """A large PAGEABLE host array -> device through two pinned chunks: the host memcpy of chunk i + 1 overlaps the
-        DMA of chunk i (a plain ``cudaMemcpy`` from pageable memory stages internally without that overlap: measured
-        3.7 GB/s on the 672 MB image of BASELINE configs[1])."""
+        DMA of chunk i, and ``STAGE_THREADS`` host threads share each memcpy (a plain ``cudaMemcpy`` from pageable memory
+        stages internally on one thread: 11 GB/s on the 672 MB image of BASELINE configs[1])."""
         chunk = (Engine.STAGE_CHUNK_MB << 20) // t.element_size()
         nt = max(1, Engine.STAGE_THREADS)
         import threading
