@@ -207,6 +207,7 @@ SIGNATURES = {
     "tvdk_slab_error": (C.c_int, [_VP, _VP, C.POINTER(_I64)]),
     "tvdk_slab_exchange": (C.c_int, [_I, C.POINTER(_PG), C.POINTER(C.POINTER(SlabComm)), _I, C.POINTER(C.POINTER(_VP)),
                                      _I, _I, C.POINTER(_VP), C.POINTER(C.c_int)]),
+    "tvdk_set_pdl": (C.c_int, [_I]),
     "tvdk_profile_arm": (C.c_int, [C.c_char_p]),
     "tvdk_profile_read": (C.c_int, [C.POINTER(_I64), C.POINTER(C.c_double)]),
     "tvdk_ipc_export": (C.c_int, [_VP, C.POINTER(C.c_ubyte * 64), C.POINTER(_I64)]),

@@ -6,6 +6,7 @@
 #include <stdarg.h>
 #include <stdio.h>
 
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -17,6 +18,10 @@
 #include <vector>
 
 #include "tvdk_core.h"
+
+#ifndef TVDK_PDL_DEFAULT
+#define TVDK_PDL_DEFAULT 0
+#endif
 
 // NVTX ranges around the solves (header-only NVTX3: a no-op unless a profiler is attached)
 #include <nvtx3/nvToolsExt.h>
@@ -70,6 +75,16 @@ struct has_unroll2 : std::false_type {};
 template <class K>
 struct has_unroll2<K, std::void_t<decltype(K::UNROLL2)>> : std::bool_constant<K::UNROLL2> {};
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may become RESIDENT while its predecessor in the stream drains; `griddepcontrol.wait` holds it until the predecessor
+// has completed and its writes are visible (a no-op for a plain launch), `launch_dependents` then lets the successor
+// do the same behind this grid.  Nothing is read or written before the wait, so the data flow is that of plain
+// stream order; what is saved is the launch latency and the block-scheduling ramp between two launches.
+__device__ __forceinline__ void pdl_prologue() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // kernels may cap their block size (K::MAXT) to get more than 128 registers per thread
 template <class K, typename = void>
 struct max_threads : std::integral_constant<int, kMaxThreads> {};
@@ -82,6 +97,7 @@ template <class K>
 __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel(const typename K::Args a, double* partials,
                                                             unsigned* counters) {
   extern __shared__ __align__(16) unsigned char smem[];
+  pdl_prologue();
   LaunchCtx lc;
   lc.tx = threadIdx.x; lc.ty = threadIdx.y; lc.ntx = blockDim.x; lc.nty = blockDim.y;
   lc.bx = blockIdx.x; lc.by = chunk_index(a.g); lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
@@ -165,6 +181,7 @@ template <class K>
 __global__ void __launch_bounds__(max_threads<K>::value) tvdk_kernel_tma(const __grid_constant__ typename K::Args a,
                                                                          double* partials, unsigned* counters) {
   extern __shared__ __align__(128) unsigned char smem_tma[];
+  pdl_prologue();
   LaunchCtx lc;
   lc.tx = threadIdx.x; lc.ty = threadIdx.y; lc.ntx = blockDim.x; lc.nty = blockDim.y;
   lc.bx = blockIdx.x; lc.by = chunk_index(a.g); lc.bz = blockIdx.z; lc.nbx = gridDim.x; lc.nby = gridDim.y;
@@ -269,6 +286,24 @@ struct ProfScope {
   }
 };
 
+// launch mode of the march / TMA kernels: plain stream order, or programmatic dependent launch (tvdk_set_pdl, TVDK_PDL)
+static bool pdl_default() {
+  const char* e = getenv("TVDK_PDL");
+  return e ? atoi(e) != 0 : TVDK_PDL_DEFAULT != 0;
+}
+static std::atomic<bool> g_pdl{pdl_default()};
+static void pdl_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* at, dim3 grid, dim3 block, size_t smem, void* stream) {
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+}
+
 template <class K>
 int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, size_t smem, void* stream,
            double* partials, unsigned* counters) {
@@ -284,6 +319,14 @@ int launch(const typename K::Args& a, int gx, int gy, int gz, int ntx, int nty, 
     }
   }
   dim3 grid(gx, gy, gz), block(ntx, nty, 1);
+  if (g_pdl.load(std::memory_order_relaxed)) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    pdl_config(cfg, at, grid, block, smem, stream);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tvdk_kernel<K>, a, partials, counters);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch (programmatic dependent launch)");
+    return 0;
+  }
   tvdk_kernel<K><<<grid, block, smem, (cudaStream_t)stream>>>(a, partials, counters);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
@@ -304,6 +347,14 @@ int launch_tma(const typename K::Args& a, int gx, int gy, int gz, int ntx, int n
     }
   }
   dim3 grid(gx, gy, gz), block(ntx, nty, 1);
+  if (g_pdl.load(std::memory_order_relaxed)) {
+    cudaLaunchConfig_t cfg;
+    cudaLaunchAttribute at[1];
+    pdl_config(cfg, at, grid, block, smem, stream);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tvdk_kernel_tma<K>, a, partials, counters);
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch (TMA, programmatic dependent launch)");
+    return 0;
+  }
   tvdk_kernel_tma<K><<<grid, block, smem, (cudaStream_t)stream>>>(a, partials, counters);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch (TMA)");
@@ -613,6 +664,11 @@ static int tma_encode(TmaMap* m, const void* base, int esize, long long nx, long
 }
 }  // namespace backend
 }  // namespace tvdk
+
+int tvdk_set_pdl(int on) {
+  const bool was = tvdk::backend::g_pdl.exchange(on != 0);
+  return was ? 1 : 0;
+}
 
 int tvdk_profile_arm(const char* kernel_substring) {
   using namespace tvdk;

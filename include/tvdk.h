@@ -374,6 +374,12 @@ int tvdk_slab_exchange(int nlocal, const tvdk_geom_t* const* geoms, const tvdk_s
                        int nfields, const void* const* const* fields, int n_up, int n_down,
                        void* const* streams, const int* devices);
 
+/* Launch mode of the compute kernels, process-wide: 0 = plain stream order, 1 = programmatic dependent launch (the
+ * next kernel's thread blocks become resident while the previous kernel drains and are held by
+ * `griddepcontrol.wait` until it has completed: same data flow, shorter gaps between launches).  Returns the
+ * previous mode.  Initial value: environment variable TVDK_PDL, else the build's default. */
+int tvdk_set_pdl(int on);
+
 /* Diagnostics for measurements (bench.py's in-step kernel time): from now on every launch of a kernel whose C++ type
  * name contains `kernel_substring` (e.g. "KCgFused") is bracketed by a pair of CUDA events on the stream it is launched
  * on; NULL or "" disarms.  tvdk_profile_read waits for the recorded events, returns their number and summed duration,

@@ -165,6 +165,7 @@ int tvdk_ipc_open(const unsigned char h[64], int64_t off, void** out) {
   return 0;
 }
 int tvdk_ipc_close(void*, int64_t) { return 0; }
+int tvdk_set_pdl(int) { return 0; }  // (no launches to overlap)
 // (no device clock here: nothing is ever recorded)
 int tvdk_profile_arm(const char*) { return 0; }
 int tvdk_profile_read(int64_t* launches, double* total_ms) {
