@@ -20,7 +20,7 @@
 #include "tvdk_core.h"
 
 #ifndef TVDK_PDL_DEFAULT
-#define TVDK_PDL_DEFAULT 0
+#define TVDK_PDL_DEFAULT 1
 #endif
 
 // NVTX ranges around the solves (header-only NVTX3: a no-op unless a profiler is attached)
