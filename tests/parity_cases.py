@@ -215,3 +215,30 @@ def check_mg_warm_start(da, oracle):
     ref = oracle.split_bregman_tvd(img, max_num_iter=3, solver=mk(oracle, tol=1e-3), x0=tuple(v.copy() for v in x0), **kw)
     out, d, b = da.split_bregman_tvd(img, max_num_iter=3, solver=mk(da, tol=1e-3), x0=x0, return_state=True, **kw)
     assert rel(out, ref) <= 1e-13 and d.shape == b.shape == (*img.shape, 2)
+
+
+def mg_hetero_cases():
+    """(shape, dim, depth, isotropic, dtype, batch, which maps): MG with per-voxel coefficients across several tiles and
+    odd extents on every level (the restriction drops a row / column, the prolongation pads it back)."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((75, 131), 2, 2, False, f8, (), ("omega", "ell")),
+        ((75, 131), 2, 1, True, f8, (2,), ("omega",)),
+        ((21, 30, 27), 3, 1, False, f8, (), ("omega", "ell")),
+        ((64, 96), 2, 2, False, f4, (), ("ell",)),
+    ]
+
+
+def run_mg_hetero_pair(da, oracle, shape, dim, depth, iso, dtype, batch, which):
+    img = phantom(tuple(shape) + tuple(batch), 5, dtype)
+    kw = dict(mu=0.1, omega=0.8, ell=1.2)
+    if "omega" in which:
+        kw["omega"] = coeff_field(shape, 9, 0.5, 2.0).astype(dtype)
+    if "ell" in which:
+        kw["ell"] = coeff_field(shape, 10, 0.5, 1.5).astype(dtype)
+    mk = lambda m: m.MG(depth=depth, smoother_iterations=3, maxiter=2, dim=dim,  # noqa: E731
+                        mass_coeff=(kw["omega"].copy() if "omega" in which else None),
+                        diffusion_coeff=(kw["ell"].copy() if "ell" in which else None))
+    ref = oracle.split_bregman_tvd(img, dim=dim, max_num_iter=4, isotropic=iso, solver=mk(oracle), **kw)
+    out = da.split_bregman_tvd(img, dim=dim, max_num_iter=4, isotropic=iso, solver=mk(da), **kw)
+    return out, ref

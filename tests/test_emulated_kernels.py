@@ -12,7 +12,7 @@ import fuzz_cases
 import oracle
 from conftest import golden_case_names, load_golden, rel_l2, run_case_with, tolerance_for
 from emu.harness import emulated
-from parity_cases import (adaptive_cases, cg_fixed_count_cases, check_mg_standalone, check_mg_warm_start, chambolle_cases, jacobi1_pair_cases, jacobi_blocked_cases,
+from parity_cases import (adaptive_cases, cg_fixed_count_cases, check_mg_standalone, check_mg_warm_start, mg_hetero_cases, run_mg_hetero_pair, chambolle_cases, jacobi1_pair_cases, jacobi_blocked_cases,
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
@@ -142,6 +142,12 @@ def test_mg_standalone_and_errors(tag, dim):
 
 def test_mg_warm_start_and_state_round_trip():
     check_mg_warm_start(da, oracle)
+
+
+@pytest.mark.parametrize("shape,dim,depth,iso,dtype,batch,which", mg_hetero_cases())
+def test_mg_per_voxel_coefficients(shape, dim, depth, iso, dtype, batch, which):
+    out, ref = run_mg_hetero_pair(da, oracle, shape, dim, depth, iso, dtype, batch, which)
+    assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 2e-5)
 
 
 def test_mg_inner_solver_batched_and_stopping():

@@ -219,6 +219,15 @@ def test_mg_warm_start_and_state_round_trip(da):
     check_mg_warm_start(da, oracle)
 
 
+from parity_cases import mg_hetero_cases, run_mg_hetero_pair  # noqa: E402
+
+
+@pytest.mark.parametrize("shape,dim,depth,iso,dtype,batch,which", mg_hetero_cases())
+def test_mg_per_voxel_coefficients(da, shape, dim, depth, iso, dtype, batch, which):
+    out, ref = run_mg_hetero_pair(da, oracle, shape, dim, depth, iso, dtype, batch, which)
+    assert rel_l2(out, ref) <= (1e-12 if dtype == np.float64 else 2e-5)
+
+
 def test_mg_inner_solver_batched_and_stopping(da):
     """MG inside split_bregman_tvd: channels are independent problems (batched without tol/eps, one at a time
     with them) and the outer eps / MG tol stop each problem where the oracle stops it."""

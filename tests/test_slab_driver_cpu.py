@@ -160,3 +160,13 @@ def test_argument_checks():
         rk.problem.f = 1  # outside the arena
         assert lib.solve_slab(1, P, Cm, None, None, None) != 0
         assert b"arena" in lib.last_error()
+        # close(): arenas released (peer mappings unmapped first in a distributed group), idempotent, no solve afterwards
+        with SlabGroup.local((8, 6, 8), 3, np.float64, 0.1, 1.0, 1.0, False, da.Jacobi(), world=2) as g2:
+            g2.setup([np.ones((4, 6, 8)), np.ones((4, 6, 8))])
+            g2.solve(2)
+            g2.check()
+            np.testing.assert_allclose(np.concatenate(g2.results(), axis=0), 1.0, rtol=0, atol=1e-15)  # a constant is a fixed point
+        assert all(rk.arena is None for rk in g2.ranks)
+        g2.close()
+        with pytest.raises(AssertionError):
+            g2.solve(1)
