@@ -67,8 +67,9 @@ class MGHierarchy:
         self.xa = [e.empty_fields(1) for e in self.levels]
         self.xb = [e.empty_fields(1) for e in self.levels]
         self.res = [e.empty_fields(1) for e in self.levels[:-1]]
-        self.cycles = 0
-        self._keep = []
+        self.cycles = 0  # V-cycles run so far: the first one descends through the `first` hierarchy
+        self._keep = []  # scaled coefficient fields (the tvdk_coef_t structs hold raw pointers)
+        self.maps = {}  # name -> (block-averaged fine-level field, problems it spans)
         nlev = len(self.levels)
         if not self.hetero:
             self.omega, self.ell = float(omega), float(ell)
@@ -76,7 +77,6 @@ class MGHierarchy:
             el = [e.coef(self.ell)[0] for e in self.levels]  # smoother: the h = 1 diagonal on every level
             el_h = [e.coef(self.ell / float(4 ** lv))[0] for lv, e in enumerate(self.levels)]  # residual: ell / h^2
             self.coefs = {w: [(om[lv], el[lv], el_h[lv]) for lv in range(nlev)] for w in ("first", "stat")}
-            self.maps = {}
             return
         om_f, om_s = self._chains(omega, full_shape, "omega", scale=False)
         el_f, el_s = self._chains(ell, full_shape, "ell", scale=True)
@@ -115,7 +115,6 @@ class MGHierarchy:
                 lib.check(lib.mg_prolong_add(C.byref(geoms[lv]), C.byref(geoms[lv + 1]), stat[lv + 1].data_ptr(), up.data_ptr(),
                                              e.stream()), "tvdk_mg_prolong_add")
             stat[lv] = up
-        self.maps = getattr(self, "maps", {})
         self.maps[name] = (stat[0], nbc)  # what the reference leaves in mass_coeff / diffusion_coeff after a cycle
 
         def as_coefs(fields):
