@@ -2695,9 +2695,11 @@ TVDK_DEV void tma_load_3d(void* dst, const TmaMap* m, int x, int y, int z, unsig
 #ifndef TVDK_TMA_NS
 #define TVDK_TMA_NS 3
 #endif
-template <typename T, bool ISO>
+template <typename T, bool ISO, int DD = 3>
 struct KFusedJ1T {
-  static constexpr int D = 3;
+  static_assert(DD == 3 || (DD == 2 && !ISO), "the 2-D variant is anisotropic only");
+  static constexpr int D = DD;
+  static constexpr int DX = D - 1;  // index of the x component of t (the contiguous axis)
   static constexpr int V = Vec<T>::N;
   static constexpr int LH = 0, RH = 1, NRED = 1;
   static constexpr int NS = TVDK_TMA_NS;
@@ -2706,6 +2708,10 @@ struct KFusedJ1T {
   // vs 0.82 with 32 x 16; five CTAs of 40 KB per SM instead of one of 148 KB), 16 x 12 for fp32 (0.91 vs 0.86)
   static constexpr int NTX3D = 16;
   static constexpr int NTY3D = sizeof(T) == 4 ? 12 : 8;
+  // 2-D (BASELINE config 1): the "plane" of the march is one image row, a CTA is a strip of ntx vectors; a TMA box holds at
+  // most 256 elements per axis, so (ntx + 2) V <= 256: 64 threads (fp64; 96 is the cap) / 32 threads (fp32)
+  static constexpr int NTX2D_MAX = ((256 / V - 2) / 32) * 32;
+  static constexpr int NTX2D = sizeof(T) == 8 ? 64 : 32;
   static constexpr bool TMA = true;
   typedef Col<T, D, LH, RH, 0, 1> C;
   struct Args {
@@ -2731,6 +2737,7 @@ struct KFusedJ1T {
     return which == 0 ? (ntx + 2) * V : which == 1 ? ntx * V : ISO ? (ntx + 1) * V : (which == 4 ? (ntx + 1) * V : ntx * V);
   }
   static TVDK_HD int box_h(int which, int nty) {
+    if (D == 2) return 1;  // (no y axis: every box is one row high; T1 is not fetched at all)
     return which == 0 ? nty + 2 : which == 1 ? nty : ISO ? nty + 1 : (which == 3 ? nty + 1 : nty);
   }
   static TVDK_HD Lay layout(int ntx, int nty) {
@@ -2743,6 +2750,7 @@ struct KFusedJ1T {
     L.pT2 = box_w(4, ntx);
     int b[5];
     for (int i = 0; i < 5; ++i) b[i] = box_w(i, ntx) * box_h(i, nty) * W;
+    if (D == 2) b[3] = 0;
     L.oU = 0;
     L.oF = L.oU + a128(b[0]);
     L.oT0 = L.oF + a128(b[1]);
@@ -2790,6 +2798,13 @@ struct KFusedJ1T {
     unsigned char* s = stage_at(smem, idx);
     mbar_expect_tx(b, L.tx_bytes);
     const int z = zb + p;
+    if (D == 2) {  // rows of a 2-D image: tensor (x, 1, nb * n0)
+      tma_load_3d(s + L.oU, &a.tm_u, x0b - V, 0, z, b);
+      tma_load_3d(s + L.oF, &a.tm_f, x0b, 0, z, b);
+      tma_load_3d(s + L.oT0, &a.tm_t0, x0b, 0, z, b);
+      tma_load_3d(s + L.oT2, &a.tm_t2, x0b - V, 0, z, b);
+      return;
+    }
     tma_load_3d(s + L.oU, &a.tm_u, x0b - V, y0b - 1, z, b);
     tma_load_3d(s + L.oF, &a.tm_f, x0b, y0b, z, b);
     if (ISO) {
@@ -2851,13 +2866,13 @@ struct KFusedJ1T {
     txt = lc.ntx * V;
     const int xt = lc.bx % a.g.xtiles, yt = lc.bx / a.g.xtiles;
     x0b = xt * C::iw(lc.ntx);
-    y0b = yt * C::ih(lc.nty);
+    y0b = D == 3 ? yt * C::ih(lc.nty) : 0;
     zb = c.b * a.g.n0;
     // (no halo threads on the low side: a tile that STARTS at the boundary must take the selecting path too; and
     //  u+ is formed on every thread row / vector, so a tile whose last thread row / vector reaches the last image
     //  row / column needs the edge-replicating selects as well)
-    c.edge = c.edge || x0b == 0 || y0b == 0 || x0b + lc.ntx * V >= a.g.nx || y0b + lc.nty >= a.g.ny;
-    iU = (lc.ty + 1) * L.pU + (lc.tx + 1) * V;
+    c.edge = c.edge || x0b == 0 || x0b + lc.ntx * V >= a.g.nx || (D == 3 && (y0b == 0 || y0b + lc.nty >= a.g.ny));
+    iU = (D == 3 ? (lc.ty + 1) * L.pU : 0) + (lc.tx + 1) * V;
     iF = lc.ty * L.pF + lc.tx * V;
     if (ISO) {
       iT0 = iT1 = iT2 = (lc.ty + 1) * L.pT0 + (lc.tx + 1) * V;
@@ -2930,14 +2945,19 @@ struct KFusedJ1T {
       if (c.has_zhi(a.g, j)) u_hi = vload(reinterpret_cast<const T*>(stage_at(smem, sr1) + L.oU) + iU);
       const Vec<T> f = vload(reinterpret_cast<const T*>(sj + L.oF) + iF);
       const Vec<T> t0 = vload(reinterpret_cast<const T*>(sj + L.oT0) + iT0);
-      const Vec<T> t1 = vload(T1 + iT1), t1m = vload(T1 + iT1 - L.pT1);
+      Vec<T> t1 = t0, t1m = t0, ym = u_c, yp = u_c;
+      if (D == 3) {
+        t1 = vload(T1 + iT1);
+        t1m = vload(T1 + iT1 - L.pT1);
+        ym = vload(U + iU - L.pU);
+        yp = vload(U + iU + L.pU);
+      }
       const Vec<T> t2 = vload(T2 + iT2);
       const T t2l = T2[iT2 - 1];
-      const Vec<T> ym = vload(U + iU - L.pU), yp = vload(U + iU + L.pU);
       const T xl = U[iU - 1], xr = U[iU + V];
       Vec<T> w1, w2, w1m;
       T w2l, bdummy;
-      if (ISO) {
+      if constexpr (ISO) {
         const T* P = phiring(smem, slot);
         const Vec<T> phm = vload(P + iT0 - L.pT0);
         bwphi(t2l, P[iT0 - 1], sc, bdummy, w2l);
@@ -2953,9 +2973,11 @@ struct KFusedJ1T {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
           bw1(t0.v[v], sc, b_cur[0].v[v], w0_cur.v[v]);
-          bw1(t1.v[v], sc, b_cur[1].v[v], w1.v[v]);
-          bw1(t2.v[v], sc, b_cur[2].v[v], w2.v[v]);
-          bw1(t1m.v[v], sc, bdummy, w1m.v[v]);
+          if (D == 3) {
+            bw1(t1.v[v], sc, b_cur[D == 3 ? 1 : 0].v[v], w1.v[v]);
+            bw1(t1m.v[v], sc, bdummy, w1m.v[v]);
+          }
+          bw1(t2.v[v], sc, b_cur[DX].v[v], w2.v[v]);
         }
       }
       // rhs = omega f + H_0 w_0 + H_1 w_1 + H_2 w_2 in the reference's order (:84-89), then the sweep (jacobi.py:112-114)
@@ -2964,12 +2986,14 @@ struct KFusedJ1T {
       for (int v = 0; v < V; ++v) {
         T rhs = sc.omega * f.v[v];
         if (zlo) rhs += w0_cur.v[v] - w0_prev.v[v];
-        if (c.template YLO<E>()) rhs += w1.v[v] - w1m.v[v];
+        if (D == 3 && c.template YLO<E>()) rhs += w1.v[v] - w1m.v[v];
         const T wl = v > 0 ? w2.v[v > 0 ? v - 1 : 0] : w2l;
         if (c.template HL<E>(v)) rhs += w2.v[v] - wl;
         T nb = u_lo.v[v] + u_hi.v[v];
-        nb += c.template YLO<E>() ? ym.v[v] : u_c.v[v];
-        nb += c.template YHI<E>() ? yp.v[v] : u_c.v[v];
+        if (D == 3) {
+          nb += c.template YLO<E>() ? ym.v[v] : u_c.v[v];
+          nb += c.template YHI<E>() ? yp.v[v] : u_c.v[v];
+        }
         const T left = v > 0 ? u_c.v[v > 0 ? v - 1 : 0] : xl;
         const T right = v < V - 1 ? u_c.v[v < V - 1 ? v + 1 : 0] : xr;
         nb += c.template HL<E>(v) ? left : u_c.v[v];
@@ -2983,16 +3007,17 @@ struct KFusedJ1T {
       const int zo = j - 1;
       const long long oo = c.cur - c.s0b;
       const T* R = ring(smem, slot ^ 1);
-      const Vec<T> yp = vload(R + iF + L.pF);
+      Vec<T> yp = up_prev;
+      if (D == 3) yp = vload(R + iF + L.pF);
       const T xr = R[iF + V];
       const bool zhi = c.template ZHI<E>(a.g, zo);
       Vec<T> tn[D];
 #pragma unroll
       for (int v = 0; v < V; ++v) {
         tn[0].v[v] = (zhi ? up.v[v] - up_prev.v[v] : (T)0) + b_prev[0].v[v];
-        tn[1].v[v] = (c.template YHI<E>() ? yp.v[v] - up_prev.v[v] : (T)0) + b_prev[1].v[v];
+        if (D == 3) tn[D == 3 ? 1 : 0].v[v] = (c.template YHI<E>() ? yp.v[v] - up_prev.v[v] : (T)0) + b_prev[D == 3 ? 1 : 0].v[v];
         const T right = v < V - 1 ? up_prev.v[v < V - 1 ? v + 1 : 0] : xr;
-        tn[2].v[v] = (c.template HR<E>(v) ? right - up_prev.v[v] : (T)0) + b_prev[2].v[v];
+        tn[DX].v[v] = (c.template HR<E>(v) ? right - up_prev.v[v] : (T)0) + b_prev[DX].v[v];
       }
       sto(c, a.u_out, oo, up_prev);
 #pragma unroll

@@ -130,6 +130,14 @@ struct KernelNty3<K, std::void_t<decltype(K::NTY3D)>> {
   static int get(bool) { return K::NTY3D; }
 };
 template <class K, typename = void>
+struct KernelNtx2 : std::integral_constant<int, 128> {};
+template <class K>
+struct KernelNtx2<K, std::void_t<decltype(K::NTX2D)>> : std::integral_constant<int, K::NTX2D> {};
+template <class K, typename = void>
+struct KernelNtx2Max : std::integral_constant<int, 1024> {};
+template <class K>
+struct KernelNtx2Max<K, std::void_t<decltype(K::NTX2D_MAX)>> : std::integral_constant<int, K::NTX2D_MAX> {};
+template <class K, typename = void>
 struct KernelIsTma : std::false_type {};
 template <class K>
 struct KernelIsTma<K, std::void_t<decltype(K::TMA)>> : std::bool_constant<K::TMA> {};
@@ -216,7 +224,8 @@ static thread_local Tune g_tune = {0, 0, 0};
 // TVDK_ALTERNATE=0 switches it off (A/B runs).  The results do not depend on it (same per-voxel arithmetic, reductions
 // summed by logical chunk index).
 static thread_local int g_alternate = 0;  // 0: off ; 1 / 2: next launch ascending / descending
-static thread_local int g_force_variants = 0;  // tvdk_problem_t.fused >= 2: take every implemented kernel variant
+static thread_local int g_force_variants = 0;  // tvdk_problem_t.fused == 2: take every implemented kernel variant
+static thread_local int g_force_tma2d = 0;     // tvdk_problem_t.fused == 4: the 2-D TMA-staged fused kernel whatever TVDK_TMA2D says
 static bool alternate_enabled() {
   static const int v = env_int("TVDK_ALTERNATE", 1);
   return v != 0;
@@ -251,9 +260,10 @@ static LaunchCfg plan_launch(Geom g, const Tune& tune, bool big_tile) {
   const int halo_x = C::LHX + C::RHX;
   const int need_x = (g.nx + V - 1) / V + halo_x;  // vectors to cover one row incl. halo
   if (D == 2) {
-    int ntx = tune.tile_x > 0 ? round_up(tune.tile_x, 32) : 128;
+    int ntx = tune.tile_x > 0 ? round_up(tune.tile_x, 32) : KernelNtx2<K>::value;
     ntx = std::min(ntx, round_up(need_x, 32));
     ntx = std::min(ntx, KernelMaxT<K>::value);
+    ntx = std::min(ntx, KernelNtx2Max<K>::value);  // (TMA-staged kernels: a box holds at most 256 elements per axis)
     ntx = std::max(ntx, 32);
     L.ntx = ntx;
     L.nty = 1;
@@ -359,6 +369,8 @@ static size_t partial_capacity(const Geom& g, const Tune& tune) {
   if constexpr (D == 2) {
     LaunchCfg x2 = plan_launch<KFusedJ1x2<T, false, false>, T, D>(g, tune, true);
     m = std::max(m, (size_t)x2.gx * x2.gy * x2.gz * 2);
+    LaunchCfg tm = plan_launch<KFusedJ1T<T, false, 2>, T, D>(g, tune, true);
+    m = std::max(m, (size_t)tm.gx * tm.gy * tm.gz * 2);
   }
   for (const LaunchCfg* L : {&a, &b, &c, &d}) m = std::max(m, (size_t)L->gx * L->gy * L->gz * 2);
   m = std::max(m, (size_t)e.gx * e.gy * e.gz * 4);
@@ -409,13 +421,24 @@ static int field_map(TmaMap* m, const T* base, const Geom& g, int bx, int by) {
                              g.s0 * (long long)sizeof(T), bx, by);
 }
 
-// K1 for 3-D problems with scalar coefficients: the TMA-staged kernel
-template <typename T, bool ISO>
+// ... and for 2-D images (anisotropic, scalar coefficients; BASELINE config 1): off by default until measured, TVDK_TMA2D=1
+#ifndef TVDK_TMA2D_DEFAULT
+#define TVDK_TMA2D_DEFAULT 0
+#endif
+static bool tma2d_enabled() {
+  static const int v = env_int("TVDK_TMA2D", TVDK_TMA2D_DEFAULT);
+  return v != 0;
+}
+
+// K1 for problems with scalar coefficients: the TMA-staged kernel (3-D; 2-D anisotropic)
+template <typename T, bool ISO, int D = 3>
 static int run_fj1_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const T* f, const T* u_in, T* u_out, const T* t_in,
                        T* t_out, long long tcs_in, long long tcs_out, const tvdk_stat_t* skip, const Fin& fin, const Scratch& sc,
                        void* stream) {
-  typedef KFusedJ1T<T, ISO> K;
-  LaunchCfg L = plan_launch<K, T, 3>(g, tune, true);
+  typedef KFusedJ1T<T, ISO, D> K;
+  LaunchCfg L = plan_launch<K, T, D>(g, tune, true);
+  static const bool trace = env_int("TVDK_TRACE_ROUTE", 0) != 0;
+  if (trace) fprintf(stderr, "[route] KFusedJ1T D=%d ntx=%d nty=%d grid=%d x %d x %d smem=%zu zchunk=%d\n", D, L.ntx, L.nty, L.gx, L.gy, L.gz, L.smem, L.g.zchunk);
   typename K::Args a;
   memset(&a, 0, sizeof a);
   a.g = L.g;
@@ -429,8 +452,9 @@ static int run_fj1_tma(const Geom& g, const Tune& tune, const Coefs<T>& k, const
   TVDK_TRY(field_map(&a.tm_u, u_in, L.g, K::box_w(0, L.ntx), K::box_h(0, L.nty)));
   TVDK_TRY(field_map(&a.tm_f, f, L.g, K::box_w(1, L.ntx), K::box_h(1, L.nty)));
   TVDK_TRY(field_map(&a.tm_t0, t_in, L.g, K::box_w(2, L.ntx), K::box_h(2, L.nty)));
-  TVDK_TRY(field_map(&a.tm_t1, t_in + tcs_in, L.g, K::box_w(3, L.ntx), K::box_h(3, L.nty)));
-  TVDK_TRY(field_map(&a.tm_t2, t_in + 2 * tcs_in, L.g, K::box_w(4, L.ntx), K::box_h(4, L.nty)));
+  // (2-D: there is no y component; its map stays a valid descriptor that is never used)
+  TVDK_TRY(field_map(&a.tm_t1, t_in + (D == 3 ? tcs_in : 0), L.g, K::box_w(3, L.ntx), K::box_h(3, L.nty)));
+  TVDK_TRY(field_map(&a.tm_t2, t_in + (D - 1) * tcs_in, L.g, K::box_w(4, L.ntx), K::box_h(4, L.nty)));
   if ((size_t)L.gx * L.gy * L.gz * K::NRED > sc.partial_cap) return fail(TVDK_ERR_WORKSPACE, "internal: partial buffer too small");
   ++g_launches;
   return backend::launch_tma<K>(a, L.gx, L.gy, L.gz, L.ntx, L.nty, L.smem, stream, sc.partials, sc.counters);
@@ -477,6 +501,10 @@ static int run_fj1(bool iso, bool het, const Geom& g, const Tune& tune, const Co
         return run_fj1_tma<T, true>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
       if (!iso) return run_fj1_tma<T, false>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
     }
+  }
+  if constexpr (D == 2) {
+    if (!het && !iso && tma_enabled() && (tma2d_enabled() || g_force_variants || g_force_tma2d))
+      return run_fj1_tma<T, false, 2>(g, tune, k, f, u_in, u_out, t_in, t_out, tcs_in, tcs_out, skip, fin, sc, stream);
   }
   return dispatch2(iso, het, [&](auto I, auto H) {
     typedef KFusedJ1<T, D, decltype(I)::value, decltype(H)::value> K;
@@ -1111,10 +1139,12 @@ int tvdk_solve(const tvdk_problem_t* p, void* stream, int* iters_launched) {
   int rc = 0;
   TVDK_RANGE("tvdk_solve");
   g_alternate = alternate_enabled() ? 1 : 0;
-  g_force_variants = p->fused >= 2 ? 1 : 0;
+  g_force_variants = p->fused == 2 ? 1 : 0;
+  g_force_tma2d = p->fused == 4 ? 1 : 0;
   TVDK_DISPATCH(p->geom, rc = (solve_impl<T, D>(p, stream, iters_launched)));
   g_alternate = 0;
   g_force_variants = 0;
+  g_force_tma2d = 0;
   return rc;
 }
 

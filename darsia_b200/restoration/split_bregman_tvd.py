@@ -98,7 +98,8 @@ def split_bregman_tvd(
             ``x0`` (``split_bregman_tvd.py:93-97``), so consecutive frames of a series can be warm-started.
         fused: kernel route (``tvdk_problem_t.fused``): True / 1 = fused and temporally blocked kernels where
             they measured faster (default); False / 0 = one building-block kernel per step; 2 = every
-            blocked variant wherever it is implemented; 3 = as 1 but one outer iteration per launch.
+            blocked variant wherever it is implemented; 3 = as 1 but one outer iteration per launch; 4 = as 1 with the
+            TMA-staged fused kernel for 2-D anisotropic Jacobi(1) problems with scalar coefficients.
             All routes compute the same numbers (tests compare them).
         tile: (block_x, block_y, planes_per_block) launch-shape override, 0 = default (tuning/tests).
     Device-resident callers: ``img`` (and ``x0``, ``mu``, ``omega``, ``ell``) may be

@@ -130,7 +130,9 @@ typedef struct tvdk_problem {
                             * 2 = take every temporally blocked / single-pass variant wherever it is implemented,
                             *     not only where it measured faster (3-D single-pass CG and blocked sweeps,
                             *     K1x2 pairs for isotropic / per-voxel / fp32 problems and small images),
-                            * 3 = as 1 but one outer iteration per launch (no K1x2 pairs) */
+                            * 3 = as 1 but one outer iteration per launch (no K1x2 pairs),
+                            * 4 = as 1, with the TMA-staged fused Jacobi(1) kernel for 2-D anisotropic problems with
+                            *     scalar coefficients whatever the environment variable TVDK_TMA2D says */
   int32_t tile_x, tile_y, zchunk; /* 0 = library default; thread-block shape / planes per CTA */
   /* `adaptive` schedule (split_bregman_tvd.py:26, :149-158): HOST array of max_num_iter flags,
    * adaptive_mask[it] != 0 <=> adaptive(it) is true: after the shrinkage of iteration `it`

@@ -16,7 +16,7 @@ from parity_cases import (adaptive_cases, cg_fixed_count_cases, check_mg_standal
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
-from tma_cases import run_stencil_case, run_tma_case, stencil_cases, tma_cases
+from tma_cases import run_stencil_case, run_tma2d_case, run_tma_case, stencil_cases, tma2d_cases, tma_cases
 
 import darsia_b200 as da
 
@@ -246,6 +246,19 @@ def test_tma_staged_fused_jacobi1_3d(shape, batch, tile, dtype, nit, iso):
     """KFusedJ1T (3-D anisotropic Jacobi(1), scalar coefficients): the TMA boxes are emulated by a zero-filling copy."""
     out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit, iso)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+    nb = max(1, int(np.prod(batch, dtype=int)))
+    assert list(info.iters) == [nit] * nb
+    np.testing.assert_allclose(info.history[:nit].reshape(-1), np.array(hist).reshape(nb, nit).T.reshape(-1),
+                               rtol=1e-9 if dtype == np.float64 else 1e-3)
+
+
+@pytest.mark.parametrize("shape,batch,tile,dtype,nit", tma2d_cases())
+def test_tma_staged_fused_jacobi1_2d(shape, batch, tile, dtype, nit):
+    """KFusedJ1T<T, false, 2> (2-D anisotropic Jacobi(1), scalar coefficients; fused = 4) against the oracle and the
+    march kernel."""
+    out, ref, info, hist, march = run_tma2d_case(da, oracle, shape, batch, tile, dtype, nit)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+    assert rel_l2(out, march) <= (1e-14 if dtype == np.float64 else 1e-6)
     nb = max(1, int(np.prod(batch, dtype=int)))
     assert list(info.iters) == [nit] * nb
     np.testing.assert_allclose(info.history[:nit].reshape(-1), np.array(hist).reshape(nb, nit).T.reshape(-1),

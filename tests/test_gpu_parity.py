@@ -14,7 +14,7 @@ from parity_cases import (adaptive_cases, cg_fixed_count_cases, chambolle_cases,
                           run_adaptive_pair, run_cg_fixed_pair, run_jacobi1_pair, run_jacobi_blocked_pair, run_pair,
                           small_grid)
 
-from tma_cases import run_stencil_case, run_tma_case, stencil_cases, tma_cases
+from tma_cases import run_stencil_case, run_tma2d_case, run_tma_case, stencil_cases, tma2d_cases, tma_cases
 
 pytestmark = pytest.mark.gpu
 
@@ -325,6 +325,22 @@ def test_tma_staged_fused_jacobi1_3d(da, shape, batch, tile, dtype, nit, iso):
     """KFusedJ1T on the B200: cp.async.bulk.tensor boxes + mbarrier ring against the oracle (and the march kernel's bar)."""
     out, ref, info, hist = run_tma_case(da, oracle, shape, batch, tile, dtype, nit, iso)
     assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+    nb = max(1, int(np.prod(batch, dtype=int)))
+    assert list(info.iters) == [nit] * nb
+    np.testing.assert_allclose(info.history[:nit].reshape(-1), np.array(hist).reshape(nb, nit).T.reshape(-1),
+                               rtol=1e-9 if dtype == np.float64 else 1e-3)
+
+
+@pytest.mark.parametrize("shape,batch,tile,dtype,nit", tma2d_cases() + [((447, 795), (), (0, 0, 0), np.float64, 12),
+                                                                           ((1788, 3180), (), (0, 0, 0), np.float64, 4),
+                                                                           ((300, 1000), (2,), (96, 0, 0), np.float64, 6),
+                                                                           ((500, 700), (), (0, 0, 0), np.float32, 8)])
+def test_tma_staged_fused_jacobi1_2d(da, shape, batch, tile, dtype, nit):
+    """KFusedJ1T<T, false, 2> on the B200 (fused = 4): row boxes through cp.async.bulk.tensor + mbarrier ring against the
+    oracle and the march kernel."""
+    out, ref, info, hist, march = run_tma2d_case(da, oracle, shape, batch, tile, dtype, nit)
+    assert rel_l2(out, ref) <= (1e-13 if dtype == np.float64 else 2e-6)
+    assert rel_l2(out, march) <= (1e-14 if dtype == np.float64 else 1e-6)
     nb = max(1, int(np.prod(batch, dtype=int)))
     assert list(info.iters) == [nit] * nb
     np.testing.assert_allclose(info.history[:nit].reshape(-1), np.array(hist).reshape(nb, nit).T.reshape(-1),

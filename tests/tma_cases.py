@@ -62,3 +62,38 @@ def run_stencil_case(da, oracle, shape, tile, dtype, solver):
     ref = oracle.split_bregman_tvd(img, solver=mk(oracle), **kw)
     out = da.split_bregman_tvd(img, solver=mk(da), tile=tile, **kw)
     return out, ref
+
+
+def tma2d_cases():
+    """2-D anisotropic Jacobi(1) through the TMA-staged kernel (KFusedJ1T<T, false, 2>: the march "plane" is one image row,
+    a CTA a strip of columns): shape, batch, tile (threads, -, rows per CTA), dtype, outer iterations."""
+    f8, f4 = np.float64, np.float32
+    return [
+        ((37, 150), (), (32, 0, 5), f8, 6),
+        ((37, 150), (), (32, 0, 5), f4, 6),
+        ((37, 150), (2,), (32, 0, 7), f8, 5),
+        ((41, 300), (), (0, 0, 0), f8, 6),
+        ((70, 300), (), (64, 0, 0), f8, 7),
+        ((33, 126), (), (0, 0, 0), f8, 4),   # one tile whose halo vector is the last image column
+        ((33, 127), (), (0, 0, 0), f8, 4),
+        ((33, 128), (), (0, 0, 0), f8, 4),
+        ((33, 252), (), (0, 0, 0), f8, 4),
+        ((33, 124), (), (0, 0, 0), f4, 4),
+        ((33, 125), (), (0, 0, 0), f4, 4),
+        ((20, 62), (), (32, 0, 3), f8, 4),
+        ((3, 40), (), (0, 0, 0), f8, 6),
+        ((1, 40), (), (0, 0, 0), f8, 4),
+        ((2, 7), (), (0, 0, 0), f8, 5),
+        ((5, 9), (3,), (0, 0, 1), f4, 3),
+        ((64, 1), (), (0, 0, 0), f8, 3),
+    ]
+
+
+def run_tma2d_case(da, oracle, shape, batch, tile, dtype, nit):
+    img = phantom(tuple(shape) + tuple(batch), 13, dtype)
+    kw = dict(mu=0.1, omega=1.3, ell=0.9, dim=2, max_num_iter=nit, isotropic=False)
+    hist = []
+    ref = oracle.split_bregman_tvd(img, solver=oracle.Jacobi(maxiter=1), history=hist, **kw)
+    out, info = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=1), tile=tile, return_info=True, fused=4, **kw)
+    march = da.split_bregman_tvd(img, solver=da.Jacobi(maxiter=1), tile=tile, fused=3, **kw)  # K1, one iteration per launch
+    return out, ref, info, hist, march
