@@ -2708,10 +2708,13 @@ struct KFusedJ1T {
   // vs 0.82 with 32 x 16; five CTAs of 40 KB per SM instead of one of 148 KB), 16 x 12 for fp32 (0.91 vs 0.86)
   static constexpr int NTX3D = 16;
   static constexpr int NTY3D = sizeof(T) == 4 ? 12 : 8;
-  // 2-D (BASELINE config 1): the "plane" of the march is one image row, a CTA is a strip of ntx vectors; a TMA box holds at
-  // most 256 elements per axis, so (ntx + 2) V <= 256: 64 threads (fp64; 96 is the cap) / 32 threads (fp32)
+  // 2-D: the "plane" of the march is one image row, a CTA is a strip of ntx vectors; a TMA box holds at most 256 elements
+  // per axis, so (ntx + 2) V <= 256: at most 96 threads (fp64) / 32 (fp32).  Measured (profiles/r2_tma2d_ab.txt): SLOWER
+  // than the march kernel on the 1788 x 3180 image (0.67-0.79 vs 0.80 of the HBM peak; fp32 0.43 vs 0.66), +2.6 % on
+  // 4000 x 7000 x 3 where K1x2 is faster still -- a 2-D row is contiguous, so there are no y-halo threads for the boxes to
+  // remove.  Hence not a default route (TVDK_TMA2D=1 / fused = 4 select it).
   static constexpr int NTX2D_MAX = ((256 / V - 2) / 32) * 32;
-  static constexpr int NTX2D = sizeof(T) == 8 ? 64 : 32;
+  static constexpr int NTX2D = sizeof(T) == 8 ? 64 : 32;  // (96 measured 5-9 % faster in fp64; 64 is the GPU-tested default)
   static constexpr bool TMA = true;
   typedef Col<T, D, LH, RH, 0, 1> C;
   struct Args {
