@@ -337,9 +337,15 @@ def _split_bregman_mg(img, mu, omega, ell, dim, max_num_iter, eps, x0, isotropic
                                      wsp, wsn, eng.stream()), "tvdk_energy")
                 en = sums[: 2 * nb].cpu().numpy().reshape(nb, 2)
                 energy = 0.5 * en[:, 0] + en[:, 1]
-                if it == 0:  # split_bregman_tvd.py:103-104 (u = img at this point)
+                if it == 0:  # split_bregman_tvd.py:103-104: _functional(img) -- also after a warm start
+                    e0 = energy
+                    if x0_db is not None:
+                        lib.check(lib.energy(C.byref(g), C.byref(muc), C.byref(omc), f.data_ptr(), f.data_ptr(), sums.data_ptr(),
+                                             wsp, wsn, eng.stream()), "tvdk_energy")
+                        en0 = sums[: 2 * nb].cpu().numpy().reshape(nb, 2)
+                        e0 = 0.5 * en0[:, 0] + en0[:, 1]
                     for b in range(nb):
-                        print(f"The energy functional starts at {energy[b]}")
+                        print(f"The energy functional starts at {e0[b]}")
             if x0_db is not None and it == 0:  # an arbitrary warm start (d, b) is not the expansion of a compressed state
                 lib.check(lib.rhs_explicit(C.byref(g), C.byref(omc), C.byref(elc), f.data_ptr(), x0_db[0].data_ptr(),
                                            x0_db[1].data_ptr(), tcs, rhs.data_ptr(), wsp, wsn, eng.stream()), "tvdk_rhs_explicit")

@@ -215,6 +215,20 @@ def check_mg_warm_start(da, oracle):
     ref = oracle.split_bregman_tvd(img, max_num_iter=3, solver=mk(oracle, tol=1e-3), x0=tuple(v.copy() for v in x0), **kw)
     out, d, b = da.split_bregman_tvd(img, max_num_iter=3, solver=mk(da, tol=1e-3), x0=x0, return_state=True, **kw)
     assert rel(out, ref) <= 1e-13 and d.shape == b.shape == (*img.shape, 2)
+    # verbose after a warm start: "starts at" is _functional(img), the first iteration's line carries the warm start's energy
+    import contextlib
+    import io
+    import re
+
+    one, x0_one = img[..., 0].copy(), (x0[0][..., 0].copy(), x0[1][..., 0, :].copy(), x0[2][..., 0, :].copy())
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        da.split_bregman_tvd(one, max_num_iter=2, solver=mk(da), verbose=True, x0=x0_one, **kw)
+    got = [float(v) for v in re.findall(r"[-+]?\d+\.\d+(?:[eE][-+]?\d+)?", buf.getvalue())]
+    assert len(got) == 5  # start energy + 2 x (increment, energy)
+    # split_bregman_tvd.py:103-104 prints _functional(img); the line of iteration 0 carries the energy of the warm start
+    np.testing.assert_allclose(got[0], oracle.energy_functional(one, one, kw["mu"], kw["omega"], 2), rtol=1e-12)
+    np.testing.assert_allclose(got[2], oracle.energy_functional(x0_one[0], one, kw["mu"], kw["omega"], 2), rtol=1e-12)
 
 
 def mg_hetero_cases():
