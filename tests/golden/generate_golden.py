@@ -269,6 +269,13 @@ def h1_cases(da):
     store["vol_cg"] = da.H1_regularization(vol.copy(), mu=0.5, omega=2.0, dim=3, solver=da.CG(maxiter=8, tol=0.0))
     store["vol_mg"] = da.H1_regularization(vol.copy(), mu=1.0, omega=1.0, dim=3,
                                            solver=da.MG(depth=1, smoother_iterations=3, maxiter=4))  # examples/regularization.py:39
+    # MG with per-voxel coefficients given to its constructor (mg.py:70-73); H1 passes omega / mu on as mass / diffusion
+    vol_om = coeff_field(vol.shape, 53, 0.5, 2.0)
+    vol_mu = coeff_field(vol.shape, 54, 0.5, 1.5)
+    store["vol_om"], store["vol_mu"] = vol_om, vol_mu
+    store["vol_mg_hetero"] = da.H1_regularization(
+        vol.copy(), mu=vol_mu.copy(), omega=vol_om.copy(), dim=3,
+        solver=da.MG(depth=1, smoother_iterations=3, maxiter=3, dim=3, mass_coeff=vol_om.copy(), diffusion_coeff=vol_mu.copy()))
     rgb = phantom((23, 31, 3), 52)
     store["rgb"] = rgb
     store["rgb_jac5"] = da.H1_regularization(rgb.copy(), mu=0.7, omega=1.0, dim=2, solver=da.Jacobi(maxiter=5))

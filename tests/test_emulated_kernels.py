@@ -102,7 +102,7 @@ def test_eps_stops_each_problem_at_the_reference_iteration():
         np.testing.assert_allclose(info.history[: len(h), b], h, rtol=1e-9)
 
 
-@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol", "vol_mg"])
+@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol", "vol_mg", "vol_mg_hetero"])
 def test_h1_regularization_golden(name):
     import h1_cases
 

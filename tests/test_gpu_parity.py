@@ -175,7 +175,7 @@ def test_standalone_solvers(da):
         assert rel_l2(mk(da)(x0=x0, rhs=rhs), s_ref(x0=x0, rhs=rhs)) < 1e-12
 
 
-@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol", "vol_mg"])
+@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol", "vol_mg", "vol_mg_hetero"])
 def test_h1_regularization_golden(da, name):
     import h1_cases
 

@@ -122,7 +122,7 @@ def test_oracle_properties():
         oracle.split_bregman_tvd((img * 255).astype(np.uint8))
 
 
-@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol", "vol_mg"])
+@pytest.mark.parametrize("name", ["vol_jac_tol", "vol_cg", "rgb_jac5", "rgb_jac_tol", "vol_mg", "vol_mg_hetero"])
 def test_oracle_h1_regularization(name):
     import h1_cases
 
