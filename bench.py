@@ -525,6 +525,8 @@ def run_ours(args, w, wname):
     roofline = {
         "bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": ncu_traffic(f"{dom_key}:{wname}"), "peak_source": peak_src,
+        "traffic_source": "profiles/ncu_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture "
+                          "of this kernel on this workload (committed; not re-measured in this run)",
         "frac_of_8TBs_spec": achieved / 8000.0,  # north_star quotes the ~8 TB/s nominal HBM3e figure
         "algo_bytes_per_launch": dom_bytes, "avg_launch_ms": dom_ms,
         "timed": "the kernel alone, 20 back-to-back launches after the timed steps (burst, like the measured peak)",
