@@ -1,7 +1,7 @@
 """CPU, build container only: the NumPy oracle against the VERBATIM reference on seeded random problems.
 
 Runs only where ``/root/reference`` exists (it does not exist on the GPU box, and nothing marked ``gpu`` ever
-reads it).  The committed fixtures (tests/golden/*.npz) pin the oracle on 36 chosen cases; this test widens the
+reads it).  The committed fixtures (tests/golden/*.npz) pin the oracle on 42 chosen cases; this test widens the
 pin to random shapes / coefficients / solvers, restricted to what the reference itself can run (SURVEY Q3/Q5/Q6:
 no trailing batch axes; isotropic only for 2-D fp64 with scalar mu and ell).  The reference is executed in a
 subprocess because loading it installs stub ``darsia`` / ``skimage`` modules and the SciPy ``tol`` shim."""
@@ -67,3 +67,50 @@ def test_oracle_matches_verbatim_reference_on_random_problems():
     res = subprocess.run([sys.executable, "-c", SCRIPT, ROOT], capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
     assert res.stdout.strip().splitlines()[-1].startswith("ok 30")
+
+
+SCRIPT_MG = r'''
+import sys
+import numpy as np
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, sys.argv[1] + "/tests"); sys.path.insert(0, sys.argv[1] + "/tests/golden")
+import generate_golden as gg
+import oracle
+ref = gg.load_reference()
+rng = np.random.default_rng(77)
+worst = 0.0
+for n in range(16):
+    dim = int(rng.choice([2, 3]))
+    depth = int(rng.integers(0, 3))
+    lo = 2 ** (depth + 1)
+    shape = tuple(int(v) for v in rng.integers(lo, 40 if dim == 2 else 15, dim))
+    img = gg.phantom(shape, int(rng.integers(0, 10**6)))
+    which = str(rng.choice(["both", "omega", "ell"]))
+    om = gg.coeff_field(shape, 7 + n, 0.5, 2.0) if which in ("both", "omega") else float(rng.choice([0.5, 1.0, 2.0]))
+    el = gg.coeff_field(shape, 5 + n, 0.5, 1.5) if which in ("both", "ell") else float(rng.choice([0.5, 1.0]))
+    cp = lambda c: c.copy() if isinstance(c, np.ndarray) else c
+    tol = None if rng.random() < 0.7 else 1e-3
+    def mk(api):
+        # (heterogeneous is decided by the constructor's arguments, mg.py:70-73)
+        return api.MG(depth=depth, smoother_iterations=int(rng_k), maxiter=int(rng_m), tol=tol, dim=dim,
+                      mass_coeff=cp(om) if isinstance(om, np.ndarray) else None,
+                      diffusion_coeff=cp(el) if isinstance(el, np.ndarray) else None)
+    rng_k, rng_m = rng.integers(1, 5), rng.integers(1, 4)
+    common = dict(dim=dim, max_num_iter=int(rng.integers(1, 5)), isotropic=bool(rng.random() < 0.3) and dim == 2 and not isinstance(el, np.ndarray),
+                  mu=0.1, omega=cp(om), ell=cp(el))
+    a = ref.split_bregman_tvd(img.copy(), solver=mk(ref), **common)
+    common["omega"], common["ell"] = cp(om), cp(el)
+    b = oracle.split_bregman_tvd(img.copy(), solver=mk(oracle), **common)
+    err = float(np.linalg.norm(a - b) / np.linalg.norm(a))
+    assert a.shape == b.shape and err <= 1e-13, (shape, depth, which, tol, common["max_num_iter"], err)
+    worst = max(worst, err)
+print("ok 16 worst", worst)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout is only present in the build container")
+def test_oracle_matches_verbatim_reference_mg_with_per_voxel_coefficients():
+    """MG constructed with per-voxel mass / diffusion coefficients (mg.py:70-73, 134-149, 170-192): random shapes (odd
+    extents on every level), depths 0-2, either or both coefficients as arrays, with and without the MG tolerance."""
+    res = subprocess.run([sys.executable, "-c", SCRIPT_MG, ROOT], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert res.stdout.strip().splitlines()[-1].startswith("ok 16")
