@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
+import threading
 from dataclasses import dataclass
 from typing import Optional, Sequence, Tuple, Union
 
@@ -123,7 +124,8 @@ class Engine:
             return t.to(self.device, non_blocking=True)
         return self._stage_pageable(t)
 
-    _STAGE: dict = {}  # (thread, device index, dtype) -> two pinned chunks, reused by every engine of that thread
+    _STAGE: dict = {}  # (device index, dtype, chunk) -> free pairs of pinned chunks (a call borrows one pair)
+    _STAGE_LOCK = threading.Lock()
     _STAGE_POOL = None
     # host threads copying into the pinned chunks / chunk size (tools/h2d_probe.py measures both on a given box)
     # (B200 box, 672 MB fp64: 1 thread 12 GB/s, 4 threads 34 GB/s, pinned source 55 GB/s -- profiles/r2_h2d_probe.txt;
@@ -138,16 +140,16 @@ class Engine:
         stages internally on one thread: 11 GB/s on the 672 MB image of BASELINE configs[1])."""
         chunk = (Engine.STAGE_CHUNK_MB << 20) // t.element_size()
         nt = max(1, Engine.STAGE_THREADS)
-        import threading
+        key = (self.device.index, t.dtype, chunk)
+        with Engine._STAGE_LOCK:  # (concurrent callers -- tvd_series' two host threads -- each borrow their own pair)
+            free = Engine._STAGE.setdefault(key, [])
+            bufs = free.pop() if free else None
+            if nt > 1 and Engine._STAGE_POOL is None:
+                from concurrent.futures import ThreadPoolExecutor
 
-        key = (threading.get_ident(), self.device.index, t.dtype, chunk)
-        bufs = Engine._STAGE.get(key)
+                Engine._STAGE_POOL = ThreadPoolExecutor(nt)
         if bufs is None:
-            bufs = Engine._STAGE[key] = [torch.empty(chunk, dtype=t.dtype, pin_memory=True) for _ in range(2)]
-        if nt > 1 and Engine._STAGE_POOL is None:
-            from concurrent.futures import ThreadPoolExecutor
-
-            Engine._STAGE_POOL = ThreadPoolExecutor(nt)
+            bufs = [torch.empty(chunk, dtype=t.dtype, pin_memory=True) for _ in range(2)]
         out = torch.empty(t.numel(), dtype=t.dtype, device=self.device)
         src = t.numpy()
         evs = [None, None]
@@ -171,6 +173,8 @@ class Engine:
         for ev in evs:  # the staging chunks are shared: do not hand them to the next caller while a DMA still reads them
             if ev is not None:
                 ev.synchronize()
+        with Engine._STAGE_LOCK:
+            Engine._STAGE[key].append(bufs)
         return out
 
     def pack(self, inter: torch.Tensor, nb: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
